@@ -1,0 +1,254 @@
+/* sadmc_gpu.h -- C ABI of the B200 walker engine (libsadmc_gpu.so).
+ *
+ * This is the drop-in boundary for ONE path of droundy/sad-monte-carlo: the
+ * propose / dE / accept loop of `EnergyMC::move_once` (src/mc/energy.rs:904-974)
+ * over the `System`/`ConfirmSystem`/`MovableSystem` traits
+ * (src/system/mod.rs:54-120), for thousands of independent walkers at once.
+ *
+ * The reference has no FFI for this path (it is Rust generics,
+ * `EnergyMC<S: MovableSystem>` energy.rs:827).  A per-move FFI call would be
+ * slower than the CPU move itself, so the boundary sits one level up: the host
+ * asks the engine to advance ALL walkers by `n` moves, where `n` is what the
+ * reference's `PluginManager::run` computes as the next `period`
+ * (src/mc/plugin.rs:93-144).  Report/Save/Movie stay on the host.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function
+ * returns 0 on success or a negative sadmc_status; the message for the last
+ * failure of the calling thread is sadmc_last_error().  Nothing unwinds across
+ * this boundary (the reference panics instead: ising.rs:39, wca.rs:186-191,
+ * two_wells.rs:240-245, lj.rs:259).  A handle is single-owner and not
+ * thread-safe (the reference's MC is `&mut self` everywhere).  `Option<f64>`
+ * fields of the reference are doubles where NaN means `None`.
+ *
+ * There is NO CPU fallback: sadmc_create fails with SADMC_ERR_CUDA when no
+ * device is usable.
+ */
+#ifndef SADMC_GPU_H
+#define SADMC_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SADMC_ABI_VERSION 1
+
+typedef enum {
+  SADMC_OK = 0,
+  SADMC_ERR_INVALID = -1,     /* bad config / argument (reference: panic!/assert!) */
+  SADMC_ERR_CUDA = -2,        /* CUDA runtime failure, or no device              */
+  SADMC_ERR_WINDOW = -3,      /* a walker's energy left the device bin window     */
+  SADMC_ERR_UNSUPPORTED = -4, /* valid in the reference, not built here           */
+  SADMC_ERR_VERIFY = -5       /* verify_energy failed (lj.rs:249-261 etc.)        */
+} sadmc_status;
+
+/* AnyParams variants, src/system/any.rs:10-27 */
+typedef enum {
+  SADMC_SYS_FAKE = 1,        /* fake.rs            */
+  SADMC_SYS_FAKE_ERFINV = 2, /* erfinv.rs          */
+  SADMC_SYS_WCA = 3,         /* wca.rs + optcell.rs */
+  SADMC_SYS_LJ = 4,          /* lj.rs              */
+  SADMC_SYS_ISING = 6,       /* ising.rs           */
+  SADMC_SYS_SW = 7,          /* optsquare.rs       */
+  SADMC_SYS_TWO_WELLS = 8    /* two_wells.rs       */
+} sadmc_system_kind;
+
+/* fake::Function, src/system/fake.rs:12-36 */
+typedef enum {
+  SADMC_FAKE_LINEAR = 0,
+  SADMC_FAKE_QUADRATIC = 1,
+  SADMC_FAKE_PIECES = 2,
+  SADMC_FAKE_GAUSSIAN = 3
+} sadmc_fake_function;
+
+/* MethodParams, src/mc/energy.rs:44-69 (Method at run time: 213-244) */
+typedef enum {
+  SADMC_METHOD_SAD = 1,
+  SADMC_METHOD_SAMC = 2,
+  SADMC_METHOD_WL = 3,
+  SADMC_METHOD_INV_T_WL = 4,
+  SADMC_METHOD_CANONICAL = 5
+} sadmc_method_kind;
+
+/* MoveParams, src/mc/energy.rs:73-78 */
+typedef enum { SADMC_MOVE_TRANSLATION_SCALE = 0, SADMC_MOVE_ACCEPTANCE_RATE = 1 } sadmc_move_plan;
+
+/* How walker w gets its first configuration. */
+typedef enum {
+  /* The reference constructor (`Any::from(AnyParams)`, any.rs:80-93): every
+   * walker starts from the SAME configuration; walker w then equals a
+   * reference process run with `--seed (seed+w)`. */
+  SADMC_INIT_REFERENCE = 0,
+  /* `System::randomize` (e.g. lj.rs:262-279) driven by the walker's own MC
+   * stream, then the reference's downhill relaxation (energy.rs:840-851).
+   * Used by the throughput configs ("synthetic random-start walkers"). */
+  SADMC_INIT_RANDOMIZE = 1,
+  /* Leave systems unset; the caller supplies them with sadmc_set_system and
+   * then calls sadmc_start (resume path, mc/mod.rs:70-84). */
+  SADMC_INIT_EXTERNAL = 2
+} sadmc_init_mode;
+
+#define SADMC_FLAG_NO_ROUND_TRIPS 1u /* skip energy.rs:950-965 diagnostics (never read by the sampler) */
+#define SADMC_FLAG_SUM_TREE 2u       /* reserved (oracle only): sum LJ pair terms in the kernel's lane order */
+
+typedef struct sadmc_config {
+  uint32_t abi_version; /* = SADMC_ABI_VERSION */
+  int32_t system;       /* sadmc_system_kind */
+
+  /* --- system parameters (the `--<sys>-*` flags of the reference CLI) --- */
+  uint32_t N;              /* ising N (ising.rs:14) | lj N (lj.rs:16) | wca N (wca.rs:375) | sw N |
+                              two-wells N (two_wells.rs:15) | erfinv N | fake quadratic `dimensions` */
+  double lj_radius;        /* lj.rs:18 */
+  double reduced_density;  /* wca: CellDimensionsGivenNumber::ReducedDensity (wca.rs:365) */
+  double filling_fraction; /* sw: FillingFraction (optsquare.rs:337) */
+  double cell_width[3];    /* wca/sw: CellWidth; used when cell_width[0] > 0 */
+  double sw_well_width;    /* optsquare.rs:345 */
+  int32_t fake_function;   /* sadmc_fake_function */
+  int32_t _pad0;
+  double fake_a, fake_b, fake_e1, fake_e2; /* Function::Pieces, fake.rs:21-30 */
+  double fake_sigma;                       /* Function::Gaussian, fake.rs:32-35 */
+  double tw_h2_to_h1, tw_barrier_over_h1, tw_r2; /* two_wells.rs:13-22 */
+  double erfinv_mean_energy;                     /* erfinv.rs:12-15 */
+
+  /* --- EnergyMCParams, energy.rs:82-97 --- */
+  int32_t method; /* sadmc_method_kind */
+  int32_t move_plan;
+  double sad_min_T;          /* MethodParams::Sad     */
+  double samc_t0;            /* MethodParams::Samc    */
+  double wl_min_gamma;       /* MethodParams::WL, NaN = None */
+  double canonical_T;        /* MethodParams::_Canonical */
+  uint64_t seed;             /* walker w (global index) is seeded `seed + w`; None == 0 (energy.rs:835) */
+  double energy_bin;         /* NaN = None -> delta_energy() or 1.0 (energy.rs:831-833) */
+  double min_allowed_energy; /* NaN = None */
+  double max_allowed_energy; /* NaN = None */
+  double move_value;         /* TranslationScale(sigma) or AcceptanceRate(r) */
+
+  /* --- engine --- */
+  uint32_t n_walkers;     /* walkers held by THIS engine (this GPU) */
+  uint32_t walker_offset; /* global index of local walker 0 (rank * n_walkers when sharded) */
+  int32_t device;         /* CUDA ordinal */
+  int32_t init_mode;      /* sadmc_init_mode */
+  /* Energy window [lo, hi) that the per-walker device bin arrays must cover.
+   * The reference grows its vectors without bound (energy.rs:400-434); the
+   * engine pre-allocates and a walker that leaves the window stops with
+   * SADMC_ERR_WINDOW.  NaN = derive from min/max_allowed_energy and the
+   * system's lowest_possible_energy(). */
+  double bin_window_lo, bin_window_hi;
+  int32_t lanes_per_walker; /* LJ only: 0 = auto, else 32,16,8,4 (threads cooperating on one walker) */
+  uint32_t flags;
+} sadmc_config;
+
+/* Per-walker scalars: the non-vector fields of `EnergyMC` (energy.rs:167-210)
+ * and of `Method` (213-244), as a checkpoint would hold them. */
+typedef struct sadmc_walker_state {
+  uint64_t moves, accepted_moves;
+  double acceptance_rate, translation_scale;
+  uint64_t rng_s0, rng_s1; /* rand_xoshiro serde fields s0,s1 */
+  double energy;           /* system.energy() */
+  double bins_min, bins_width;
+  uint32_t bins_len;     /* bins.lnw.len() */
+  uint32_t window_first; /* device window index of reference bin 0 */
+  int32_t method;        /* current sadmc_method_kind (1/t-WL may have become SAMC, energy.rs:754-756) */
+  int32_t status;        /* sadmc_status of this walker */
+  /* Sad */
+  double too_lo, too_hi, latest_parameter;
+  uint64_t tL, tF, num_states, highest_hist;
+  /* Samc */
+  double samc_t0;
+  /* WL */
+  double wl_gamma, wl_num_states, wl_min_energy;
+  uint64_t wl_lowest_hist, wl_highest_hist, wl_total_hist;
+  uint32_t wl_hist_len;
+  int32_t wl_inv_t;
+  /* round trips */
+  double max_S;
+  uint32_t max_S_index; /* reference index (relative to bins_min) */
+  uint32_t _pad;
+} sadmc_walker_state;
+
+typedef struct sadmc_engine sadmc_engine;
+
+/* ---- lifecycle --------------------------------------------------------- */
+/* `EnergyMC::from_params` for every walker (energy.rs:830-898) + the system
+ * constructor selected by cfg->init_mode. */
+int sadmc_create(const sadmc_config* cfg, sadmc_engine** out);
+void sadmc_destroy(sadmc_engine* e);
+const char* sadmc_last_error(void);
+int sadmc_abi_version(void);
+
+/* With SADMC_INIT_EXTERNAL: finish from_params (relaxation + first bin) after
+ * the systems were supplied. */
+int sadmc_start(sadmc_engine* e);
+
+/* Launch on this CUDA stream (a cudaStream_t) instead of the engine's own. */
+int sadmc_set_stream(sadmc_engine* e, void* cuda_stream);
+void* sadmc_get_stream(sadmc_engine* e);
+
+/* ---- the hot path ------------------------------------------------------ */
+/* n_moves x `move_once` (energy.rs:904-974) for every walker.  Blocking. */
+int sadmc_run(sadmc_engine* e, uint64_t n_moves);
+/* Same, but only enqueues on the engine's stream. */
+int sadmc_run_async(sadmc_engine* e, uint64_t n_moves);
+int sadmc_sync(sadmc_engine* e);
+/* Device time of the move kernel(s) of the last sadmc_run, CUDA events. */
+int sadmc_last_run_ms(sadmc_engine* e, float* ms);
+/* How many kernels of this library have been launched by this engine. */
+int sadmc_launch_count(sadmc_engine* e, uint64_t* n);
+
+/* ---- state out (what Report/Save/Movie and the parity tests read) ------ */
+int sadmc_num_moves(sadmc_engine* e, uint64_t* moves);                  /* MonteCarlo::num_moves, energy.rs:981 */
+int sadmc_num_accepted_moves(sadmc_engine* e, uint64_t* accepted_sum);  /* energy.rs:984, summed over walkers */
+int sadmc_get_walker(sadmc_engine* e, uint32_t w, sadmc_walker_state* out);
+int sadmc_get_energies(sadmc_engine* e, double* energies /* [n_walkers] */);
+/* `Bins` (energy.rs:146-163) + round-trip vectors (203-205) of walker w, in
+ * reference index order (element 0 = bin at bins_min).  Any pointer may be
+ * NULL.  `cap` is the capacity of every non-NULL array; fails if < bins_len. */
+int sadmc_get_bins(sadmc_engine* e, uint32_t w, uint32_t cap, uint64_t* histogram, uint64_t* t_found,
+                   double* lnw, double* energy_total, double* energy_squared_total,
+                   uint64_t* round_trips, uint8_t* have_visited_since_maxentropy, uint64_t* wl_hist,
+                   double* extra_total, uint64_t* extra_count);
+/* System configuration of walker w as f64s.  Layout: LJ/WCA/SW: x0,y0,z0,x1,..
+ * (3N), then E, then error (WCA/LJ; 0 for SW).  Fake/ErfInv/TwoWells:
+ * position[dim] (+ d_squared for two-wells).  Ising: N*N spins as +-1.0, then E. */
+int sadmc_system_len(sadmc_engine* e, size_t* n_doubles);
+int sadmc_get_system(sadmc_engine* e, uint32_t w, double* buf, size_t n);
+int sadmc_set_system(sadmc_engine* e, uint32_t w, const double* buf, size_t n);
+/* Bulk variants: [n_walkers][system_len] row-major host buffers. */
+int sadmc_get_systems(sadmc_engine* e, double* buf, size_t n);
+int sadmc_set_systems(sadmc_engine* e, const double* buf, size_t n);
+int sadmc_get_rngs(sadmc_engine* e, uint64_t* s /* [n_walkers][2] */);
+int sadmc_set_rngs(sadmc_engine* e, const uint64_t* s /* [n_walkers][2] */);
+
+/* ---- window geometry ---------------------------------------------------- */
+/* Device window: bin j of every walker covers [lo + j*width, lo + (j+1)*width). */
+int sadmc_window(sadmc_engine* e, double* lo, double* width, uint32_t* nbins);
+
+/* ---- merge for reporting ------------------------------------------------ */
+/* Fold the local walkers' bins into window-aligned sums, written to DEVICE
+ * buffers of length nbins (caller-owned, e.g. torch tensors; a following
+ * NCCL all-reduce(sum) merges GPUs): histogram (u64), energy_total,
+ * energy_squared_total (f64), lnw_sum / lnw_sq_sum / lnw_count: sum, sum of
+ * squares and number of walkers contributing their max-aligned lnw
+ * (plotting/parse-binning.py:169 alignment).  Any pointer may be NULL. */
+int sadmc_fold_device(sadmc_engine* e, void* d_histogram, void* d_energy_total, void* d_energy_squared_total,
+                      void* d_lnw_sum, void* d_lnw_sq_sum, void* d_lnw_count);
+/* Same into HOST buffers (single-GPU convenience). */
+int sadmc_fold(sadmc_engine* e, uint64_t* histogram, double* energy_total, double* energy_squared_total,
+               double* lnw_sum, double* lnw_sq_sum, uint64_t* lnw_count);
+
+/* ---- trait-shaped single-walker shims (src/system/mod.rs:54-120) -------- */
+/* For parity tests and for a Rust `impl MovableSystem for GpuSystem`.  Each is
+ * one tiny kernel launch; never use them in a loop that matters. */
+int sadmc_sys_energy(sadmc_engine* e, uint32_t w, double* energy);            /* System::energy          */
+int sadmc_sys_compute_energy(sadmc_engine* e, uint32_t w, double* energy);    /* System::compute_energy  */
+/* MovableSystem::plan_move: draws from walker w's RNG; *some = 0 is `None`. */
+int sadmc_sys_plan_move(sadmc_engine* e, uint32_t w, double mean_distance, int* some, double* e_new);
+int sadmc_sys_confirm(sadmc_engine* e, uint32_t w);                           /* ConfirmSystem::confirm  */
+int sadmc_sys_verify_energy(sadmc_engine* e, uint32_t w);                     /* System::verify_energy   */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SADMC_GPU_H */

@@ -1,0 +1,350 @@
+// oracle_capi.cpp -- TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+//
+// extern "C" face of the CPU oracle, loaded by tests/ (ctypes), by
+// __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs.
+// Nothing under sad_monte_carlo_b200/ may link or load this library.
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+
+#include "../include/sadmc_gpu.h" // config / state structs only (shared vocabulary with the engine)
+#include "oracle_mc.hpp"
+
+namespace oracle {
+
+// statrs 0.7 `erf_inv` (erfinv.rs:66) is an un-vendored dependency whose
+// coefficient tables are not reproducible from memory; restated instead as
+// Newton iterations on libm erf from the Winitzki starting guess -- accurate to
+// a few ulp, which is inside the floating-point tier (1e-12) of this system.
+double erf_inv(double x) {
+  if (x <= -1.0) return -INFINITY;
+  if (x >= 1.0) return INFINITY;
+  if (x == 0.0) return 0.0;
+  const double a = 0.147;
+  const double ln1mx2 = std::log(1.0 - x * x);
+  const double t = 2.0 / (M_PI * a) + 0.5 * ln1mx2;
+  double y = std::sqrt(std::sqrt(t * t - ln1mx2 / a) - t);
+  if (x < 0) y = -y;
+  for (int it = 0; it < 4; it++) {
+    const double err = std::erf(y) - x;
+    const double d = 2.0 / std::sqrt(M_PI) * std::exp(-y * y);
+    // Halley step
+    y -= err / (d + y * err);
+  }
+  return y;
+}
+
+// Test-only: pair sum of Lj::move_atom in the order of the kernel's
+// lanes_per_walker = G layout (atom a -> lane a % G, slot a / G; per-lane
+// sequential over slots, then an xor butterfly), with the kernel's pair
+// arithmetic (sad_monte_carlo_b200/csrc/sys_lj.cuh: fma-contracted r^2).
+double Lj::move_atom_tree(size_t which, Vec3 r) const {
+  const int G = tree_lanes;
+  const Vec3 from = positions[which];
+  std::vector<double> lane(G, 0.0);
+  auto r2 = [](const Vec3& a, const Vec3& b) {
+    const double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+    return std::fma(dz, dz, std::fma(dy, dy, dx * dx));
+  };
+  auto pot = [](double rr) {
+    const double s = 1.0 / rr;
+    const double s3 = s * s * s;
+    return std::fma(s3, s3, -s3);
+  };
+  for (size_t k = 0; k < positions.size(); k++) {
+    if (k == which) continue;
+    lane[k % G] += pot(r2(positions[k], r)) - pot(r2(positions[k], from));
+  }
+  for (int off = G / 2; off >= 1; off >>= 1) {
+    std::vector<double> nxt(G);
+    for (int l = 0; l < G; l++) nxt[l] = lane[l] + lane[l ^ off];
+    lane.swap(nxt);
+  }
+  return E + 4.0 * lane[0];
+}
+
+static thread_local std::string g_err;
+
+static Vec3 box_from_config(const sadmc_config& c, bool sw) {
+  if (c.cell_width[0] > 0) return Vec3(std::fabs(c.cell_width[0]), std::fabs(c.cell_width[1]), std::fabs(c.cell_width[2]));
+  double vol;
+  if (sw)
+    vol = (double)c.N * (M_PI * 1.0 * 1.0 * 1.0 / 6.0) / c.filling_fraction; // optsquare.rs:365-367
+  else
+    vol = (double)c.N / c.reduced_density; // wca.rs:399-401
+  const double w = std::cbrt(vol);         // optcell.rs:47-50
+  return Vec3(w, w, w);
+}
+
+static std::unique_ptr<System> make_system(const sadmc_config& c, uint64_t attempts_override) {
+  const bool ref = c.init_mode == SADMC_INIT_REFERENCE;
+  switch (c.system) {
+    case SADMC_SYS_ISING: return std::unique_ptr<System>(new Ising(c.N));
+    case SADMC_SYS_LJ:
+      if (ref) return std::unique_ptr<System>(attempts_override ? new Lj(c.N, c.lj_radius, attempts_override, 100000000ull) : new Lj(c.N, c.lj_radius));
+      return std::unique_ptr<System>(new Lj(c.N, c.lj_radius, Lj::Empty()));
+    case SADMC_SYS_WCA:
+      if (ref) return std::unique_ptr<System>(new Wca(Wca::from_n(c.N, box_from_config(c, false), attempts_override ? attempts_override : ~0ull)));
+      {
+        Wca* w = new Wca(Cell(box_from_config(c, false), Wca::r_cutoff()));
+        w->cell.positions.assign(c.N, Vec3());
+        w->cell.update_caches();
+        return std::unique_ptr<System>(w);
+      }
+    case SADMC_SYS_SW:
+      if (ref) return std::unique_ptr<System>(new SquareWell(SquareWell::from_n(c.N, box_from_config(c, true), c.sw_well_width)));
+      {
+        SquareWell* s = new SquareWell(Cell(box_from_config(c, true), c.sw_well_width));
+        s->cell.positions.assign(c.N, Vec3());
+        s->cell.update_caches();
+        return std::unique_ptr<System>(s);
+      }
+    case SADMC_SYS_FAKE:
+      return std::unique_ptr<System>(new Fake((Fake::Kind)c.fake_function, c.N, c.fake_a, c.fake_b, c.fake_e1, c.fake_e2, c.fake_sigma));
+    case SADMC_SYS_TWO_WELLS: return std::unique_ptr<System>(new TwoWells(c.N, c.tw_h2_to_h1, c.tw_barrier_over_h1, c.tw_r2));
+    case SADMC_SYS_FAKE_ERFINV: return std::unique_ptr<System>(new ErfInv(c.N, c.erfinv_mean_energy));
+  }
+  throw std::invalid_argument("unknown system kind");
+}
+
+static MCParams mc_params(const sadmc_config& c, uint32_t walker) {
+  MCParams p;
+  p.method = c.method;
+  p.sad_min_T = c.sad_min_T;
+  p.samc_t0 = c.samc_t0;
+  p.wl_min_gamma = c.wl_min_gamma;
+  p.canonical_T = c.canonical_T;
+  p.seed = c.seed + walker;
+  p.energy_bin = c.energy_bin;
+  p.min_allowed_energy = c.min_allowed_energy;
+  p.max_allowed_energy = c.max_allowed_energy;
+  p.acceptance_rate_plan = c.move_plan == SADMC_MOVE_ACCEPTANCE_RATE;
+  p.move_value = c.move_value;
+  p.randomize_first = c.init_mode == SADMC_INIT_RANDOMIZE;
+  return p;
+}
+
+} // namespace oracle
+
+using namespace oracle;
+
+struct oracle_mc {
+  std::unique_ptr<EnergyMC> mc;
+  sadmc_config cfg;
+};
+
+extern "C" {
+
+const char* oracle_last_error(void) { return g_err.c_str(); }
+
+void oracle_set_math_mode(int use_libm) { MathMode::use_libm() = use_libm != 0; }
+
+// Walker `walker` (global index) of the configuration `cfg`: the reference process
+// `histogram <flags> --seed (cfg->seed + walker)`.  If `system_state` is non-NULL the
+// system is overwritten with it before from_params runs (SADMC_INIT_EXTERNAL).
+// `attempts_override` != 0 shrinks the constructor's attempt count (tests only).
+oracle_mc* oracle_create(const sadmc_config* cfg, uint32_t walker, const double* system_state, size_t n_state,
+                         uint64_t attempts_override) {
+  try {
+    std::unique_ptr<System> sys = make_system(*cfg, attempts_override);
+    if (system_state) sys->set_state(std::vector<double>(system_state, system_state + n_state));
+    oracle_mc* o = new oracle_mc;
+    o->cfg = *cfg;
+    MCParams p = mc_params(*cfg, walker);
+    if (system_state) p.randomize_first = false;
+    o->mc.reset(new EnergyMC(p, std::move(sys)));
+    return o;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return nullptr;
+  }
+}
+void oracle_destroy(oracle_mc* o) { delete o; }
+
+int oracle_set_lj_tree_lanes(oracle_mc* o, int lanes) {
+  Lj* lj = dynamic_cast<Lj*>(o->mc->system.get());
+  if (!lj) return -1;
+  lj->tree_lanes = lanes;
+  return 0;
+}
+
+int oracle_run(oracle_mc* o, uint64_t n) {
+  try {
+    for (uint64_t k = 0; k < n; k++) o->mc->move_once();
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+
+int oracle_get_walker(oracle_mc* o, sadmc_walker_state* s) {
+  const EnergyMC& m = *o->mc;
+  std::memset(s, 0, sizeof(*s));
+  s->moves = m.moves;
+  s->accepted_moves = m.accepted_moves;
+  s->acceptance_rate = m.acceptance_rate;
+  s->translation_scale = m.translation_scale;
+  s->rng_s0 = m.rng.s0;
+  s->rng_s1 = m.rng.s1;
+  s->energy = m.system->energy();
+  s->bins_min = m.bins.min;
+  s->bins_width = m.bins.width;
+  s->bins_len = (uint32_t)m.bins.lnw.size();
+  s->window_first = 0;
+  const Method& me = m.method;
+  s->method = me.kind == M_WL ? (me.inv_t ? SADMC_METHOD_INV_T_WL : SADMC_METHOD_WL) : me.kind;
+  s->status = m.verify_failures ? SADMC_ERR_VERIFY : 0;
+  s->too_lo = me.too_lo;
+  s->too_hi = me.too_hi;
+  s->latest_parameter = me.latest_parameter;
+  s->tL = me.tL;
+  s->tF = me.tF;
+  s->num_states = me.num_states;
+  s->highest_hist = me.highest_hist;
+  s->samc_t0 = me.t0;
+  s->wl_gamma = me.gamma;
+  s->wl_num_states = me.wl_num_states;
+  s->wl_min_energy = me.min_energy;
+  s->wl_lowest_hist = me.wl_lowest_hist;
+  s->wl_highest_hist = me.wl_highest_hist;
+  s->wl_total_hist = me.wl_total_hist;
+  s->wl_hist_len = (uint32_t)me.hist.size();
+  s->wl_inv_t = me.inv_t;
+  s->max_S = m.max_S;
+  s->max_S_index = (uint32_t)m.max_S_index;
+  return 0;
+}
+
+int oracle_get_bins(oracle_mc* o, uint32_t cap, uint64_t* histogram, uint64_t* t_found, double* lnw, double* energy_total,
+                    double* energy_squared_total, uint64_t* round_trips, uint8_t* have_visited, uint64_t* wl_hist,
+                    double* extra_total, uint64_t* extra_count) {
+  const EnergyMC& m = *o->mc;
+  const size_t n = m.bins.lnw.size();
+  if (cap < n) {
+    g_err = "capacity too small";
+    return -1;
+  }
+  for (size_t i = 0; i < n; i++) {
+    if (histogram) histogram[i] = m.bins.histogram[i];
+    if (t_found) t_found[i] = m.bins.t_found[i];
+    if (lnw) lnw[i] = m.bins.lnw[i];
+    if (energy_total) energy_total[i] = m.bins.energy_total[i];
+    if (energy_squared_total) energy_squared_total[i] = m.bins.energy_squared_total[i];
+    if (round_trips) round_trips[i] = m.round_trips[i];
+    if (have_visited) have_visited[i] = m.have_visited_since_maxentropy[i];
+    if (wl_hist) wl_hist[i] = i < m.method.hist.size() ? m.method.hist[i] : 0;
+    if (extra_total) extra_total[i] = 0;
+    if (extra_count) extra_count[i] = 0;
+  }
+  if (!m.bins.extra.empty()) {
+    const BinCounts& b = m.bins.extra.begin()->second;
+    for (size_t i = 0; i < n && i < b.total.size(); i++) {
+      if (extra_total) extra_total[i] = b.total[i];
+      if (extra_count) extra_count[i] = b.count[i];
+    }
+  }
+  return 0;
+}
+
+size_t oracle_system_len(oracle_mc* o) { return o->mc->system->get_state().size(); }
+int oracle_get_system(oracle_mc* o, double* buf, size_t n) {
+  const std::vector<double> s = o->mc->system->get_state();
+  if (n < s.size()) return -1;
+  std::memcpy(buf, s.data(), s.size() * sizeof(double));
+  return 0;
+}
+int oracle_set_system(oracle_mc* o, const double* buf, size_t n) {
+  o->mc->system->set_state(std::vector<double>(buf, buf + n));
+  return 0;
+}
+int oracle_set_rng(oracle_mc* o, uint64_t s0, uint64_t s1) {
+  o->mc->rng.s0 = s0;
+  o->mc->rng.s1 = s1;
+  return 0;
+}
+
+// trait-shaped shims, src/system/mod.rs:54-120
+double oracle_sys_energy(oracle_mc* o) { return o->mc->system->energy(); }
+double oracle_sys_compute_energy(oracle_mc* o) { return o->mc->system->compute_energy(); }
+int oracle_sys_plan_move(oracle_mc* o, double mean_distance, int* some, double* e_new) {
+  double e = 0;
+  *some = o->mc->system->plan_move(o->mc->rng, mean_distance, &e) ? 1 : 0;
+  *e_new = e;
+  return 0;
+}
+void oracle_sys_confirm(oracle_mc* o) { o->mc->system->confirm(); }
+int oracle_sys_verify_energy(oracle_mc* o) { return o->mc->system->verify_energy() ? 0 : SADMC_ERR_VERIFY; }
+// SquareWell only: the reference's slow all-image recount (optsquare.rs:108-152)
+double oracle_sw_compute_energy_slowly(oracle_mc* o) {
+  SquareWell* s = dynamic_cast<SquareWell*>(o->mc->system.get());
+  return s ? s->compute_energy_slowly() : NAN;
+}
+
+// ---- RNG / math probes for tests ----
+void oracle_rng_seed(uint64_t seed, uint64_t* s) {
+  Rng r = Rng::seed_from_u64(seed);
+  s[0] = r.s0;
+  s[1] = r.s1;
+}
+// kind: 0 next_u64, 1 gen_f64 (as bits), 2 gen_range_usize(0,n), 3 uniform_usize(0,n), 4 standard_normal (bits),
+//       5 uniform_f64(lo,hi) bits, 6 open01 bits, 7 gen_range_f64(lo,hi) bits
+void oracle_rng_stream(uint64_t* state, int kind, uint64_t n_arg, double lo, double hi, uint64_t count, uint64_t* out) {
+  Rng r;
+  r.s0 = state[0];
+  r.s1 = state[1];
+  for (uint64_t k = 0; k < count; k++) {
+    double d = 0;
+    switch (kind) {
+      case 0: out[k] = r.next_u64(); continue;
+      case 1: d = r.gen_f64(); break;
+      case 2: out[k] = r.gen_range_usize(0, n_arg); continue;
+      case 3: out[k] = r.uniform_usize(0, n_arg); continue;
+      case 4: d = r.standard_normal(); break;
+      case 5: d = r.uniform_f64(lo, hi); break;
+      case 6: d = r.open01(); break;
+      case 7: d = r.gen_range_f64(lo, hi); break;
+    }
+    std::memcpy(&out[k], &d, 8);
+  }
+  state[0] = r.s0;
+  state[1] = r.s1;
+}
+double oracle_exp(double x) { return sadmc_exp(x); }
+double oracle_log(double x) { return sadmc_log(x); }
+double oracle_erf_inv(double x) { return erf_inv(x); }
+void oracle_zig_tables(double* x, double* f) {
+  std::memcpy(x, ZIG_X, sizeof(ZIG_X));
+  std::memcpy(f, ZIG_F, sizeof(ZIG_F));
+}
+
+// ---- CPU baseline: one independent walker per thread, all on this host ----
+// Returns wall seconds for `n_moves` moves on each of `n_threads` walkers
+// (construction excluded).  Used by bench.py only.
+double oracle_bench(const sadmc_config* cfg, uint32_t n_threads, uint64_t warmup_moves, uint64_t n_moves) {
+  std::vector<oracle_mc*> w(n_threads, nullptr);
+  {
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < n_threads; t++)
+      th.emplace_back([&, t] {
+        w[t] = oracle_create(cfg, cfg->walker_offset + t, nullptr, 0, 0);
+        if (w[t]) oracle_run(w[t], warmup_moves);
+      });
+    for (auto& x : th) x.join();
+  }
+  for (auto* p : w)
+    if (!p) return -1.0;
+  const auto t0 = std::chrono::steady_clock::now();
+  {
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < n_threads; t++) th.emplace_back([&, t] { oracle_run(w[t], n_moves); });
+    for (auto& x : th) x.join();
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  for (auto* p : w) oracle_destroy(p);
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+} // extern "C"

@@ -1,0 +1,156 @@
+"""ctypes face of oracle/liboracle_sadmc.so -- the CPU oracle (test infrastructure)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from sad_monte_carlo_b200._abi import Config, WalkerState
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+
+u64p = C.POINTER(C.c_uint64)
+f64p = C.POINTER(C.c_double)
+u8p = C.POINTER(C.c_uint8)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def load_oracle():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    so = os.path.join(ROOT, "oracle", "liboracle_sadmc.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    L = C.CDLL(so)
+    L.oracle_last_error.restype = C.c_char_p
+    L.oracle_create.restype = C.c_void_p
+    L.oracle_create.argtypes = [C.POINTER(Config), C.c_uint32, f64p, C.c_size_t, C.c_uint64]
+    L.oracle_destroy.argtypes = [C.c_void_p]
+    L.oracle_run.argtypes = [C.c_void_p, C.c_uint64]
+    L.oracle_get_walker.argtypes = [C.c_void_p, C.POINTER(WalkerState)]
+    L.oracle_get_bins.argtypes = [C.c_void_p, C.c_uint32, u64p, u64p, f64p, f64p, f64p, u64p, u8p, u64p, f64p, u64p]
+    L.oracle_system_len.restype = C.c_size_t
+    L.oracle_system_len.argtypes = [C.c_void_p]
+    L.oracle_get_system.argtypes = [C.c_void_p, f64p, C.c_size_t]
+    L.oracle_set_system.argtypes = [C.c_void_p, f64p, C.c_size_t]
+    L.oracle_set_rng.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+    L.oracle_set_lj_tree_lanes.argtypes = [C.c_void_p, C.c_int]
+    L.oracle_sys_energy.restype = C.c_double
+    L.oracle_sys_energy.argtypes = [C.c_void_p]
+    L.oracle_sys_compute_energy.restype = C.c_double
+    L.oracle_sys_compute_energy.argtypes = [C.c_void_p]
+    L.oracle_sw_compute_energy_slowly.restype = C.c_double
+    L.oracle_sw_compute_energy_slowly.argtypes = [C.c_void_p]
+    L.oracle_sys_plan_move.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_int), f64p]
+    L.oracle_sys_confirm.argtypes = [C.c_void_p]
+    L.oracle_sys_verify_energy.argtypes = [C.c_void_p]
+    L.oracle_rng_seed.argtypes = [C.c_uint64, u64p]
+    L.oracle_rng_stream.argtypes = [u64p, C.c_int, C.c_uint64, C.c_double, C.c_double, C.c_uint64, u64p]
+    L.oracle_exp.restype = C.c_double
+    L.oracle_exp.argtypes = [C.c_double]
+    L.oracle_log.restype = C.c_double
+    L.oracle_log.argtypes = [C.c_double]
+    L.oracle_erf_inv.restype = C.c_double
+    L.oracle_erf_inv.argtypes = [C.c_double]
+    L.oracle_zig_tables.argtypes = [f64p, f64p]
+    L.oracle_bench.restype = C.c_double
+    L.oracle_bench.argtypes = [C.POINTER(Config), C.c_uint32, C.c_uint64, C.c_uint64]
+    L.oracle_set_math_mode.argtypes = [C.c_int]
+    _LIB = L
+    return L
+
+
+class OracleMC:
+    """One reference walker: `EnergyMC<Any>` of the reference, restated on the CPU."""
+
+    def __init__(self, cfg, walker=0, system_state=None, attempts_override=0):
+        self.L = load_oracle()
+        self.cfg = cfg
+        st = None
+        n = 0
+        if system_state is not None:
+            st = np.ascontiguousarray(system_state, dtype=np.float64)
+            n = st.size
+        self.h = self.L.oracle_create(C.byref(cfg), walker, _ptr(st, f64p), n, attempts_override)
+        if not self.h:
+            raise RuntimeError("oracle_create: " + self.L.oracle_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.oracle_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, n):
+        if self.L.oracle_run(self.h, int(n)) != 0:
+            raise RuntimeError("oracle_run: " + self.L.oracle_last_error().decode())
+
+    def walker(self):
+        s = WalkerState()
+        self.L.oracle_get_walker(self.h, C.byref(s))
+        return s
+
+    def bins(self):
+        n = self.walker().bins_len
+        out = {
+            "histogram": np.zeros(n, np.uint64), "t_found": np.zeros(n, np.uint64), "lnw": np.zeros(n),
+            "energy_total": np.zeros(n), "energy_squared_total": np.zeros(n),
+            "round_trips": np.zeros(n, np.uint64), "have_visited": np.zeros(n, np.uint8),
+            "wl_hist": np.zeros(n, np.uint64), "extra_total": np.zeros(n), "extra_count": np.zeros(n, np.uint64),
+        }
+        rc = self.L.oracle_get_bins(self.h, n, _ptr(out["histogram"], u64p), _ptr(out["t_found"], u64p),
+                                    _ptr(out["lnw"], f64p), _ptr(out["energy_total"], f64p),
+                                    _ptr(out["energy_squared_total"], f64p), _ptr(out["round_trips"], u64p),
+                                    _ptr(out["have_visited"], u8p), _ptr(out["wl_hist"], u64p),
+                                    _ptr(out["extra_total"], f64p), _ptr(out["extra_count"], u64p))
+        assert rc == 0
+        return out
+
+    def system(self):
+        n = self.L.oracle_system_len(self.h)
+        buf = np.zeros(n)
+        assert self.L.oracle_get_system(self.h, _ptr(buf, f64p), n) == 0
+        return buf
+
+    def set_system(self, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.float64)
+        self.L.oracle_set_system(self.h, _ptr(buf, f64p), buf.size)
+
+    def set_rng(self, s0, s1):
+        self.L.oracle_set_rng(self.h, int(s0), int(s1))
+
+    def energy(self):
+        return self.L.oracle_sys_energy(self.h)
+
+    def compute_energy(self):
+        return self.L.oracle_sys_compute_energy(self.h)
+
+    def plan_move(self, mean_distance):
+        some = C.c_int(0)
+        e = C.c_double(0)
+        self.L.oracle_sys_plan_move(self.h, mean_distance, C.byref(some), C.byref(e))
+        return (e.value if some.value else None)
+
+    def confirm(self):
+        self.L.oracle_sys_confirm(self.h)
+
+    def verify_energy(self):
+        return self.L.oracle_sys_verify_energy(self.h) == 0
+
+
+def rng_stream(state, kind, count, n_arg=0, lo=0.0, hi=1.0):
+    """Draw `count` values; `state` is a 2-element uint64 array, updated in place."""
+    L = load_oracle()
+    out = np.zeros(count, np.uint64)
+    L.oracle_rng_stream(_ptr(state, u64p), kind, n_arg, lo, hi, count, _ptr(out, u64p))
+    return out
