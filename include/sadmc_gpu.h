@@ -248,6 +248,11 @@ int sadmc_sys_plan_move(sadmc_engine* e, uint32_t w, double mean_distance, int* 
 int sadmc_sys_confirm(sadmc_engine* e, uint32_t w);                           /* ConfirmSystem::confirm  */
 int sadmc_sys_verify_energy(sadmc_engine* e, uint32_t w);                     /* System::verify_energy   */
 
+/* ---- measurement utility (bench.py) --------------------------------------- */
+/* Achievable FP64 FMA throughput of `device` in TFLOP/s (independent DFMA chains,
+ * best of `reps`): the denominator of the FP64 roofline fraction. */
+int sadmc_measure_fp64_peak(int device, int reps, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,27 @@ double Lj::move_atom_tree(size_t which, Vec3 r) const {
   return E + 4.0 * lane[0];
 }
 
+// Test-only: compute_energy in the kernel's order (sys_lj.cuh compute_energy).
+double Lj::compute_energy_tree() const {
+  const int G = tree_lanes;
+  const size_t n = positions.size();
+  std::vector<double> lane(G, 0.0);
+  for (size_t b = 1; b < n; b++)
+    for (size_t a = 0; a < b; a++) { // per lane: b ascending, then slot (a / G) ascending
+      const double dx = positions[a].x - positions[b].x, dy = positions[a].y - positions[b].y, dz = positions[a].z - positions[b].z;
+      const double rr = std::fma(dz, dz, std::fma(dy, dy, dx * dx));
+      const double s = 1.0 / rr;
+      const double s3 = s * s * s;
+      lane[a % G] += std::fma(s3, s3, -s3);
+    }
+  for (int off = G / 2; off >= 1; off >>= 1) {
+    std::vector<double> nxt(G);
+    for (int l = 0; l < G; l++) nxt[l] = lane[l] + lane[l ^ off];
+    lane.swap(nxt);
+  }
+  return 4.0 * lane[0];
+}
+
 static thread_local std::string g_err;
 
 static Vec3 box_from_config(const sadmc_config& c, bool sw) {
@@ -84,7 +105,11 @@ static std::unique_ptr<System> make_system(const sadmc_config& c, uint64_t attem
     case SADMC_SYS_ISING: return std::unique_ptr<System>(new Ising(c.N));
     case SADMC_SYS_LJ:
       if (ref) return std::unique_ptr<System>(attempts_override ? new Lj(c.N, c.lj_radius, attempts_override, 100000000ull) : new Lj(c.N, c.lj_radius));
-      return std::unique_ptr<System>(new Lj(c.N, c.lj_radius, Lj::Empty()));
+      {
+        Lj* lj = new Lj(c.N, c.lj_radius, Lj::Empty());
+        if (c.flags & SADMC_FLAG_SUM_TREE) lj->tree_lanes = c.lanes_per_walker ? c.lanes_per_walker : 8;
+        return std::unique_ptr<System>(lj);
+      }
     case SADMC_SYS_WCA:
       if (ref) return std::unique_ptr<System>(new Wca(Wca::from_n(c.N, box_from_config(c, false), attempts_override ? attempts_override : ~0ull)));
       {

@@ -207,7 +207,9 @@ struct Lj : System {
     }
   }
   double energy() const override { return E; }
+  double compute_energy_tree() const; // oracle_capi.cpp (test-only variant)
   double compute_energy() const override { // lj.rs:236-244
+    if (tree_lanes) return compute_energy_tree();
     double e = 0.0;
     for (size_t which = 0; which < positions.size(); which++)
       for (size_t k = 0; k < which; k++) e += potential((positions[which] - positions[k]).norm2());

@@ -1,0 +1,56 @@
+"""ctypes prototypes for every symbol include/sadmc_gpu.h declares."""
+import ctypes as C
+
+from ._abi import Config, WalkerState
+
+u64p = C.POINTER(C.c_uint64)
+f64p = C.POINTER(C.c_double)
+u8p = C.POINTER(C.c_uint8)
+vp = C.c_void_p
+
+# name -> (restype, argtypes); the list is also what tests/test_abi.py checks against the header
+PROTOTYPES = {
+    "sadmc_create": (C.c_int, [C.POINTER(Config), C.POINTER(vp)]),
+    "sadmc_destroy": (None, [vp]),
+    "sadmc_last_error": (C.c_char_p, []),
+    "sadmc_abi_version": (C.c_int, []),
+    "sadmc_start": (C.c_int, [vp]),
+    "sadmc_set_stream": (C.c_int, [vp, vp]),
+    "sadmc_get_stream": (vp, [vp]),
+    "sadmc_run": (C.c_int, [vp, C.c_uint64]),
+    "sadmc_run_async": (C.c_int, [vp, C.c_uint64]),
+    "sadmc_sync": (C.c_int, [vp]),
+    "sadmc_last_run_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+    "sadmc_launch_count": (C.c_int, [vp, u64p]),
+    "sadmc_num_moves": (C.c_int, [vp, u64p]),
+    "sadmc_num_accepted_moves": (C.c_int, [vp, u64p]),
+    "sadmc_get_walker": (C.c_int, [vp, C.c_uint32, C.POINTER(WalkerState)]),
+    "sadmc_get_energies": (C.c_int, [vp, f64p]),
+    "sadmc_get_bins": (C.c_int, [vp, C.c_uint32, C.c_uint32, u64p, u64p, f64p, f64p, f64p, u64p, u8p, u64p, f64p, u64p]),
+    "sadmc_system_len": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
+    "sadmc_get_system": (C.c_int, [vp, C.c_uint32, f64p, C.c_size_t]),
+    "sadmc_set_system": (C.c_int, [vp, C.c_uint32, f64p, C.c_size_t]),
+    "sadmc_get_systems": (C.c_int, [vp, f64p, C.c_size_t]),
+    "sadmc_set_systems": (C.c_int, [vp, f64p, C.c_size_t]),
+    "sadmc_get_rngs": (C.c_int, [vp, u64p]),
+    "sadmc_set_rngs": (C.c_int, [vp, u64p]),
+    "sadmc_window": (C.c_int, [vp, f64p, f64p, C.POINTER(C.c_uint32)]),
+    "sadmc_fold_device": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    "sadmc_fold": (C.c_int, [vp, u64p, f64p, f64p, f64p, f64p, u64p]),
+    "sadmc_sys_energy": (C.c_int, [vp, C.c_uint32, f64p]),
+    "sadmc_sys_compute_energy": (C.c_int, [vp, C.c_uint32, f64p]),
+    "sadmc_sys_plan_move": (C.c_int, [vp, C.c_uint32, C.c_double, C.POINTER(C.c_int), f64p]),
+    "sadmc_sys_confirm": (C.c_int, [vp, C.c_uint32]),
+    "sadmc_sys_verify_energy": (C.c_int, [vp, C.c_uint32]),
+    "sadmc_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, f64p]),
+}
+
+
+def bind(lib):
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    lib.sadmc_sizeof_config.restype = C.c_size_t
+    lib.sadmc_sizeof_walker_state.restype = C.c_size_t
+    return lib

@@ -1,0 +1,503 @@
+// book.cuh -- flat-histogram bookkeeping of one walker, on the device.
+//
+// Device form of the reference's `EnergyMC` fields and of
+//   prepare_for_state  src/mc/energy.rs:400-434
+//   reject_move        src/mc/energy.rs:440-512
+//   update_weights     src/mc/energy.rs:514-761
+//   gamma              src/mc/energy.rs:799-824 (+ SadVersion::compute_gamma 21-39)
+//   move_once          src/mc/energy.rs:904-965 (driver in move_kernel.cuh)
+//
+// Layout decisions (B200):
+//  * The reference grows five parallel Vecs (front inserts included).  Here each
+//    walker owns a FIXED window of `cap` bins in HBM; `lo`/`len`/`bmin` track which
+//    part of the window the reference's vectors would currently occupy, so every
+//    `bins.len()`-dependent rule is reproduced and `bmin` is decremented by
+//    `width` per front insert exactly as energy.rs:419 does.
+//  * lnw / histogram / energy_total / energy_squared_total of a bin share one
+//    32-byte record = one HBM sector; t_found and the round-trip arrays are side
+//    arrays that are touched only on first visits / bin changes.
+//  * The record of the walker's CURRENT bin is cached in registers and written
+//    back only when the walker leaves the bin (most proposals are rejected or
+//    stay in the bin), so a rejected move costs one 32-byte read (lnw of the
+//    proposed bin) and no write.
+//  * All G lanes that cooperate on a walker hold identical copies of the scalars
+//    and execute the bookkeeping redundantly; only lane 0 stores to HBM.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/sadmc_gpu.h"
+#include "../../include/sadmc_math.h"
+
+namespace sadmc {
+
+struct __align__(32) BinRec {
+  double lnw;
+  unsigned long long hist;
+  double etot;
+  double e2tot;
+};
+
+// Per-walker scalars as they sit in HBM between launches.
+struct __align__(16) WalkerRec {
+  unsigned long long s0, s1; // rng
+  unsigned long long accepted;
+  double acc_rate, tscale;
+  double E, err; // system energy cache (+ error estimate for LJ/WCA)
+  double bmin;
+  int lo, len;
+  int method, status;
+  // Sad
+  double too_lo, too_hi, latest_parameter;
+  unsigned long long tL, tF, num_states, highest_hist;
+  unsigned long long tfmax; // max(t_found[ilo..=ihi]), maintained incrementally
+  int ilo, ihi;             // window indices of too_lo / too_hi
+  // Samc
+  double samc_t0;
+  // WL
+  double wl_gamma, wl_num_states, wl_min_energy;
+  unsigned long long wl_lowest, wl_highest, wl_total;
+  long long wl_low_count; // visited bins with hist <= wl_lowest (flatness test in O(1))
+  int wl_hist_len, wl_pad;
+  // round trips
+  double max_S;
+  int max_S_index;   // REFERENCE index (not shifted on front inserts, as in the reference)
+  int rt_fill_val;   // value of the last bulk fill of have_visited_since_maxentropy
+  unsigned long long rt_fill_time;
+  int rt_fill_lo, rt_fill_hi; // window extent covered by that fill
+  // system extras
+  double d_squared; // two-wells
+  unsigned long long verify_fail;
+};
+
+struct DevParams {
+  BinRec* rec;
+  unsigned long long* t_found;
+  unsigned long long* rt_stamp;
+  unsigned long long* round_trips; // stored minus one (new bins start at 1, energy.rs:418,432)
+  unsigned long long* wl_hist;
+  double* extra_total;
+  unsigned long long* extra_count;
+  WalkerRec* walkers;
+  double* sys;         // [n_walkers][sys_stride] f64 system image (LJ/WCA/SW/fake/two-wells)
+  uint32_t* sys_words; // Ising: [n_walkers][ising_words] packed spins
+  const double* zig;   // X[257] then F[257]
+  uint32_t n_walkers, cap, sys_stride, ising_words;
+  double width;
+  int has_min, has_max;
+  double min_allowed, max_allowed;
+  double min_T;
+  int inv_t, has_min_gamma;
+  double min_gamma, canonical_T;
+  int move_plan;
+  double move_value;
+  uint32_t flags;
+  // system parameters
+  uint32_t N;
+  double lj_R2, lj_R;
+  double box[3];
+  int ncell[3];
+  double r_cut2, well2;
+  int fake_fn, fake_dim;
+  double fake_a, fake_b, fake_e1, fake_e2, fake_sigma;
+  double tw_h2h1, tw_r2, tw_rw;
+  double erfinv_mean;
+  unsigned long long zone_a, zone_b; // precomputed integer-sampling zones
+};
+
+// Rust `x as usize` for f64 (saturating, NaN -> 0), clipped to int range.
+__device__ __forceinline__ int f64_as_index(double x) {
+  if (!(x > 0.0)) return 0;
+  if (x >= 2147483647.0) return 2147483647;
+  return (int)x;
+}
+
+template <int METHOD, int G>
+struct Book {
+  const DevParams& P;
+  const uint32_t w;
+  const bool writer; // lane 0 of the walker's group
+  const unsigned gmask;
+  BinRec* const rec;
+  // persistent
+  unsigned long long accepted;
+  double acc_rate, tscale, bmin;
+  int lo, len, method, status;
+  double too_lo, too_hi, latest_parameter;
+  unsigned long long tL, tF, num_states, highest_hist, tfmax;
+  int ilo, ihi;
+  double samc_t0;
+  double wl_gamma, wl_num_states, wl_min_energy;
+  unsigned long long wl_lowest, wl_highest, wl_total;
+  long long wl_low_count;
+  int wl_hist_len;
+  double max_S;
+  int max_S_index, rt_fill_val, rt_fill_lo, rt_fill_hi;
+  unsigned long long rt_fill_time;
+  // cached current bin
+  int ci;
+  double c_lnw, c_etot, c_e2;
+  unsigned long long c_hist, c_wlh;
+  bool c_visited;
+
+  __device__ Book(const DevParams& p, uint32_t walker, bool is_writer, unsigned mask)
+      : P(p), w(walker), writer(is_writer), gmask(mask), rec(p.rec + (size_t)walker * p.cap) {}
+
+  __device__ __forceinline__ void sync() const {
+    if (G > 1) __syncwarp(gmask);
+  }
+  __device__ __forceinline__ size_t side(int i) const { return (size_t)w * P.cap + (size_t)i; }
+
+  __device__ void load(const WalkerRec& r) {
+    accepted = r.accepted;
+    acc_rate = r.acc_rate;
+    tscale = r.tscale;
+    bmin = r.bmin;
+    lo = r.lo;
+    len = r.len;
+    method = r.method;
+    status = r.status;
+    too_lo = r.too_lo;
+    too_hi = r.too_hi;
+    latest_parameter = r.latest_parameter;
+    tL = r.tL;
+    tF = r.tF;
+    num_states = r.num_states;
+    highest_hist = r.highest_hist;
+    tfmax = r.tfmax;
+    ilo = r.ilo;
+    ihi = r.ihi;
+    samc_t0 = r.samc_t0;
+    wl_gamma = r.wl_gamma;
+    wl_num_states = r.wl_num_states;
+    wl_min_energy = r.wl_min_energy;
+    wl_lowest = r.wl_lowest;
+    wl_highest = r.wl_highest;
+    wl_total = r.wl_total;
+    wl_low_count = r.wl_low_count;
+    wl_hist_len = r.wl_hist_len;
+    max_S = r.max_S;
+    max_S_index = r.max_S_index;
+    rt_fill_val = r.rt_fill_val;
+    rt_fill_time = r.rt_fill_time;
+    rt_fill_lo = r.rt_fill_lo;
+    rt_fill_hi = r.rt_fill_hi;
+    ci = -1;
+  }
+  __device__ void store(WalkerRec& r) {
+    flush();
+    if (!writer) return;
+    r.accepted = accepted;
+    r.acc_rate = acc_rate;
+    r.tscale = tscale;
+    r.bmin = bmin;
+    r.lo = lo;
+    r.len = len;
+    r.method = method;
+    r.status = status;
+    r.too_lo = too_lo;
+    r.too_hi = too_hi;
+    r.latest_parameter = latest_parameter;
+    r.tL = tL;
+    r.tF = tF;
+    r.num_states = num_states;
+    r.highest_hist = highest_hist;
+    r.tfmax = tfmax;
+    r.ilo = ilo;
+    r.ihi = ihi;
+    r.samc_t0 = samc_t0;
+    r.wl_gamma = wl_gamma;
+    r.wl_num_states = wl_num_states;
+    r.wl_min_energy = wl_min_energy;
+    r.wl_lowest = wl_lowest;
+    r.wl_highest = wl_highest;
+    r.wl_total = wl_total;
+    r.wl_low_count = wl_low_count;
+    r.wl_hist_len = wl_hist_len;
+    r.max_S = max_S;
+    r.max_S_index = max_S_index;
+    r.rt_fill_val = rt_fill_val;
+    r.rt_fill_time = rt_fill_time;
+    r.rt_fill_lo = rt_fill_lo;
+    r.rt_fill_hi = rt_fill_hi;
+  }
+
+  // ---- bins ------------------------------------------------------------
+  // Bins::state_to_index (energy.rs:371-373) shifted into the window.
+  __device__ __forceinline__ int widx(double e) const { return lo + f64_as_index((e - bmin) / P.width); }
+  // Bins::index_to_state (energy.rs:366-370) for window index j.
+  __device__ __forceinline__ double centre(int j) const { return bmin + ((double)(j - lo) + 0.5) * P.width; }
+
+  __device__ __forceinline__ bool visited_flag(int i) const {
+    if (P.flags & SADMC_FLAG_NO_ROUND_TRIPS) return true;
+    if (i < rt_fill_lo || i >= rt_fill_hi) return true; // created after the last bulk fill (energy.rs:417,431)
+    return P.rt_stamp[side(i)] > rt_fill_time ? true : (rt_fill_val != 0);
+  }
+  __device__ __forceinline__ void load_bin(int i) {
+    const BinRec r = rec[i];
+    ci = i;
+    c_lnw = r.lnw;
+    c_hist = r.hist;
+    c_etot = r.etot;
+    c_e2 = r.e2tot;
+    if (METHOD == SADMC_METHOD_WL) c_wlh = P.wl_hist[side(i)];
+    c_visited = visited_flag(i);
+  }
+  __device__ __forceinline__ void flush() {
+    if (ci >= 0 && writer) {
+      BinRec r;
+      r.lnw = c_lnw;
+      r.hist = c_hist;
+      r.etot = c_etot;
+      r.e2tot = c_e2;
+      rec[ci] = r;
+      if (METHOD == SADMC_METHOD_WL) P.wl_hist[side(ci)] = c_wlh;
+    }
+    sync();
+  }
+  __device__ __forceinline__ double lnw_at(int i) const { return i == ci ? c_lnw : rec[i].lnw; }
+  __device__ __forceinline__ unsigned long long hist_at(int i) const { return i == ci ? c_hist : rec[i].hist; }
+
+  // energy.rs:400-434.  Returns false when the fixed window cannot hold e.
+  __device__ __forceinline__ bool prepare_for_state(double e) {
+    while (e < bmin) {
+      if (lo == 0) return false;
+      lo -= 1;
+      len += 1;
+      bmin -= P.width;
+    }
+    while (e >= bmin + P.width * (double)len) {
+      if (lo + len >= (int)P.cap) return false;
+      len += 1;
+    }
+    return true;
+  }
+
+  // ---- gamma (energy.rs:799-824) ------------------------------------------
+  __device__ __forceinline__ double gamma(unsigned long long moves) const {
+    if (METHOD == SADMC_METHOD_CANONICAL) return 0.0;
+    if (METHOD == SADMC_METHOD_SAD) {
+      const double t = (double)moves, tf = (double)tF, ns = (double)num_states;
+      if (latest_parameter * tf * ns == 0.0) return 0.0; // energy.rs:23-25
+      return (latest_parameter + t / tf) / (latest_parameter + t / ns * (t / tf));
+    }
+    if (METHOD == SADMC_METHOD_SAMC || method == SADMC_METHOD_SAMC) {
+      const double t = (double)moves;
+      return t > samc_t0 ? samc_t0 / t : 1.0;
+    }
+    return wl_gamma;
+  }
+
+  // ---- reject_move (energy.rs:440-512) -------------------------------------
+  // i2 = widx(e2); r2 = record of bin i2 (already loaded).  `u01` draws gen::<f64>().
+  template <class RNG>
+  __device__ __forceinline__ bool reject_move(double e1, double e2, int i2, double lnw_i2, unsigned long long hist_i2,
+                                              unsigned long long moves, RNG& rng) {
+    if (METHOD == SADMC_METHOD_CANONICAL) {
+      if (e1 >= e2) return false;
+      return rng.gen_f64() > sadmc_exp((e1 - e2) / P.canonical_T);
+    }
+    double lnw1, lnw2;
+    if (METHOD == SADMC_METHOD_SAD) {
+      lnw1 = e1 < too_lo ? lnw_at(ilo) + (e1 - too_lo) / P.min_T : (e1 > too_hi ? lnw_at(ihi) : c_lnw);
+      lnw2 = e2 < too_lo ? lnw_at(ilo) + (e2 - too_lo) / P.min_T : (e2 > too_hi ? lnw_at(ihi) : lnw_i2);
+    } else {
+      lnw1 = c_lnw;
+      lnw2 = lnw_i2;
+    }
+    const bool rejected = lnw2 > lnw1 && rng.gen_f64() > sadmc_exp(lnw1 - lnw2);
+    if (METHOD == SADMC_METHOD_SAD) {
+      if (!rejected && hist_i2 == 0 && e2 < too_hi && e2 > too_lo) { // energy.rs:466-483
+        latest_parameter = (too_hi - too_lo) / P.min_T;
+        num_states += 1;
+        tL = moves;
+      }
+    } else if (METHOD == SADMC_METHOD_WL) {
+      if (method != SADMC_METHOD_SAMC && !rejected && hist_i2 == 0 && wl_lowest > 0) wl_num_states += 1.0; // energy.rs:499-501
+    }
+    return rejected;
+  }
+
+  // ---- SAD part of update_weights (energy.rs:523-636) ------------------------
+  __device__ __noinline__ void sad_extend_range(double energy, unsigned long long moves) {
+    // Reached when histogram[i] just exceeded highest_hist AND energy lies outside [too_lo, too_hi].
+    flush();
+    const int i = ci;
+    if (energy > too_hi) {
+      const double lnw_hi = rec[ihi].lnw;
+      // energy.rs:544-555 loops over every bin; only bins from ihi up to the walker's bin can satisfy
+      // `ej > too_hi && ej <= energy`.
+      for (int j = ihi; j <= i; j++) {
+        const double ej = centre(j);
+        if (ej > too_hi && ej <= energy) {
+          if (rec[j].hist != 0) {
+            if (writer) rec[j].lnw = lnw_hi;
+            num_states += 1;
+          } else if (writer) {
+            rec[j].lnw = 0.0;
+          }
+        }
+        const unsigned long long tf = P.t_found[side(j)];
+        if (j > ihi && tf > tfmax) tfmax = tf;
+      }
+      latest_parameter = (energy - too_lo) / P.min_T;
+      tL = moves;
+      too_hi = centre(i);
+      ihi = i;
+    } else { // energy < too_lo
+      const double lnw_lo = rec[ilo].lnw;
+      for (int j = i; j <= ilo; j++) {
+        const double ej = centre(j);
+        if (ej < too_lo && ej >= energy) {
+          if (rec[j].hist != 0) {
+            double v = lnw_lo + (ej - too_lo) / P.min_T;
+            if (v < 0.0) v = 0.0;
+            if (writer) rec[j].lnw = v;
+            num_states += 1;
+          } else if (writer) {
+            rec[j].lnw = 0.0;
+          }
+        }
+        const unsigned long long tf = P.t_found[side(j)];
+        if (j < ilo && tf > tfmax) tfmax = tf;
+      }
+      latest_parameter = (too_hi - energy) / P.min_T;
+      tL = moves;
+      too_lo = centre(i);
+      ilo = i;
+    }
+    sync();
+    c_lnw = rec[i].lnw; // the walker's own bin may have been overwritten
+  }
+
+  __device__ __forceinline__ void update_weights_sad(double energy, unsigned long long moves) {
+    const double g = gamma(moves);
+    const double old_lnw = c_lnw;
+    c_lnw += g;
+    if (too_lo > too_hi || energy < too_lo || energy > too_hi) c_lnw = old_lnw; // energy.rs:535-538
+    if (c_hist > highest_hist) {
+      highest_hist = c_hist;
+      if (energy > too_hi || energy < too_lo) sad_extend_range(energy, moves);
+    }
+    if (tL == moves) { // energy.rs:585-635
+      const unsigned long long old_tF = tF;
+      tF = tfmax;
+      if (old_tF != tF && P.move_plan == SADMC_MOVE_ACCEPTANCE_RATE) {
+        double s = acc_rate / P.move_value;
+        s = s < 0.8 ? 0.8 : (s > 1.2 ? 1.2 : s);
+        tscale *= s;
+      }
+    }
+  }
+
+  // ---- WL part of update_weights (energy.rs:638-752) -------------------------
+  // Number of visited bins whose WL hist is <= wl_lowest, by a full scan (rare).
+  __device__ __noinline__ long long wl_count_low() {
+    long long n = 0;
+    for (int j = lo; j < lo + len; j++)
+      if (rec[j].hist != 0 && P.wl_hist[side(j)] <= wl_lowest) n++;
+    return n;
+  }
+  __device__ __noinline__ void wl_regroup(unsigned long long moves) {
+    // energy.rs:656-687: hist.len() != lnw.len()
+    flush();
+    if (wl_hist_len == 0 || (wl_gamma != 1.0 && wl_lowest > 0)) {
+      wl_gamma = 1.0;
+      wl_lowest = 0;
+      wl_highest = 0;
+      wl_total = 0;
+      if (writer)
+        for (int j = lo; j < lo + len; j++) P.wl_hist[side(j)] = 0;
+      wl_min_energy = bmin;
+    } else {
+      // the window keeps zeros where the reference pads; replay the min_energy arithmetic
+      while (wl_min_energy > bmin) wl_min_energy -= P.width;
+      unsigned long long mn = ~0ull;
+      for (int j = lo; j < lo + len; j++) {
+        const unsigned long long h = P.wl_hist[side(j)];
+        if (h < mn) mn = h;
+      }
+      wl_lowest = mn;
+    }
+    wl_hist_len = len;
+    sync();
+    c_wlh = P.wl_hist[side(ci)];
+    wl_low_count = wl_count_low();
+    (void)moves;
+  }
+  __device__ __forceinline__ void update_weights_wl(double energy, unsigned long long moves, bool first_visit) {
+    (void)energy;
+    c_lnw += gamma(moves);
+    if (method == SADMC_METHOD_SAMC) return; // 1/t-WL after its switch (energy.rs:754-756)
+    if (P.has_min_gamma && wl_gamma < P.min_gamma) { // production run, energy.rs:649-655
+      c_wlh += 1;
+      return;
+    }
+    if (wl_hist_len != len) {
+      wl_regroup(moves);
+    } else if (first_visit && c_wlh <= wl_lowest) {
+      wl_low_count += 1; // a bin just became "visited" (histogram != 0) for the flatness filter
+    }
+    if (c_wlh == wl_lowest) wl_low_count -= 1; // it is about to exceed wl_lowest
+    c_wlh += 1;
+    if (c_wlh > wl_highest) wl_highest = c_wlh;
+    wl_total += 1;
+    const double max_energy = wl_min_energy + (double)wl_hist_len * P.width;
+    // energy.rs:695-708; `min over visited bins == lowest + 1`  <=>  no visited bin is still <= lowest
+    if (c_wlh == wl_lowest + 1 && wl_hist_len > 1 && (!P.has_min || P.min_allowed >= wl_min_energy) &&
+        (!P.has_max || P.max_allowed <= max_energy) && wl_low_count == 0) {
+      wl_lowest = c_wlh;
+      bool rescan = true;
+      if ((P.inv_t && wl_lowest > 0) || (double)wl_lowest >= 0.8 * (double)wl_total / wl_num_states) {
+        wl_gamma *= 0.5;
+        flush();
+        if (writer)
+          for (int j = lo; j < lo + len; j++) P.wl_hist[side(j)] = 0;
+        sync();
+        c_wlh = 0;
+        wl_total = 0;
+        wl_lowest = 0;
+        wl_highest = 0;
+        if (P.has_min_gamma && wl_gamma < P.min_gamma) wl_gamma = 0.0;
+      }
+      if (rescan) {
+        flush();
+        wl_low_count = wl_count_low();
+      }
+      if (P.inv_t && wl_gamma < wl_num_states / (double)moves) {
+        method = SADMC_METHOD_SAMC;
+        samc_t0 = wl_num_states;
+      }
+    }
+  }
+
+  // ---- round trips (energy.rs:950-965) ------------------------------------
+  __device__ __forceinline__ void round_trips(int i1_ref, unsigned long long moves) {
+    if (P.flags & SADMC_FLAG_NO_ROUND_TRIPS) return;
+    const int i_ref = ci - lo;
+    if (c_lnw > max_S) {
+      max_S = c_lnw;
+      max_S_index = i_ref;
+      rt_fill_val = 1;
+      rt_fill_time = moves;
+      rt_fill_lo = lo;
+      rt_fill_hi = lo + len;
+      c_visited = true;
+    } else if (i_ref == max_S_index) {
+      if (i1_ref != i_ref) {
+        rt_fill_val = 0;
+        rt_fill_time = moves;
+        rt_fill_lo = lo;
+        rt_fill_hi = lo + len;
+        c_visited = false;
+      }
+    } else if (!c_visited) {
+      c_visited = true;
+      if (writer) {
+        P.rt_stamp[side(ci)] = moves;
+        P.round_trips[side(ci)] += 1;
+      }
+    }
+  }
+};
+
+} // namespace sadmc

@@ -1,0 +1,790 @@
+// engine.cu -- the C ABI of include/sadmc_gpu.h: device memory, launches, state I/O.
+//
+// Replaces, for many walkers at once, what `EnergyMC::from_params`
+// (src/mc/energy.rs:830-898) and the `loop { mc.move_once() }` of
+// src/bin/histogram.rs:6-11 do for one.  No CPU fallback: every entry point that
+// computes launches a kernel of this library.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sadmc_gpu.h"
+#include "book.cuh"
+#include "host_ctor.hpp"
+#include "move_kernel.cuh"
+#include "rng.cuh"
+#include "sys_ising.cuh"
+#include "sys_lj.cuh"
+
+using namespace sadmc;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t _e = (call);                                                                             \
+    if (_e != cudaSuccess) return fail(SADMC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+typedef void (*move_fn)(const DevParams, unsigned long long, unsigned long long);
+typedef void (*init_fn)(const DevParams, unsigned long long, int, long long, int, double, unsigned long long);
+typedef void (*shim_fn)(const DevParams, uint32_t, int, double, ShimOut*, double*);
+
+struct KernelSet {
+  move_fn move[6]; // indexed by sadmc_method_kind (WL and INV_T_WL share)
+  init_fn init;
+  shim_fn shim;
+  int G, block;
+  size_t smem;
+};
+
+template <class Sys>
+static KernelSet make_set(const DevParams& P) {
+  KernelSet k;
+  memset(&k, 0, sizeof k);
+  k.move[SADMC_METHOD_SAD] = move_kernel<Sys, SADMC_METHOD_SAD>;
+  k.move[SADMC_METHOD_SAMC] = move_kernel<Sys, SADMC_METHOD_SAMC>;
+  k.move[SADMC_METHOD_WL] = move_kernel<Sys, SADMC_METHOD_WL>;
+  k.move[SADMC_METHOD_INV_T_WL] = move_kernel<Sys, SADMC_METHOD_WL>;
+  k.move[SADMC_METHOD_CANONICAL] = move_kernel<Sys, SADMC_METHOD_CANONICAL>;
+  k.init = init_kernel<Sys>;
+  k.shim = shim_kernel<Sys>;
+  k.G = Sys::G;
+  k.block = Sys::BLOCK;
+  k.smem = ZIG_SMEM_BYTES + Sys::smem_bytes(P, Sys::BLOCK);
+  return k;
+}
+
+struct sadmc_engine {
+  sadmc_config cfg;
+  DevParams P;
+  KernelSet ks;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  unsigned long long moves = 0;
+  unsigned long long launches = 0;
+  long long k_base = 0;
+  size_t sys_len = 0; // doubles per walker in the ABI image
+  bool started = false;
+  double* d_zig = nullptr;
+  ShimOut* d_shim = nullptr;
+  double* d_pending = nullptr;
+  double* d_wmax = nullptr;
+  void* d_fold = nullptr;
+  float last_ms = 0.f;
+  std::vector<void*> allocs;
+};
+
+static int dev_alloc(sadmc_engine* e, void** p, size_t bytes, bool zero) {
+  if (bytes == 0) bytes = 8;
+  cudaError_t er = cudaMalloc(p, bytes);
+  if (er != cudaSuccess) return fail(SADMC_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(er));
+  e->allocs.push_back(*p);
+  if (zero) {
+    er = cudaMemsetAsync(*p, 0, bytes, e->stream);
+    if (er != cudaSuccess) return fail(SADMC_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(er));
+  }
+  return 0;
+}
+
+static int pick_kernels(sadmc_engine* e) {
+  const sadmc_config& c = e->cfg;
+  DevParams& P = e->P;
+  switch (c.system) {
+    case SADMC_SYS_ISING: e->ks = make_set<IsingSys>(P); return 0;
+    case SADMC_SYS_LJ: {
+      int G = c.lanes_per_walker;
+      if (G == 0) G = 8;
+      const int A = ((int)c.N + G - 1) / G;
+#define LJ_CASE(g, a)                          \
+  if (G == g && A == a) {                      \
+    e->ks = make_set<LjSys<g, a>>(P);          \
+    return 0;                                  \
+  }
+      LJ_CASE(32, 1) LJ_CASE(32, 2) LJ_CASE(16, 1) LJ_CASE(16, 2) LJ_CASE(16, 3) LJ_CASE(8, 1) LJ_CASE(8, 2) LJ_CASE(8, 3) LJ_CASE(8, 4)
+      LJ_CASE(8, 5) LJ_CASE(4, 1) LJ_CASE(4, 2) LJ_CASE(4, 4) LJ_CASE(4, 8) LJ_CASE(4, 10)
+#undef LJ_CASE
+      return fail(SADMC_ERR_UNSUPPORTED, "lj: no kernel instance for N=%u with lanes_per_walker=%d (atoms per lane %d)", c.N, G, A);
+    }
+    default: return fail(SADMC_ERR_UNSUPPORTED, "system kind %d has no kernel yet", c.system);
+  }
+}
+
+static bool is_none(double x) { return std::isnan(x); }
+
+static int setup_params(sadmc_engine* e) {
+  const sadmc_config& c = e->cfg;
+  DevParams& P = e->P;
+  memset(&P, 0, sizeof P);
+  if (c.abi_version != SADMC_ABI_VERSION) return fail(SADMC_ERR_INVALID, "abi_version %u != %d", c.abi_version, SADMC_ABI_VERSION);
+  if (c.n_walkers == 0) return fail(SADMC_ERR_INVALID, "n_walkers must be > 0");
+  if (c.method < SADMC_METHOD_SAD || c.method > SADMC_METHOD_CANONICAL) return fail(SADMC_ERR_INVALID, "unknown method %d", c.method);
+  P.n_walkers = c.n_walkers;
+  P.N = c.N;
+  P.flags = c.flags;
+  P.has_min = !is_none(c.min_allowed_energy);
+  P.has_max = !is_none(c.max_allowed_energy);
+  P.min_allowed = c.min_allowed_energy;
+  P.max_allowed = c.max_allowed_energy;
+  P.min_T = c.sad_min_T;
+  P.inv_t = c.method == SADMC_METHOD_INV_T_WL;
+  P.has_min_gamma = c.method == SADMC_METHOD_WL && !is_none(c.wl_min_gamma);
+  P.min_gamma = c.wl_min_gamma;
+  P.canonical_T = c.canonical_T;
+  P.move_plan = c.move_plan;
+  P.move_value = c.move_value;
+  if (c.method == SADMC_METHOD_SAD && !(c.sad_min_T > 0)) return fail(SADMC_ERR_INVALID, "sad_min_T must be > 0");
+
+  double native_de = NAN, lowest = NAN, greatest = NAN;
+  switch (c.system) {
+    case SADMC_SYS_ISING:
+      if (!(c.N > 1)) return fail(SADMC_ERR_INVALID, "ising N must be > 1 (ising.rs:39)");
+      if (c.N > 256) return fail(SADMC_ERR_UNSUPPORTED, "ising N > 256 does not fit the shared-memory lattice");
+      native_de = 4.0; // ising.rs:76-78
+      lowest = -2.0 * c.N * c.N;
+      greatest = 2.0 * c.N * c.N;
+      P.ising_words = (c.N * c.N + 31) / 32;
+      P.zone_a = zone_single(c.N);
+      e->sys_len = (size_t)c.N * c.N + 1;
+      break;
+    case SADMC_SYS_LJ:
+      if (c.N < 1) return fail(SADMC_ERR_INVALID, "lj N must be >= 1");
+      if (!(c.lj_radius > 0)) return fail(SADMC_ERR_INVALID, "lj radius must be > 0");
+      P.lj_R = c.lj_radius;
+      P.lj_R2 = c.lj_radius * c.lj_radius;
+      P.zone_b = zone_uniform(c.N);
+      lowest = std::fmax(-0.5 * c.N * (c.N - 1.0), -8.7 * c.N); // lj.rs:245-248, tightened by the bulk fcc cohesive energy
+      e->sys_len = 3 * (size_t)c.N + 2;
+      P.sys_stride = (uint32_t)e->sys_len;
+      break;
+    default: return fail(SADMC_ERR_UNSUPPORTED, "system kind %d has no kernel yet", c.system);
+  }
+  P.width = !is_none(c.energy_bin) ? c.energy_bin : (!is_none(native_de) ? native_de : 1.0); // energy.rs:831-833
+  if (!(P.width > 0)) return fail(SADMC_ERR_INVALID, "energy_bin must be > 0 (energy.rs:402)");
+
+  double wlo = c.bin_window_lo, whi = c.bin_window_hi;
+  if (is_none(wlo)) wlo = P.has_min ? c.min_allowed_energy - 2 * P.width : lowest;
+  if (is_none(whi)) whi = P.has_max ? c.max_allowed_energy + 2 * P.width : greatest;
+  if (is_none(wlo) || is_none(whi))
+    return fail(SADMC_ERR_INVALID, "cannot derive the bin window: give bin_window_lo/hi or min/max_allowed_energy");
+  if (!(whi > wlo)) return fail(SADMC_ERR_INVALID, "empty bin window [%g, %g)", wlo, whi);
+  e->k_base = (long long)std::floor(wlo / P.width + 0.5) - 1;
+  const long long k_top = (long long)std::ceil(whi / P.width + 0.5) + 1;
+  const long long cap = k_top - e->k_base + 1;
+  if (cap > (1ll << 28)) return fail(SADMC_ERR_INVALID, "bin window needs %lld bins per walker", cap);
+  P.cap = (uint32_t)cap;
+  return 0;
+}
+
+static int launch_cfg(const sadmc_engine* e, int* grid) {
+  const long long threads = (long long)e->cfg.n_walkers * e->ks.G;
+  *grid = (int)((threads + e->ks.block - 1) / e->ks.block);
+  return 0;
+}
+
+static int upload_initial_systems(sadmc_engine* e) {
+  const sadmc_config& c = e->cfg;
+  if (c.init_mode != SADMC_INIT_REFERENCE) return 0;
+  std::vector<double> img;
+  switch (c.system) {
+    case SADMC_SYS_ISING: img = hostctor::ising_image(c.N); break;
+    case SADMC_SYS_LJ: img = hostctor::lj_image(c.N, c.lj_radius); break;
+    default: return fail(SADMC_ERR_UNSUPPORTED, "no reference constructor for system %d yet", c.system);
+  }
+  std::vector<double> all((size_t)c.n_walkers * e->sys_len);
+  for (uint32_t w = 0; w < c.n_walkers; w++) memcpy(&all[(size_t)w * e->sys_len], img.data(), e->sys_len * sizeof(double));
+  return sadmc_set_systems(e, all.data(), all.size());
+}
+
+// ---- measurement utility: the chip's FP64 FMA peak, for the roofline denominator ----
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      x0 = fma(x0, a, b);
+      x1 = fma(x1, a, b);
+      x2 = fma(x2, a, b);
+      x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b);
+      x5 = fma(x5, a, b);
+      x6 = fma(x6, a, b);
+      x7 = fma(x7, a, b);
+    }
+  }
+  const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 12345.678) out[0] = s;
+}
+
+extern "C" {
+
+// TFLOP/s of dependent-chain-free DFMA (2 flops each) on `device`; best of `reps`.
+int sadmc_measure_fp64_peak(int device, int reps, double* tflops) {
+  if (!tflops) return fail(SADMC_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  double* d = nullptr;
+  CK(cudaMalloc(&d, 8));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  double best = 0.0;
+  for (int r = 0; r < reps + 1; r++) {
+    CK(cudaEventRecord(a));
+    fp64_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+    CK(cudaEventRecord(b));
+    CK(cudaEventSynchronize(b));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    const double fl = 2.0 * 64.0 * (double)iters * blocks * threads;
+    if (r > 0 && fl / (ms * 1e-3) / 1e12 > best) best = fl / (ms * 1e-3) / 1e12;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  *tflops = best;
+  return 0;
+}
+
+const char* sadmc_last_error(void) { return g_err.c_str(); }
+int sadmc_abi_version(void) { return SADMC_ABI_VERSION; }
+size_t sadmc_sizeof_config(void) { return sizeof(sadmc_config); }
+size_t sadmc_sizeof_walker_state(void) { return sizeof(sadmc_walker_state); }
+
+void sadmc_destroy(sadmc_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int sadmc_create(const sadmc_config* cfg, sadmc_engine** out) {
+  if (!cfg || !out) return fail(SADMC_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(SADMC_ERR_CUDA, "no CUDA device: the walker engine has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(SADMC_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+  sadmc_engine* e = new sadmc_engine;
+  e->cfg = *cfg;
+  int rc = setup_params(e);
+  if (rc) {
+    delete e;
+    return rc;
+  }
+  rc = pick_kernels(e);
+  if (rc) {
+    delete e;
+    return rc;
+  }
+#define BAIL(expr)          \
+  do {                      \
+    int _rc = (expr);       \
+    if (_rc) {              \
+      sadmc_destroy(e);     \
+      return _rc;           \
+    }                       \
+  } while (0)
+#define CKB(call)                                                                                   \
+  do {                                                                                              \
+    cudaError_t _e = (call);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      fail(SADMC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e));                         \
+      sadmc_destroy(e);                                                                             \
+      return SADMC_ERR_CUDA;                                                                        \
+    }                                                                                               \
+  } while (0)
+  CKB(cudaSetDevice(cfg->device));
+  CKB(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  e->own_stream = true;
+  CKB(cudaEventCreate(&e->ev0));
+  CKB(cudaEventCreate(&e->ev1));
+  DevParams& P = e->P;
+  const size_t nb = (size_t)P.n_walkers * P.cap;
+  size_t need = nb * (sizeof(BinRec) + 8) + (size_t)P.n_walkers * (sizeof(WalkerRec) + e->sys_len * 8 + P.ising_words * 4);
+  const bool rt = !(P.flags & SADMC_FLAG_NO_ROUND_TRIPS);
+  if (rt) need += nb * 16;
+  const bool wl = cfg->method == SADMC_METHOD_WL || cfg->method == SADMC_METHOD_INV_T_WL;
+  if (wl) need += nb * 8;
+  size_t free_b = 0, total_b = 0;
+  CKB(cudaMemGetInfo(&free_b, &total_b));
+  if (need > free_b) {
+    fail(SADMC_ERR_INVALID, "%u walkers x %u bins need %.1f GB of HBM, %.1f GB free: shrink the bin window or the walker count",
+         P.n_walkers, P.cap, need / 1e9, free_b / 1e9);
+    sadmc_destroy(e);
+    return SADMC_ERR_INVALID;
+  }
+  BAIL(dev_alloc(e, (void**)&P.rec, nb * sizeof(BinRec), true));
+  BAIL(dev_alloc(e, (void**)&P.t_found, nb * 8, true));
+  if (rt) {
+    BAIL(dev_alloc(e, (void**)&P.rt_stamp, nb * 8, true));
+    BAIL(dev_alloc(e, (void**)&P.round_trips, nb * 8, true));
+  }
+  if (wl) BAIL(dev_alloc(e, (void**)&P.wl_hist, nb * 8, true));
+  BAIL(dev_alloc(e, (void**)&P.walkers, (size_t)P.n_walkers * sizeof(WalkerRec), true));
+  BAIL(dev_alloc(e, (void**)&P.sys, (size_t)P.n_walkers * (P.sys_stride ? P.sys_stride : 1) * 8, true));
+  BAIL(dev_alloc(e, (void**)&P.sys_words, (size_t)P.n_walkers * (P.ising_words ? P.ising_words : 1) * 4, true));
+  BAIL(dev_alloc(e, (void**)&e->d_zig, 2 * SADMC_ZIG_TABLE_LEN * 8, false));
+  BAIL(dev_alloc(e, (void**)&e->d_shim, sizeof(ShimOut), true));
+  BAIL(dev_alloc(e, (void**)&e->d_pending, 8 * 8, true));
+  {
+    double z[2 * SADMC_ZIG_TABLE_LEN];
+    memcpy(z, hostctor::H_ZX, sizeof hostctor::H_ZX);
+    memcpy(z + SADMC_ZIG_TABLE_LEN, hostctor::H_ZF, sizeof hostctor::H_ZF);
+    CKB(cudaMemcpyAsync(e->d_zig, z, sizeof z, cudaMemcpyHostToDevice, e->stream));
+    CKB(cudaStreamSynchronize(e->stream));
+  }
+  P.zig = e->d_zig;
+  if (e->ks.smem > 48 * 1024) {
+    for (int m = 1; m <= 5; m++)
+      if (e->ks.move[m]) CKB(cudaFuncSetAttribute((const void*)e->ks.move[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ks.smem));
+    CKB(cudaFuncSetAttribute((const void*)e->ks.init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ks.smem));
+    CKB(cudaFuncSetAttribute((const void*)e->ks.shim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ks.smem));
+  }
+  BAIL(upload_initial_systems(e));
+  if (cfg->init_mode != SADMC_INIT_EXTERNAL) BAIL(sadmc_start(e));
+  *out = e;
+  return 0;
+#undef BAIL
+#undef CKB
+}
+
+int sadmc_start(sadmc_engine* e) {
+  if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  if (e->started) return fail(SADMC_ERR_INVALID, "engine already started");
+  CK(cudaSetDevice(e->cfg.device));
+  int grid;
+  launch_cfg(e, &grid);
+  e->ks.init<<<grid, e->ks.block, e->ks.smem, e->stream>>>(e->P, e->cfg.seed + e->cfg.walker_offset, e->cfg.init_mode, e->k_base,
+                                                         e->cfg.method, e->cfg.samc_t0, 100000000ull);
+  e->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  e->started = true;
+  e->moves = 0;
+  return 0;
+}
+
+int sadmc_set_stream(sadmc_engine* e, void* s) {
+  if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  CK(cudaStreamSynchronize(e->stream));
+  if (e->own_stream) cudaStreamDestroy(e->stream);
+  e->stream = (cudaStream_t)s;
+  e->own_stream = false;
+  return 0;
+}
+void* sadmc_get_stream(sadmc_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int sadmc_run_async(sadmc_engine* e, uint64_t n_moves) {
+  if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  if (!e->started) return fail(SADMC_ERR_INVALID, "engine not started (call sadmc_start)");
+  if (n_moves == 0) return 0;
+  CK(cudaSetDevice(e->cfg.device));
+  int grid;
+  launch_cfg(e, &grid);
+  move_fn f = e->ks.move[e->cfg.method];
+  CK(cudaEventRecord(e->ev0, e->stream));
+  f<<<grid, e->ks.block, e->ks.smem, e->stream>>>(e->P, e->moves, n_moves);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e->ev1, e->stream));
+  e->launches++;
+  e->moves += n_moves;
+  return 0;
+}
+int sadmc_sync(sadmc_engine* e) {
+  if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int sadmc_run(sadmc_engine* e, uint64_t n_moves) {
+  int rc = sadmc_run_async(e, n_moves);
+  if (rc) return rc;
+  return sadmc_sync(e);
+}
+int sadmc_last_run_ms(sadmc_engine* e, float* ms) {
+  if (!e || !ms) return fail(SADMC_ERR_INVALID, "null argument");
+  CK(cudaEventSynchronize(e->ev1));
+  CK(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+  return 0;
+}
+int sadmc_launch_count(sadmc_engine* e, uint64_t* n) {
+  if (!e || !n) return fail(SADMC_ERR_INVALID, "null argument");
+  *n = e->launches;
+  return 0;
+}
+int sadmc_num_moves(sadmc_engine* e, uint64_t* moves) {
+  if (!e || !moves) return fail(SADMC_ERR_INVALID, "null argument");
+  *moves = e->moves;
+  return 0;
+}
+
+static int fetch_walkers(sadmc_engine* e, std::vector<WalkerRec>& v) {
+  v.resize(e->P.n_walkers);
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaMemcpyAsync(v.data(), e->P.walkers, v.size() * sizeof(WalkerRec), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+static int fetch_walker(sadmc_engine* e, uint32_t w, WalkerRec* r) {
+  if (w >= e->P.n_walkers) return fail(SADMC_ERR_INVALID, "walker %u out of range", w);
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaMemcpyAsync(r, e->P.walkers + w, sizeof(WalkerRec), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int sadmc_num_accepted_moves(sadmc_engine* e, uint64_t* accepted_sum) {
+  if (!e || !accepted_sum) return fail(SADMC_ERR_INVALID, "null argument");
+  std::vector<WalkerRec> v;
+  int rc = fetch_walkers(e, v);
+  if (rc) return rc;
+  uint64_t s = 0;
+  for (auto& r : v) s += r.accepted;
+  *accepted_sum = s;
+  return 0;
+}
+
+int sadmc_get_walker(sadmc_engine* e, uint32_t w, sadmc_walker_state* s) {
+  if (!e || !s) return fail(SADMC_ERR_INVALID, "null argument");
+  WalkerRec r;
+  int rc = fetch_walker(e, w, &r);
+  if (rc) return rc;
+  memset(s, 0, sizeof *s);
+  s->moves = e->moves;
+  s->accepted_moves = r.accepted;
+  s->acceptance_rate = r.acc_rate;
+  s->translation_scale = r.tscale;
+  s->rng_s0 = r.s0;
+  s->rng_s1 = r.s1;
+  s->energy = r.E;
+  s->bins_min = r.bmin;
+  s->bins_width = e->P.width;
+  s->bins_len = (uint32_t)r.len;
+  s->window_first = (uint32_t)r.lo;
+  s->method = r.method == SADMC_METHOD_WL && e->P.inv_t ? SADMC_METHOD_INV_T_WL : r.method;
+  s->status = r.status;
+  s->too_lo = r.too_lo;
+  s->too_hi = r.too_hi;
+  s->latest_parameter = r.latest_parameter;
+  s->tL = r.tL;
+  s->tF = r.tF;
+  s->num_states = r.num_states;
+  s->highest_hist = r.highest_hist;
+  s->samc_t0 = r.samc_t0;
+  s->wl_gamma = r.wl_gamma;
+  s->wl_num_states = r.wl_num_states;
+  s->wl_min_energy = r.wl_min_energy;
+  s->wl_lowest_hist = r.wl_lowest;
+  s->wl_highest_hist = r.wl_highest;
+  s->wl_total_hist = r.wl_total;
+  s->wl_hist_len = (uint32_t)r.wl_hist_len;
+  s->wl_inv_t = e->P.inv_t;
+  s->max_S = r.max_S;
+  s->max_S_index = (uint32_t)r.max_S_index;
+  return 0;
+}
+
+int sadmc_get_energies(sadmc_engine* e, double* energies) {
+  if (!e || !energies) return fail(SADMC_ERR_INVALID, "null argument");
+  std::vector<WalkerRec> v;
+  int rc = fetch_walkers(e, v);
+  if (rc) return rc;
+  for (size_t i = 0; i < v.size(); i++) energies[i] = v[i].E;
+  return 0;
+}
+
+int sadmc_get_bins(sadmc_engine* e, uint32_t w, uint32_t cap, uint64_t* histogram, uint64_t* t_found, double* lnw, double* energy_total,
+                   double* energy_squared_total, uint64_t* round_trips, uint8_t* have_visited, uint64_t* wl_hist, double* extra_total,
+                   uint64_t* extra_count) {
+  if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  WalkerRec r;
+  int rc = fetch_walker(e, w, &r);
+  if (rc) return rc;
+  const size_t n = (size_t)r.len;
+  if (cap < n) return fail(SADMC_ERR_INVALID, "capacity %u < bins_len %zu", cap, n);
+  const size_t base = (size_t)w * e->P.cap + (size_t)r.lo;
+  std::vector<BinRec> recs(n);
+  std::vector<unsigned long long> tmp(n), stamps(n);
+  CK(cudaMemcpyAsync(recs.data(), e->P.rec + base, n * sizeof(BinRec), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  for (size_t i = 0; i < n; i++) {
+    if (histogram) histogram[i] = recs[i].hist;
+    if (lnw) lnw[i] = recs[i].lnw;
+    if (energy_total) energy_total[i] = recs[i].etot;
+    if (energy_squared_total) energy_squared_total[i] = recs[i].e2tot;
+  }
+  if (t_found) {
+    CK(cudaMemcpyAsync(t_found, e->P.t_found + base, n * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  const bool rt = !(e->P.flags & SADMC_FLAG_NO_ROUND_TRIPS);
+  if (round_trips) {
+    if (rt) {
+      CK(cudaMemcpyAsync(round_trips, e->P.round_trips + base, n * 8, cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+      for (size_t i = 0; i < n; i++) round_trips[i] += 1; // stored minus one
+    } else
+      for (size_t i = 0; i < n; i++) round_trips[i] = 1;
+  }
+  if (have_visited) {
+    if (rt) {
+      CK(cudaMemcpyAsync(stamps.data(), e->P.rt_stamp + base, n * 8, cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+      for (size_t i = 0; i < n; i++) {
+        const int j = r.lo + (int)i;
+        bool v;
+        if (j < r.rt_fill_lo || j >= r.rt_fill_hi)
+          v = true;
+        else
+          v = stamps[i] > r.rt_fill_time ? true : (r.rt_fill_val != 0);
+        have_visited[i] = v ? 1 : 0;
+      }
+    } else
+      for (size_t i = 0; i < n; i++) have_visited[i] = 1;
+  }
+  if (wl_hist) {
+    if (e->P.wl_hist && r.wl_hist_len > 0) {
+      CK(cudaMemcpyAsync(wl_hist, e->P.wl_hist + base, n * 8, cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+    } else
+      for (size_t i = 0; i < n; i++) wl_hist[i] = 0;
+  }
+  if (extra_total) {
+    if (e->P.extra_total) {
+      CK(cudaMemcpyAsync(extra_total, e->P.extra_total + base, n * 8, cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+    } else
+      for (size_t i = 0; i < n; i++) extra_total[i] = 0;
+  }
+  if (extra_count) {
+    if (e->P.extra_count) {
+      CK(cudaMemcpyAsync(extra_count, e->P.extra_count + base, n * 8, cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+    } else
+      for (size_t i = 0; i < n; i++) extra_count[i] = 0;
+  }
+  return 0;
+}
+
+int sadmc_system_len(sadmc_engine* e, size_t* n) {
+  if (!e || !n) return fail(SADMC_ERR_INVALID, "null argument");
+  *n = e->sys_len;
+  return 0;
+}
+
+// ---- system images: ABI f64 layout <-> device-native layout -------------------
+static int systems_to_host(sadmc_engine* e, uint32_t w0, uint32_t nw, double* buf) {
+  const DevParams& P = e->P;
+  std::vector<WalkerRec> recs(nw);
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaMemcpyAsync(recs.data(), P.walkers + w0, nw * sizeof(WalkerRec), cudaMemcpyDeviceToHost, e->stream));
+  if (e->cfg.system == SADMC_SYS_ISING) {
+    std::vector<uint32_t> words((size_t)nw * P.ising_words);
+    CK(cudaMemcpyAsync(words.data(), P.sys_words + (size_t)w0 * P.ising_words, words.size() * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    const size_t sites = (size_t)P.N * P.N;
+    for (uint32_t w = 0; w < nw; w++) {
+      double* o = buf + (size_t)w * e->sys_len;
+      const uint32_t* wd = &words[(size_t)w * P.ising_words];
+      for (size_t s = 0; s < sites; s++) o[s] = ((wd[s >> 5] >> (s & 31)) & 1u) ? 1.0 : -1.0;
+      o[sites] = recs[w].E;
+    }
+    return 0;
+  }
+  CK(cudaMemcpyAsync(buf, P.sys + (size_t)w0 * P.sys_stride, (size_t)nw * P.sys_stride * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+static int systems_from_host(sadmc_engine* e, uint32_t w0, uint32_t nw, const double* buf) {
+  const DevParams& P = e->P;
+  CK(cudaSetDevice(e->cfg.device));
+  std::vector<WalkerRec> recs(nw);
+  CK(cudaMemcpyAsync(recs.data(), P.walkers + w0, nw * sizeof(WalkerRec), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (e->cfg.system == SADMC_SYS_ISING) {
+    std::vector<uint32_t> words((size_t)nw * P.ising_words, 0u);
+    const size_t sites = (size_t)P.N * P.N;
+    for (uint32_t w = 0; w < nw; w++) {
+      const double* in = buf + (size_t)w * e->sys_len;
+      uint32_t* wd = &words[(size_t)w * P.ising_words];
+      for (size_t s = 0; s < sites; s++)
+        if (in[s] > 0) wd[s >> 5] |= 1u << (s & 31);
+      recs[w].E = in[sites];
+      recs[w].err = 0;
+    }
+    CK(cudaMemcpyAsync(P.sys_words + (size_t)w0 * P.ising_words, words.data(), words.size() * 4, cudaMemcpyHostToDevice, e->stream));
+  } else {
+    CK(cudaMemcpyAsync(P.sys + (size_t)w0 * P.sys_stride, buf, (size_t)nw * P.sys_stride * 8, cudaMemcpyHostToDevice, e->stream));
+    for (uint32_t w = 0; w < nw; w++) {
+      const double* in = buf + (size_t)w * e->sys_len;
+      if (e->cfg.system == SADMC_SYS_LJ || e->cfg.system == SADMC_SYS_WCA || e->cfg.system == SADMC_SYS_SW) {
+        recs[w].E = in[3 * (size_t)P.N];
+        recs[w].err = in[3 * (size_t)P.N + 1];
+      } else if (e->cfg.system == SADMC_SYS_TWO_WELLS) {
+        recs[w].d_squared = in[P.N];
+      }
+    }
+  }
+  CK(cudaMemcpyAsync(P.walkers + w0, recs.data(), nw * sizeof(WalkerRec), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int sadmc_get_system(sadmc_engine* e, uint32_t w, double* buf, size_t n) {
+  if (!e || !buf) return fail(SADMC_ERR_INVALID, "null argument");
+  if (w >= e->P.n_walkers) return fail(SADMC_ERR_INVALID, "walker %u out of range", w);
+  if (n < e->sys_len) return fail(SADMC_ERR_INVALID, "buffer of %zu doubles < system_len %zu", n, e->sys_len);
+  return systems_to_host(e, w, 1, buf);
+}
+int sadmc_set_system(sadmc_engine* e, uint32_t w, const double* buf, size_t n) {
+  if (!e || !buf) return fail(SADMC_ERR_INVALID, "null argument");
+  if (w >= e->P.n_walkers) return fail(SADMC_ERR_INVALID, "walker %u out of range", w);
+  if (n < e->sys_len) return fail(SADMC_ERR_INVALID, "buffer of %zu doubles < system_len %zu", n, e->sys_len);
+  return systems_from_host(e, w, 1, buf);
+}
+int sadmc_get_systems(sadmc_engine* e, double* buf, size_t n) {
+  if (!e || !buf) return fail(SADMC_ERR_INVALID, "null argument");
+  if (n < e->sys_len * e->P.n_walkers) return fail(SADMC_ERR_INVALID, "buffer too small");
+  return systems_to_host(e, 0, e->P.n_walkers, buf);
+}
+int sadmc_set_systems(sadmc_engine* e, const double* buf, size_t n) {
+  if (!e || !buf) return fail(SADMC_ERR_INVALID, "null argument");
+  if (n < e->sys_len * e->P.n_walkers) return fail(SADMC_ERR_INVALID, "buffer too small");
+  return systems_from_host(e, 0, e->P.n_walkers, buf);
+}
+int sadmc_get_rngs(sadmc_engine* e, uint64_t* s) {
+  if (!e || !s) return fail(SADMC_ERR_INVALID, "null argument");
+  std::vector<WalkerRec> v;
+  int rc = fetch_walkers(e, v);
+  if (rc) return rc;
+  for (size_t i = 0; i < v.size(); i++) {
+    s[2 * i] = v[i].s0;
+    s[2 * i + 1] = v[i].s1;
+  }
+  return 0;
+}
+int sadmc_set_rngs(sadmc_engine* e, const uint64_t* s) {
+  if (!e || !s) return fail(SADMC_ERR_INVALID, "null argument");
+  std::vector<WalkerRec> v;
+  int rc = fetch_walkers(e, v);
+  if (rc) return rc;
+  for (size_t i = 0; i < v.size(); i++) {
+    v[i].s0 = s[2 * i];
+    v[i].s1 = s[2 * i + 1];
+  }
+  CK(cudaMemcpyAsync(e->P.walkers, v.data(), v.size() * sizeof(WalkerRec), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int sadmc_window(sadmc_engine* e, double* lo, double* width, uint32_t* nbins) {
+  if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  if (lo) *lo = ((double)e->k_base - 0.5) * e->P.width;
+  if (width) *width = e->P.width;
+  if (nbins) *nbins = e->P.cap;
+  return 0;
+}
+
+// ---- merge for reporting -------------------------------------------------------
+int sadmc_fold_device(sadmc_engine* e, void* d_histogram, void* d_energy_total, void* d_energy_squared_total, void* d_lnw_sum,
+                      void* d_lnw_sq_sum, void* d_lnw_count) {
+  if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  CK(cudaSetDevice(e->cfg.device));
+  if (!e->d_wmax) {
+    int rc = dev_alloc(e, (void**)&e->d_wmax, (size_t)e->P.n_walkers * 8, false);
+    if (rc) return rc;
+  }
+  walker_max_lnw_kernel<<<e->P.n_walkers, 256, 0, e->stream>>>(e->P, e->d_wmax);
+  CK(cudaGetLastError());
+  fold_kernel<<<(e->P.cap + 255) / 256, 256, 0, e->stream>>>(e->P, e->d_wmax, (unsigned long long*)d_histogram, (double*)d_energy_total,
+                                                           (double*)d_energy_squared_total, (double*)d_lnw_sum, (double*)d_lnw_sq_sum,
+                                                           (unsigned long long*)d_lnw_count);
+  CK(cudaGetLastError());
+  e->launches += 2;
+  return 0;
+}
+int sadmc_fold(sadmc_engine* e, uint64_t* histogram, double* energy_total, double* energy_squared_total, double* lnw_sum,
+               double* lnw_sq_sum, uint64_t* lnw_count) {
+  if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  const size_t n = e->P.cap;
+  if (!e->d_fold) {
+    int rc = dev_alloc(e, (void**)&e->d_fold, 6 * n * 8, false);
+    if (rc) return rc;
+  }
+  unsigned long long* d = (unsigned long long*)e->d_fold;
+  int rc = sadmc_fold_device(e, d, d + n, d + 2 * n, d + 3 * n, d + 4 * n, d + 5 * n);
+  if (rc) return rc;
+  void* outs[6] = {histogram, energy_total, energy_squared_total, lnw_sum, lnw_sq_sum, lnw_count};
+  for (int k = 0; k < 6; k++)
+    if (outs[k]) CK(cudaMemcpyAsync(outs[k], d + k * n, n * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+// ---- trait shims -------------------------------------------------------------
+static int run_shim(sadmc_engine* e, uint32_t w, int op, double arg, ShimOut* o) {
+  if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  if (w >= e->P.n_walkers) return fail(SADMC_ERR_INVALID, "walker %u out of range", w);
+  CK(cudaSetDevice(e->cfg.device));
+  e->ks.shim<<<1, e->ks.block, e->ks.smem, e->stream>>>(e->P, w, op, arg, e->d_shim, e->d_pending);
+  e->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(o, e->d_shim, sizeof(ShimOut), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int sadmc_sys_energy(sadmc_engine* e, uint32_t w, double* energy) {
+  ShimOut o;
+  int rc = run_shim(e, w, OP_ENERGY, 0, &o);
+  if (!rc) *energy = o.value;
+  return rc;
+}
+int sadmc_sys_compute_energy(sadmc_engine* e, uint32_t w, double* energy) {
+  ShimOut o;
+  int rc = run_shim(e, w, OP_COMPUTE_ENERGY, 0, &o);
+  if (!rc) *energy = o.value;
+  return rc;
+}
+int sadmc_sys_plan_move(sadmc_engine* e, uint32_t w, double mean_distance, int* some, double* e_new) {
+  ShimOut o;
+  int rc = run_shim(e, w, OP_PLAN_MOVE, mean_distance, &o);
+  if (!rc) {
+    *some = o.some;
+    *e_new = o.value;
+  }
+  return rc;
+}
+int sadmc_sys_confirm(sadmc_engine* e, uint32_t w) {
+  ShimOut o;
+  return run_shim(e, w, OP_CONFIRM, 0, &o);
+}
+int sadmc_sys_verify_energy(sadmc_engine* e, uint32_t w) {
+  ShimOut o;
+  int rc = run_shim(e, w, OP_VERIFY, 0, &o);
+  if (rc) return rc;
+  return o.ok ? 0 : fail(SADMC_ERR_VERIFY, "verify_energy failed for walker %u", w);
+}
+
+} // extern "C"

@@ -1,0 +1,140 @@
+// host_ctor.hpp -- the reference's system CONSTRUCTORS, run once on the host.
+//
+// With SADMC_INIT_REFERENCE every walker starts from the configuration the
+// reference builds in `Any::from(AnyParams)` (src/system/any.rs:80-93).  Those
+// constructors are sequential, RNG-driven set-up code (seconds, once per run),
+// not the hot path; they produce one f64 system image (layout of
+// sadmc_get_system) that the engine replicates to all walkers.  Arithmetic is in
+// the reference's order (no FMA) because the constructors' accept/stop decisions
+// depend on it.
+#pragma once
+#include <cmath>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/sadmc_gpu.h"
+#include "rng.cuh"
+
+namespace sadmc {
+namespace hostctor {
+
+static const double H_ZX[SADMC_ZIG_TABLE_LEN] = SADMC_ZIG_NORM_X_INIT;
+static const double H_ZF[SADMC_ZIG_TABLE_LEN] = SADMC_ZIG_NORM_F_INIT;
+
+struct V3 {
+  double x, y, z;
+};
+inline double norm2(const V3& a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+inline V3 sub(const V3& a, const V3& b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+
+inline double lj_potential(double r2) { // lj.rs:78-81
+  const double s = 1.0 / r2;
+  const double s3 = s * s * s;
+  return 4.0 * (s3 * s3 - s3);
+}
+inline double lj_compute_energy(const std::vector<V3>& p) { // lj.rs:236-244
+  double e = 0.0;
+  for (size_t which = 0; which < p.size(); which++)
+    for (size_t k = 0; k < which; k++) e += lj_potential(norm2(sub(p[which], p[k])));
+  return e;
+}
+
+// From<LjParams> for Lj, lj.rs:126-205
+inline std::vector<double> lj_image(uint32_t n, double radius) {
+  Rng rng;
+  seed_from_u64(0, &rng.s0, &rng.s1);
+  double best_energy = 1e80;
+  std::vector<V3> best, pos(n);
+  double E = 0.0, error = 0.0;
+  bool done = false;
+  for (uint64_t attempt = 0; attempt < 10000000ull && !done; attempt++) {
+    for (uint32_t k = 0; k < n; k++) {
+      V3 r;
+      for (;;) {
+        r.x = rng.uniform_f64(-1.0, 2.0);
+        r.y = rng.uniform_f64(-1.0, 2.0);
+        r.z = rng.uniform_f64(-1.0, 2.0);
+        if (norm2(r) < 1.0) break;
+      }
+      pos[k] = V3{r.x * radius, r.y * radius, r.z * radius};
+    }
+    V3 cm = pos[0];
+    for (uint32_t k = 1; k < n; k++) cm = V3{cm.x + pos[k].x, cm.y + pos[k].y, cm.z + pos[k].z};
+    cm = V3{cm.x / (double)n, cm.y / (double)n, cm.z / (double)n};
+    for (auto& x : pos) x = sub(x, cm);
+    bool outside = false;
+    for (auto& x : pos)
+      if (norm2(x) > radius * radius) {
+        outside = true;
+        break;
+      }
+    if (outside) continue;
+    E = lj_compute_energy(pos);
+    if (E < best_energy) {
+      best_energy = E;
+      best = pos;
+    }
+    if (E < 0.0) done = true;
+  }
+  if (!done) {
+    // downhill-only relaxation of the best attempt, lj.rs:183-203
+    pos = best;
+    E = best_energy;
+    error = 0.0;
+    const uint64_t zone = zone_uniform(n);
+    const double R2 = radius * radius;
+    for (uint64_t attempt = 0; attempt < 100000000ull; attempt++) {
+      const uint32_t which = rng.below(n, zone);
+      const double vx = rng.normal(H_ZX, H_ZF), vy = rng.normal(H_ZX, H_ZF), vz = rng.normal(H_ZX, H_ZF);
+      const V3 from = pos[which];
+      const V3 to{from.x + vx * 0.03, from.y + vy * 0.03, from.z + vz * 0.03};
+      if (norm2(to) > R2 && norm2(to) > norm2(from)) continue; // None
+      double e = E;
+      for (uint32_t k = 0; k < n; k++) {
+        if (k == which) continue;
+        e += lj_potential(norm2(sub(pos[k], to))) - lj_potential(norm2(sub(pos[k], from)));
+      }
+      if (e < E) { // confirm + set_energy, lj.rs:110-123
+        pos[which] = to;
+        const double new_error = std::fabs(e) > std::fabs(E) ? std::fabs(e) * 1e-15 * (double)n : std::fabs(E) * 1e-15 * (double)n;
+        error = new_error + error;
+        if (error > std::fabs(e) * 1e-14 * (double)n * (double)n) {
+          error *= 0.0;
+          E = lj_compute_energy(pos);
+        } else {
+          E = e;
+        }
+      }
+      if (E < 0.0) break;
+    }
+  }
+  std::vector<double> img;
+  for (auto& p : pos) {
+    img.push_back(p.x);
+    img.push_back(p.y);
+    img.push_back(p.z);
+  }
+  img.push_back(E);
+  img.push_back(error);
+  return img;
+}
+
+// From<IsingParams>, ising.rs:31-53: spins from seed 10137, +-1.0 per site, then E
+inline std::vector<double> ising_image(uint32_t N) {
+  Rng rng;
+  seed_from_u64(10137, &rng.s0, &rng.s1);
+  std::vector<double> img((size_t)N * N + 1);
+  for (size_t k = 0; k < (size_t)N * N; k++) img[k] = (rng.next() & 1ull) ? 1.0 : -1.0;
+  double e = 0.0;
+  for (uint32_t i1 = 0; i1 < N; i1++)
+    for (uint32_t j1 = 0; j1 < N; j1++) {
+      const uint32_t j2 = (j1 + 1) % N, i2 = (i1 + 1) % N;
+      e += (img[i1 + (size_t)j2 * N] + img[i2 + (size_t)j1 * N]) * img[i1 + (size_t)j1 * N];
+    }
+  img[(size_t)N * N] = e;
+  return img;
+}
+
+} // namespace hostctor
+} // namespace sadmc

@@ -1,0 +1,344 @@
+// move_kernel.cuh -- the hot loop: n_moves x `EnergyMC::move_once`
+// (src/mc/energy.rs:904-965) for every walker of one GPU, in one launch.
+//
+// One launch == one plugin period of the reference (`PluginManager::run`,
+// src/mc/plugin.rs:93-144): walker state (system, RNG, method scalars, current
+// bin record) is loaded into registers / shared memory once, advanced n_moves
+// times, and stored once.  Only bin records travel to and from HBM in between.
+#pragma once
+#include "book.cuh"
+#include "rng.cuh"
+
+namespace sadmc {
+
+constexpr int ZIG_SMEM_BYTES = 4128; // 2 * 257 doubles, padded to 32 B
+
+template <int G>
+__device__ __forceinline__ unsigned group_mask() {
+  if (G >= 32) return 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  return ((1u << (G & 31)) - 1u) << (lane / G * G);
+}
+
+__device__ __forceinline__ const double* stage_zig(const DevParams& P, unsigned char* smem) {
+  double* z = reinterpret_cast<double*>(smem);
+  for (int i = threadIdx.x; i < 2 * SADMC_ZIG_TABLE_LEN; i += blockDim.x) z[i] = P.zig[i];
+  __syncthreads();
+  return z;
+}
+
+// Sad/WL method state at construction, `Method::new` (energy.rs:246-313), and the
+// first bin (energy.rs:852, 868-882).  k_base: window bin j covers
+// [(k_base + j - 0.5) width, (k_base + j + 0.5) width).
+template <int G>
+__device__ void first_bin(const DevParams& P, uint32_t w, WalkerRec& r, double e0, long long k_base, int method_param, bool writer) {
+  const double k0 = round(e0 / P.width); // f64::round: half away from zero
+  const double emin = (k0 - 0.5) * P.width;
+  const long long lo = (long long)k0 - k_base;
+  if (!writer) return;
+  r.accepted = 0;
+  r.acc_rate = 0.5;
+  r.tscale = P.move_plan == SADMC_MOVE_TRANSLATION_SCALE ? P.move_value : 0.05; // energy.rs:884-887
+  r.bmin = emin;
+  r.len = 1;
+  r.status = 0;
+  if (lo < 0 || lo >= (long long)P.cap || !(e0 == e0)) {
+    r.lo = 0;
+    r.status = SADMC_ERR_WINDOW;
+    return;
+  }
+  r.lo = (int)lo;
+  BinRec b;
+  b.lnw = 0.0;
+  b.hist = 1;
+  b.etot = e0;
+  b.e2tot = e0 * e0;
+  P.rec[(size_t)w * P.cap + lo] = b;
+  P.t_found[(size_t)w * P.cap + lo] = 0;
+  r.method = method_param == SADMC_METHOD_INV_T_WL ? SADMC_METHOD_WL : method_param;
+  r.too_lo = e0;
+  r.too_hi = e0;
+  r.latest_parameter = 0.0;
+  r.tL = 0;
+  r.tF = 0;
+  r.num_states = 1;
+  r.highest_hist = 1;
+  r.tfmax = 0;
+  r.ilo = (int)lo;
+  r.ihi = (int)lo;
+  r.samc_t0 = 0.0;
+  r.wl_gamma = 1.0;
+  const bool both = P.has_min && P.has_max;
+  r.wl_lowest = both ? 0 : 1;
+  r.wl_highest = 1;
+  r.wl_total = 0;
+  r.wl_num_states = both ? (P.max_allowed - P.min_allowed) / P.width : 1.0;
+  r.wl_min_energy = e0;
+  r.wl_low_count = 0;
+  r.wl_hist_len = 0;
+  r.max_S = 0.0;
+  r.max_S_index = 0;
+  r.rt_fill_val = 0; // have_visited_since_maxentropy = [false], energy.rs:879
+  r.rt_fill_time = 0;
+  r.rt_fill_lo = (int)lo;
+  r.rt_fill_hi = (int)lo + 1;
+  r.verify_fail = 0;
+}
+
+// `from_params` for every walker: optional randomize, the downhill relaxation
+// (energy.rs:840-851), then the first bin.
+template <class Sys>
+__global__ void __launch_bounds__(Sys::BLOCK) init_kernel(const DevParams P, unsigned long long seed0, int init_mode, long long k_base,
+                                                         int method_param, double samc_t0, unsigned long long max_relax) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const double* zx = stage_zig(P, smem);
+  const double* zf = zx + SADMC_ZIG_TABLE_LEN;
+  constexpr int G = Sys::G;
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t w = tid / G;
+  const int lane = (int)(tid % G);
+  if (w >= P.n_walkers) return;
+  const unsigned gmask = group_mask<G>();
+  WalkerRec& wr = P.walkers[w];
+  Sys sys(P, w, lane, gmask, smem + ZIG_SMEM_BYTES);
+  sys.load(P, w, wr);
+  Rng rng;
+  seed_from_u64(seed0 + (unsigned long long)w, (uint64_t*)&rng.s0, (uint64_t*)&rng.s1); // energy.rs:835, walker w <-> --seed seed0+w
+  if (init_mode == SADMC_INIT_RANDOMIZE) sys.randomize(rng);
+  if (P.has_max) {
+#pragma unroll 1
+    for (unsigned long long it = 0; it < max_relax; it++) {
+      double newe;
+      if (sys.plan_move(rng, 0.05, zx, zf, newe)) {
+        if (newe < sys.energy()) sys.confirm();
+        if (sys.energy() < P.max_allowed) break;
+      }
+    }
+  }
+  first_bin<G>(P, w, wr, sys.energy(), k_base, method_param, lane == 0);
+  if (lane == 0) {
+    wr.s0 = rng.s0;
+    wr.s1 = rng.s1;
+    wr.samc_t0 = samc_t0;
+  }
+  sys.store(P, w, wr, lane == 0);
+}
+
+template <class Sys, int METHOD>
+__global__ void __launch_bounds__(Sys::BLOCK) move_kernel(const DevParams P, unsigned long long moves0, unsigned long long n_moves) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const double* zx = stage_zig(P, smem);
+  const double* zf = zx + SADMC_ZIG_TABLE_LEN;
+  constexpr int G = Sys::G;
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t w = tid / G;
+  const int lane = (int)(tid % G);
+  if (w >= P.n_walkers) return;
+  const unsigned gmask = group_mask<G>();
+  WalkerRec& wr = P.walkers[w];
+  if (wr.status != 0) return; // a walker that left the window stays halted
+  Sys sys(P, w, lane, gmask, smem + ZIG_SMEM_BYTES);
+  sys.load(P, w, wr);
+  Book<METHOD, G> bk(P, w, lane == 0, gmask);
+  bk.load(wr);
+  Rng rng;
+  rng.s0 = wr.s0;
+  rng.s1 = wr.s1;
+  bk.load_bin(bk.widx(sys.energy()));
+
+  unsigned long long moves = moves0;
+#pragma unroll 1
+  for (unsigned long long m = 0; m < n_moves; m++) {
+    moves += 1; // energy.rs:905
+    const double e1 = sys.energy();
+    const int i1 = bk.ci;
+    const double recent_scale = sqrt(1.0 / (double)moves); // energy.rs:913
+    bk.acc_rate *= 1.0 - recent_scale;
+    double e2;
+    int inew = i1;
+    if (sys.plan_move(rng, bk.tscale, zx, zf, e2)) { // energy.rs:915
+      bool out_of_bounds = false;
+      if (P.has_max) out_of_bounds = e2 > P.max_allowed && e2 > e1;
+      if (P.has_min) out_of_bounds = out_of_bounds || (e2 < P.min_allowed && e2 < e1);
+      if (!out_of_bounds) {
+        if (!bk.prepare_for_state(e2)) { // energy.rs:925
+          bk.status = SADMC_ERR_WINDOW;
+          break;
+        }
+        const int i2 = bk.widx(e2);
+        double lnw2;
+        unsigned long long hist2;
+        BinRec r2;
+        if (i2 == i1) {
+          lnw2 = bk.c_lnw;
+          hist2 = bk.c_hist;
+        } else {
+          r2 = bk.rec[i2];
+          lnw2 = r2.lnw;
+          hist2 = r2.hist;
+        }
+        if (!bk.reject_move(e1, e2, i2, lnw2, hist2, moves, rng)) { // energy.rs:927-931
+          bk.accepted += 1;
+          bk.acc_rate += recent_scale;
+          sys.confirm();
+          const double e_now = sys.energy();
+          inew = e_now == e2 ? i2 : bk.widx(e_now); // set_energy may have recomputed E (lj.rs:117-120)
+          if (inew != i1) {
+            bk.flush();
+            if (inew == i2) {
+              bk.ci = i2;
+              bk.c_lnw = r2.lnw;
+              bk.c_hist = r2.hist;
+              bk.c_etot = r2.etot;
+              bk.c_e2 = r2.e2tot;
+              if (METHOD == SADMC_METHOD_WL) bk.c_wlh = P.wl_hist[bk.side(i2)];
+              bk.c_visited = bk.visited_flag(i2);
+            } else {
+              if (inew < bk.lo || inew >= bk.lo + bk.len) {
+                bk.status = SADMC_ERR_WINDOW;
+                break;
+              }
+              bk.load_bin(inew);
+            }
+          }
+        }
+      }
+    }
+    const double energy = sys.energy(); // energy.rs:934
+    const bool first_visit = bk.c_hist == 0;
+    if (first_visit) { // energy.rs:938-940
+      if (bk.writer) P.t_found[bk.side(bk.ci)] = moves;
+      if (METHOD == SADMC_METHOD_SAD && bk.ci >= bk.ilo && bk.ci <= bk.ihi) bk.tfmax = moves;
+    }
+    bk.c_hist += 1;
+    bk.c_etot += energy;
+    bk.c_e2 += energy * energy;
+    {
+      double xv;
+      if (sys.extra(moves, xv) && bk.writer) { // energy.rs:944-946, Bins::accumulate_extra 374-386
+        P.extra_count[bk.side(bk.ci)] += 1;
+        P.extra_total[bk.side(bk.ci)] += xv;
+      }
+    }
+    if (METHOD == SADMC_METHOD_SAD) bk.update_weights_sad(energy, moves); // energy.rs:948
+    if (METHOD == SADMC_METHOD_SAMC) bk.c_lnw += bk.gamma(moves);
+    if (METHOD == SADMC_METHOD_WL) bk.update_weights_wl(energy, moves, first_visit);
+    bk.round_trips(i1 - bk.lo, moves); // energy.rs:950-965
+  }
+  bk.store(wr);
+  sys.store(P, w, wr, lane == 0);
+  if (lane == 0) {
+    wr.s0 = rng.s0;
+    wr.s1 = rng.s1;
+  }
+}
+
+// ---- trait-shaped single-walker shims (src/system/mod.rs:54-120) ---------------
+enum SysOp { OP_ENERGY = 0, OP_COMPUTE_ENERGY = 1, OP_PLAN_MOVE = 2, OP_CONFIRM = 3, OP_VERIFY = 4 };
+
+struct ShimOut {
+  double value;
+  int some;
+  int ok;
+};
+
+template <class Sys>
+__global__ void __launch_bounds__(Sys::BLOCK) shim_kernel(const DevParams P, uint32_t w, int op, double arg, ShimOut* out, double* pending) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const double* zx = stage_zig(P, smem);
+  const double* zf = zx + SADMC_ZIG_TABLE_LEN;
+  constexpr int G = Sys::G;
+  const int lane = (int)threadIdx.x;
+  if (lane >= G) return;
+  const unsigned gmask = group_mask<G>();
+  WalkerRec& wr = P.walkers[w];
+  Sys sys(P, w, lane, gmask, smem + ZIG_SMEM_BYTES);
+  sys.load(P, w, wr);
+  Rng rng;
+  rng.s0 = wr.s0;
+  rng.s1 = wr.s1;
+  ShimOut o;
+  o.value = 0.0;
+  o.some = 1;
+  o.ok = 1;
+  switch (op) {
+    case OP_ENERGY: o.value = sys.energy(); break;
+    case OP_COMPUTE_ENERGY: o.value = sys.compute_energy(); break;
+    case OP_VERIFY: o.ok = sys.verify_energy() ? 1 : 0; break;
+    case OP_PLAN_MOVE: {
+      double e2 = 0.0;
+      o.some = sys.plan_move(rng, arg, zx, zf, e2) ? 1 : 0;
+      o.value = e2;
+      sys.get_pending(pending, lane == 0, o.some != 0);
+      if (lane == 0) {
+        wr.s0 = rng.s0;
+        wr.s1 = rng.s1;
+      }
+      break;
+    }
+    case OP_CONFIRM:
+      if (sys.set_pending(pending)) sys.confirm();
+      sys.store(P, w, wr, lane == 0);
+      if (lane == 0) pending[0] = 0.0; // Change::None afterwards (lj.rs:344)
+      break;
+  }
+  if (lane == 0) *out = o;
+}
+
+} // namespace sadmc
+
+namespace sadmc {
+
+// ---- merge for reporting ---------------------------------------------------
+// One thread per window bin; loops over the local walkers (each warp reads 32
+// consecutive bins of one walker: coalesced 1 KB).  lnw is aligned per walker by
+// subtracting that walker's maximum lnw (plotting/parse-binning.py:169) before
+// it is summed; bins a walker never visited do not contribute to the lnw sums.
+__global__ void __launch_bounds__(256) walker_max_lnw_kernel(const DevParams P, double* wmax) {
+  const uint32_t w = blockIdx.x;
+  const WalkerRec& r = P.walkers[w];
+  double m = -1e300;
+  for (int j = r.lo + (int)threadIdx.x; j < r.lo + r.len; j += blockDim.x) {
+    const BinRec b = P.rec[(size_t)w * P.cap + j];
+    if (b.hist != 0 && b.lnw > m) m = b.lnw;
+  }
+  __shared__ double sm[256];
+  sm[threadIdx.x] = m;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s && sm[threadIdx.x + s] > sm[threadIdx.x]) sm[threadIdx.x] = sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) wmax[w] = sm[0];
+}
+
+__global__ void __launch_bounds__(256) fold_kernel(const DevParams P, const double* wmax, unsigned long long* histogram, double* energy_total,
+                                                  double* energy_squared_total, double* lnw_sum, double* lnw_sq_sum,
+                                                  unsigned long long* lnw_count) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= P.cap) return;
+  unsigned long long h = 0, cnt = 0;
+  double et = 0.0, e2 = 0.0, ls = 0.0, lq = 0.0;
+  for (uint32_t w = 0; w < P.n_walkers; w++) {
+    const WalkerRec& r = P.walkers[w];
+    if ((int)j < r.lo || (int)j >= r.lo + r.len) continue;
+    const BinRec b = P.rec[(size_t)w * P.cap + j];
+    h += b.hist;
+    et += b.etot;
+    e2 += b.e2tot;
+    if (b.hist != 0) {
+      const double a = b.lnw - wmax[w];
+      ls += a;
+      lq += a * a;
+      cnt += 1;
+    }
+  }
+  if (histogram) histogram[j] = h;
+  if (energy_total) energy_total[j] = et;
+  if (energy_squared_total) energy_squared_total[j] = e2;
+  if (lnw_sum) lnw_sum[j] = ls;
+  if (lnw_sq_sum) lnw_sq_sum[j] = lq;
+  if (lnw_count) lnw_count[j] = cnt;
+}
+
+} // namespace sadmc

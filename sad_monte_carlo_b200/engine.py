@@ -1,0 +1,201 @@
+"""Host-side mirror of the reference's `EnergyMC` for a batch of walkers.
+
+`WalkerEngine` is a thin, typed wrapper over the C ABI (include/sadmc_gpu.h):
+the names follow the reference (`move_once` -> `run(n)`, `num_moves`,
+`num_accepted_moves`, `system`, `bins`, `plan_move` / `confirm` / `energy` /
+`compute_energy` / `verify_energy` of src/system/mod.rs:54-120).  All compute
+happens in libsadmc_gpu.so; numpy is only used for host buffers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi, load_library
+from ._abi import Config, WalkerState
+from ._capi import f64p, u64p, u8p
+
+
+class SadmcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("sadmc error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+class WalkerEngine:
+    """`EnergyMC<Any>` x n_walkers on one GPU (reference: src/mc/energy.rs:167-210)."""
+
+    def __init__(self, cfg: Config):
+        self.L = load_library()
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        self._check(self.L.sadmc_create(C.byref(cfg), C.byref(self.h)))
+        n = C.c_size_t()
+        self._check(self.L.sadmc_system_len(self.h, C.byref(n)))
+        self.system_len = n.value
+        self.n_walkers = cfg.n_walkers
+
+    # -- plumbing ---------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise SadmcError(rc, self.L.sadmc_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None) and self.h:
+            self.L.sadmc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- the hot path -------------------------------------------------------
+    def run(self, n_moves):
+        """n_moves x move_once (energy.rs:904-974) for every walker; blocking."""
+        self._check(self.L.sadmc_run(self.h, int(n_moves)))
+
+    def run_async(self, n_moves):
+        self._check(self.L.sadmc_run_async(self.h, int(n_moves)))
+
+    def sync(self):
+        self._check(self.L.sadmc_sync(self.h))
+
+    def start(self):
+        self._check(self.L.sadmc_start(self.h))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.L.sadmc_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def last_run_ms(self):
+        ms = C.c_float()
+        self._check(self.L.sadmc_last_run_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_uint64()
+        self._check(self.L.sadmc_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    # -- state --------------------------------------------------------------
+    def num_moves(self):
+        n = C.c_uint64()
+        self._check(self.L.sadmc_num_moves(self.h, C.byref(n)))
+        return n.value
+
+    def num_accepted_moves(self):
+        n = C.c_uint64()
+        self._check(self.L.sadmc_num_accepted_moves(self.h, C.byref(n)))
+        return n.value
+
+    def walker(self, w=0) -> WalkerState:
+        s = WalkerState()
+        self._check(self.L.sadmc_get_walker(self.h, w, C.byref(s)))
+        return s
+
+    def energies(self):
+        e = np.zeros(self.n_walkers)
+        self._check(self.L.sadmc_get_energies(self.h, _p(e, f64p)))
+        return e
+
+    def bins(self, w=0):
+        n = self.walker(w).bins_len
+        out = {
+            "histogram": np.zeros(n, np.uint64), "t_found": np.zeros(n, np.uint64), "lnw": np.zeros(n),
+            "energy_total": np.zeros(n), "energy_squared_total": np.zeros(n),
+            "round_trips": np.zeros(n, np.uint64), "have_visited": np.zeros(n, np.uint8),
+            "wl_hist": np.zeros(n, np.uint64), "extra_total": np.zeros(n), "extra_count": np.zeros(n, np.uint64),
+        }
+        self._check(self.L.sadmc_get_bins(
+            self.h, w, n, _p(out["histogram"], u64p), _p(out["t_found"], u64p), _p(out["lnw"], f64p),
+            _p(out["energy_total"], f64p), _p(out["energy_squared_total"], f64p), _p(out["round_trips"], u64p),
+            _p(out["have_visited"], u8p), _p(out["wl_hist"], u64p), _p(out["extra_total"], f64p),
+            _p(out["extra_count"], u64p)))
+        return out
+
+    def system(self, w=0):
+        buf = np.zeros(self.system_len)
+        self._check(self.L.sadmc_get_system(self.h, w, _p(buf, f64p), buf.size))
+        return buf
+
+    def set_system(self, w, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.float64)
+        self._check(self.L.sadmc_set_system(self.h, w, _p(buf, f64p), buf.size))
+
+    def systems(self):
+        buf = np.zeros((self.n_walkers, self.system_len))
+        self._check(self.L.sadmc_get_systems(self.h, _p(buf, f64p), buf.size))
+        return buf
+
+    def set_systems(self, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.float64)
+        assert buf.size == self.n_walkers * self.system_len
+        self._check(self.L.sadmc_set_systems(self.h, _p(buf, f64p), buf.size))
+
+    def rngs(self):
+        s = np.zeros((self.n_walkers, 2), np.uint64)
+        self._check(self.L.sadmc_get_rngs(self.h, _p(s, u64p)))
+        return s
+
+    def set_rngs(self, s):
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        assert s.shape == (self.n_walkers, 2)
+        self._check(self.L.sadmc_set_rngs(self.h, _p(s, u64p)))
+
+    def window(self):
+        lo, width, n = C.c_double(), C.c_double(), C.c_uint32()
+        self._check(self.L.sadmc_window(self.h, C.byref(lo), C.byref(width), C.byref(n)))
+        return lo.value, width.value, n.value
+
+    def fold(self):
+        """Window-aligned sums over the local walkers (device fold kernel), as host arrays."""
+        _, _, n = self.window()
+        out = {"histogram": np.zeros(n, np.uint64), "energy_total": np.zeros(n), "energy_squared_total": np.zeros(n),
+               "lnw_sum": np.zeros(n), "lnw_sq_sum": np.zeros(n), "lnw_count": np.zeros(n, np.uint64)}
+        self._check(self.L.sadmc_fold(self.h, _p(out["histogram"], u64p), _p(out["energy_total"], f64p),
+                                      _p(out["energy_squared_total"], f64p), _p(out["lnw_sum"], f64p),
+                                      _p(out["lnw_sq_sum"], f64p), _p(out["lnw_count"], u64p)))
+        return out
+
+    def fold_device(self, hist, etot, e2tot, lnw_sum, lnw_sq, lnw_cnt):
+        """Same, into caller-owned DEVICE buffers given as raw pointers (e.g. torch tensors' data_ptr())."""
+        self._check(self.L.sadmc_fold_device(self.h, *[C.c_void_p(p) for p in (hist, etot, e2tot, lnw_sum, lnw_sq, lnw_cnt)]))
+
+    # -- trait-shaped shims (src/system/mod.rs:54-120) -------------------------
+    def energy(self, w=0):
+        e = C.c_double()
+        self._check(self.L.sadmc_sys_energy(self.h, w, C.byref(e)))
+        return e.value
+
+    def compute_energy(self, w=0):
+        e = C.c_double()
+        self._check(self.L.sadmc_sys_compute_energy(self.h, w, C.byref(e)))
+        return e.value
+
+    def plan_move(self, w, mean_distance):
+        some, e = C.c_int(), C.c_double()
+        self._check(self.L.sadmc_sys_plan_move(self.h, w, mean_distance, C.byref(some), C.byref(e)))
+        return e.value if some.value else None
+
+    def confirm(self, w=0):
+        self._check(self.L.sadmc_sys_confirm(self.h, w))
+
+    def verify_energy(self, w=0):
+        rc = self.L.sadmc_sys_verify_energy(self.h, w)
+        if rc == _abi.ERR_VERIFY:
+            return False
+        self._check(rc)
+        return True
+
+
+EnergyMC = WalkerEngine

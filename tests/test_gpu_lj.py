@@ -1,0 +1,131 @@
+"""GPU parity, floating-point tier: Lennard-Jones clusters (BASELINE.json configs 3 and 4).
+
+Tolerance (stated by BASELINE.json's north_star): per-move energies within 1e-12 relative in f64.  The kernel sums
+the O(N) pair terms in a lane-tree order with FMA-contracted r^2, the reference sums them sequentially; everything
+else (RNG stream, positions, accept decisions, bookkeeping) is arithmetic-identical, which the SUM_TREE tests pin
+bit for bit by letting the oracle add the pair terms in the kernel's order."""
+import numpy as np
+import pytest
+
+from sad_monte_carlo_b200 import WalkerEngine, make_config, _abi
+from tests.gpu_common import assert_walker_equal, clone_config
+from tests.oracle_lib import OracleMC
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+FLAG_SUM_TREE = 2
+
+
+def lj_cfg(N=31, R=2.5, method="sad", lanes=8, **kw):
+    base = dict(N=N, lj_radius=R, sad_min_T=0.01, energy_bin=0.01, max_allowed_energy=0.0, move_value=0.05,
+                n_walkers=16, seed=0, init_mode=_abi.INIT_RANDOMIZE, lanes_per_walker=lanes,
+                bin_window_lo=-8.0 * N, bin_window_hi=0.1)
+    base.update(kw)
+    return make_config("lj", method, **base)
+
+
+@pytest.mark.parametrize("N,R,lanes", [(31, 2.5, 32), (31, 2.5, 8), (31, 2.5, 16), (31, 2.5, 4), (38, 3.0, 8),
+                                       (38, 3.0, 32), (13, 2.0, 4), (7, 2.0, 8)])
+def test_lj_sad_trajectory_bit_exact_with_tree_ordered_oracle(N, R, lanes):
+    cfg = lj_cfg(N=N, R=R, lanes=lanes, flags=FLAG_SUM_TREE)
+    eng = WalkerEngine(cfg)
+    walkers = (0, 5, 15)
+    oracles = {w: OracleMC(cfg, walker=w) for w in walkers}
+    for w, o in oracles.items():
+        assert_walker_equal(eng, w, o, exact=True, context="init")
+    for n in (1000, 30000):
+        eng.run(n)
+        for w, o in oracles.items():
+            o.run(n)
+            assert_walker_equal(eng, w, o, exact=True, context="N=%d G=%d after %d" % (N, lanes, eng.num_moves()))
+
+
+@pytest.mark.parametrize("method,kw", [("samc", dict(samc_t0=1e4)), ("wl", dict(min_allowed_energy=-110.0)),
+                                       ("inv-t-wl", dict(min_allowed_energy=-110.0)),
+                                       ("canonical", dict(canonical_T=0.3))])
+def test_lj31_other_methods_bit_exact_with_tree_ordered_oracle(method, kw):
+    cfg = lj_cfg(method=method, flags=FLAG_SUM_TREE, energy_bin=0.5, **kw)
+    eng = WalkerEngine(cfg)
+    oracles = {w: OracleMC(cfg, walker=w) for w in (0, 9)}
+    for n in (2000, 40000):
+        eng.run(n)
+        for w, o in oracles.items():
+            o.run(n)
+            assert_walker_equal(eng, w, o, exact=True, context="%s after %d" % (method, eng.num_moves()))
+
+
+def test_lj31_per_move_energy_within_1e12_of_reference_order():
+    """The parity claim proper: same configuration + same RNG state -> proposed energy within 1e-12 relative of
+    the reference-order (sequential, no FMA) sum, for 3000 consecutive proposals along a SAD trajectory."""
+    cfg = lj_cfg(n_walkers=4, lanes=8)
+    eng = WalkerEngine(cfg)
+    o = OracleMC(cfg, walker=1)
+    worst = 0.0
+    rng = np.random.default_rng(0)
+    for step in range(3000):
+        # put the GPU walker exactly where the oracle is
+        eng.set_system(1, o.system())
+        st = o.walker()
+        rngs = eng.rngs()
+        rngs[1] = (st.rng_s0, st.rng_s1)
+        eng.set_rngs(rngs)
+        scale = 0.05 if step % 3 else 0.3
+        eg, eo = eng.plan_move(1, scale), o.plan_move(scale)
+        assert (eg is None) == (eo is None)
+        if eo is not None:
+            worst = max(worst, abs(eg - eo) / max(1.0, abs(eo)))
+            assert abs(eg - eo) <= RTOL * max(1.0, abs(eo)), (step, eg, eo)
+            if eo < o.energy() or rng.random() < 0.3:
+                o.confirm()
+    assert worst < RTOL
+    print("worst relative per-move energy error: %.3g" % worst)
+
+
+def test_lj31_sad_trajectory_tracks_reference_order_oracle():
+    """Reference-order oracle vs kernel over a whole SAD run: energies stay within 1e-12 and, because a 1e-13
+    perturbation almost never flips a bin index or an accept test, the histograms are identical."""
+    cfg = lj_cfg(n_walkers=16, lanes=8)
+    eng = WalkerEngine(cfg)
+    oracles = {w: OracleMC(cfg, walker=w) for w in (0, 3)}
+    eng.run(50000)
+    for w, o in oracles.items():
+        o.run(50000)
+        g, s = eng.walker(w), o.walker()
+        assert abs(g.energy - s.energy) <= RTOL * abs(s.energy)
+        assert (g.rng_s0, g.rng_s1) == (s.rng_s0, s.rng_s1)
+        assert g.accepted_moves == s.accepted_moves
+        gb, ob = eng.bins(w), o.bins()
+        assert np.array_equal(gb["histogram"], ob["histogram"])
+        assert np.allclose(gb["lnw"], ob["lnw"], rtol=1e-12, atol=1e-12)
+        assert np.allclose(gb["energy_total"], ob["energy_total"], rtol=1e-12)
+        assert np.allclose(eng.system(w)[:-2], o.system()[:-2], rtol=0, atol=0)  # positions: identical arithmetic
+
+
+@pytest.mark.parametrize("N", [3, 50])
+def test_lj_verify_energy_like_the_reference_test(N):
+    # src/system/lj.rs:380-434, through the trait shims
+    radius = 10.0 * N ** (1.0 / 3.0)
+    cfg = make_config("lj", "sad", N=N, lj_radius=radius, n_walkers=2, seed=1, init_mode=_abi.INIT_RANDOMIZE,
+                      lanes_per_walker=32, bin_window_lo=-8.0 * N, bin_window_hi=1e7, energy_bin=1e3)
+    eng = WalkerEngine(cfg)
+    assert abs(eng.energy(0) - eng.compute_energy(0)) <= abs(eng.energy(0)) * 1e-14 * N * N + 1e-300
+    old = eng.energy(0)
+    maxe = N * 16.0
+    done = 0
+    tries = 0
+    while done < 150 and tries < 3000:
+        tries += 1
+        e = eng.plan_move(0, 1.0)
+        if e is not None and (e < maxe or e < old):
+            eng.confirm(0)
+            assert eng.verify_energy(0)
+            old = e
+            done += 1
+    assert done > 20
+
+
+def test_lj_hard_wall_returns_none():
+    cfg = lj_cfg(N=7, R=2.0, n_walkers=2, lanes=8)
+    eng = WalkerEngine(cfg)
+    nones = sum(eng.plan_move(0, 3.0) is None for _ in range(200))
+    assert nones > 50
