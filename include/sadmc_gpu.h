@@ -92,6 +92,10 @@ typedef enum {
 
 #define SADMC_FLAG_NO_ROUND_TRIPS 1u /* skip energy.rs:950-965 diagnostics (never read by the sampler) */
 #define SADMC_FLAG_SUM_TREE 2u       /* reserved (oracle only): sum LJ pair terms in the kernel's lane order */
+/* LJ, lanes_per_walker = 1 only: FMA-contracted pair arithmetic with a Newton reciprocal and a
+ * warp-cooperative energy recomputation instead of the reference's exact operation order.
+ * Per-move energies then agree with the reference to <= 1e-12 relative instead of bit for bit. */
+#define SADMC_FLAG_FAST_MATH 4u
 
 typedef struct sadmc_config {
   uint32_t abi_version; /* = SADMC_ABI_VERSION */
@@ -136,7 +140,8 @@ typedef struct sadmc_config {
    * SADMC_ERR_WINDOW.  NaN = derive from min/max_allowed_energy and the
    * system's lowest_possible_energy(). */
   double bin_window_lo, bin_window_hi;
-  int32_t lanes_per_walker; /* LJ only: 0 = auto, else 32,16,8,4 (threads cooperating on one walker) */
+  int32_t lanes_per_walker; /* LJ only: 0 = auto; 32/16/8/4 = that many lanes of a warp cooperate on one walker
+                               (registers + shuffles); 1 = one thread per walker, cluster in shared memory */
   uint32_t flags;
 } sadmc_config;
 

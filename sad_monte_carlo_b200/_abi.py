@@ -21,6 +21,8 @@ METHOD_NAMES = {"sad": METHOD_SAD, "samc": METHOD_SAMC, "wl": METHOD_WL, "inv-t-
 MOVE_TRANSLATION_SCALE, MOVE_ACCEPTANCE_RATE = 0, 1
 INIT_REFERENCE, INIT_RANDOMIZE, INIT_EXTERNAL = 0, 1, 2
 FLAG_NO_ROUND_TRIPS = 1
+FLAG_SUM_TREE = 2
+FLAG_FAST_MATH = 4
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WINDOW, ERR_UNSUPPORTED, ERR_VERIFY = 0, -1, -2, -3, -4, -5
 

@@ -318,7 +318,7 @@ struct Book {
   }
 
   // ---- SAD part of update_weights (energy.rs:523-636) ------------------------
-  __device__ __noinline__ void sad_extend_range(double energy, unsigned long long moves) {
+  __device__ __forceinline__ void sad_extend_range(double energy, unsigned long long moves) {
     // Reached when histogram[i] just exceeded highest_hist AND energy lies outside [too_lo, too_hi].
     flush();
     const int i = ci;
@@ -391,13 +391,13 @@ struct Book {
 
   // ---- WL part of update_weights (energy.rs:638-752) -------------------------
   // Number of visited bins whose WL hist is <= wl_lowest, by a full scan (rare).
-  __device__ __noinline__ long long wl_count_low() {
+  __device__ __forceinline__ long long wl_count_low() {
     long long n = 0;
     for (int j = lo; j < lo + len; j++)
       if (rec[j].hist != 0 && P.wl_hist[side(j)] <= wl_lowest) n++;
     return n;
   }
-  __device__ __noinline__ void wl_regroup(unsigned long long moves) {
+  __device__ __forceinline__ void wl_regroup(unsigned long long moves) {
     // energy.rs:656-687: hist.len() != lnw.len()
     flush();
     if (wl_hist_len == 0 || (wl_gamma != 1.0 && wl_lowest > 0)) {

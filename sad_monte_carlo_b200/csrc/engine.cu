@@ -20,6 +20,7 @@
 #include "rng.cuh"
 #include "sys_ising.cuh"
 #include "sys_lj.cuh"
+#include "sys_lj_thread.cuh"
 
 using namespace sadmc;
 
@@ -109,15 +110,23 @@ static int pick_kernels(sadmc_engine* e) {
     case SADMC_SYS_ISING: e->ks = make_set<IsingSys>(P); return 0;
     case SADMC_SYS_LJ: {
       int G = c.lanes_per_walker;
-      if (G == 0) G = 8;
+      if (G == 0) G = c.n_walkers >= 16384 ? 1 : (c.n_walkers >= 4096 ? 8 : 32);
+      if (G == 1) {
+        if (c.N > 64) return fail(SADMC_ERR_UNSUPPORTED, "lj: thread-per-walker kernel holds N <= 64 atoms (N=%u)", c.N);
+        if (c.flags & SADMC_FLAG_FAST_MATH)
+          e->ks = make_set<LjThreadSys<true>>(P);
+        else
+          e->ks = make_set<LjThreadSys<false>>(P);
+        return 0;
+      }
       const int A = ((int)c.N + G - 1) / G;
 #define LJ_CASE(g, a)                          \
   if (G == g && A == a) {                      \
     e->ks = make_set<LjSys<g, a>>(P);          \
     return 0;                                  \
   }
-      LJ_CASE(32, 1) LJ_CASE(32, 2) LJ_CASE(16, 1) LJ_CASE(16, 2) LJ_CASE(16, 3) LJ_CASE(8, 1) LJ_CASE(8, 2) LJ_CASE(8, 3) LJ_CASE(8, 4)
-      LJ_CASE(8, 5) LJ_CASE(4, 1) LJ_CASE(4, 2) LJ_CASE(4, 4) LJ_CASE(4, 8) LJ_CASE(4, 10)
+      LJ_CASE(32, 1) LJ_CASE(32, 2) LJ_CASE(16, 2) LJ_CASE(16, 3) LJ_CASE(8, 1) LJ_CASE(8, 2) LJ_CASE(8, 4) LJ_CASE(8, 5) LJ_CASE(4, 4)
+      LJ_CASE(4, 8)
 #undef LJ_CASE
       return fail(SADMC_ERR_UNSUPPORTED, "lj: no kernel instance for N=%u with lanes_per_walker=%d (atoms per lane %d)", c.N, G, A);
     }

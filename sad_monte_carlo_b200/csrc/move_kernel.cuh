@@ -88,7 +88,7 @@ __device__ void first_bin(const DevParams& P, uint32_t w, WalkerRec& r, double e
 // `from_params` for every walker: optional randomize, the downhill relaxation
 // (energy.rs:840-851), then the first bin.
 template <class Sys>
-__global__ void __launch_bounds__(Sys::BLOCK) init_kernel(const DevParams P, unsigned long long seed0, int init_mode, long long k_base,
+__global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) init_kernel(const DevParams P, unsigned long long seed0, int init_mode, long long k_base,
                                                          int method_param, double samc_t0, unsigned long long max_relax) {
   extern __shared__ __align__(16) unsigned char smem[];
   const double* zx = stage_zig(P, smem);
@@ -125,26 +125,33 @@ __global__ void __launch_bounds__(Sys::BLOCK) init_kernel(const DevParams P, uns
 }
 
 template <class Sys, int METHOD>
-__global__ void __launch_bounds__(Sys::BLOCK) move_kernel(const DevParams P, unsigned long long moves0, unsigned long long n_moves) {
+__global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const DevParams P, unsigned long long moves0, unsigned long long n_moves) {
   extern __shared__ __align__(16) unsigned char smem[];
   const double* zx = stage_zig(P, smem);
   const double* zf = zx + SADMC_ZIG_TABLE_LEN;
   constexpr int G = Sys::G;
   const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t w = tid / G;
+  const uint32_t w_raw = tid / G;
   const int lane = (int)(tid % G);
-  if (w >= P.n_walkers) return;
-  const unsigned gmask = group_mask<G>();
+  // Systems whose rare paths are warp-cooperative (Sys::COOP) keep every thread of the
+  // block alive: threads past the last walker become ghosts that only take part in
+  // the cooperative steps.
+  const bool ghost = w_raw >= P.n_walkers;
+  if (ghost && !Sys::COOP) return;
+  const uint32_t w = ghost ? P.n_walkers - 1 : w_raw;
+  const unsigned gmask = Sys::COOP ? 0xffffffffu : group_mask<G>();
   WalkerRec& wr = P.walkers[w];
-  if (wr.status != 0) return; // a walker that left the window stays halted
+  bool halted = ghost || wr.status != 0; // a walker that left the window stays halted
+  if (halted && !Sys::COOP) return;
   Sys sys(P, w, lane, gmask, smem + ZIG_SMEM_BYTES);
   sys.load(P, w, wr);
-  Book<METHOD, G> bk(P, w, lane == 0, gmask);
+  sys.set_cooperative(true);
+  Book<METHOD, G> bk(P, w, lane == 0 && !ghost, gmask);
   bk.load(wr);
   Rng rng;
   rng.s0 = wr.s0;
   rng.s1 = wr.s1;
-  bk.load_bin(bk.widx(sys.energy()));
+  if (!halted) bk.load_bin(bk.widx(sys.energy()));
 
   unsigned long long moves = moves0;
 #pragma unroll 1
@@ -152,79 +159,94 @@ __global__ void __launch_bounds__(Sys::BLOCK) move_kernel(const DevParams P, uns
     moves += 1; // energy.rs:905
     const double e1 = sys.energy();
     const int i1 = bk.ci;
-    const double recent_scale = sqrt(1.0 / (double)moves); // energy.rs:913
-    bk.acc_rate *= 1.0 - recent_scale;
-    double e2;
-    int inew = i1;
-    if (sys.plan_move(rng, bk.tscale, zx, zf, e2)) { // energy.rs:915
-      bool out_of_bounds = false;
-      if (P.has_max) out_of_bounds = e2 > P.max_allowed && e2 > e1;
-      if (P.has_min) out_of_bounds = out_of_bounds || (e2 < P.min_allowed && e2 < e1);
-      if (!out_of_bounds) {
-        if (!bk.prepare_for_state(e2)) { // energy.rs:925
-          bk.status = SADMC_ERR_WINDOW;
-          break;
-        }
-        const int i2 = bk.widx(e2);
-        double lnw2;
-        unsigned long long hist2;
-        BinRec r2;
-        if (i2 == i1) {
-          lnw2 = bk.c_lnw;
-          hist2 = bk.c_hist;
-        } else {
-          r2 = bk.rec[i2];
-          lnw2 = r2.lnw;
-          hist2 = r2.hist;
-        }
-        if (!bk.reject_move(e1, e2, i2, lnw2, hist2, moves, rng)) { // energy.rs:927-931
-          bk.accepted += 1;
-          bk.acc_rate += recent_scale;
-          sys.confirm();
-          const double e_now = sys.energy();
-          inew = e_now == e2 ? i2 : bk.widx(e_now); // set_energy may have recomputed E (lj.rs:117-120)
-          if (inew != i1) {
-            bk.flush();
-            if (inew == i2) {
-              bk.ci = i2;
-              bk.c_lnw = r2.lnw;
-              bk.c_hist = r2.hist;
-              bk.c_etot = r2.etot;
-              bk.c_e2 = r2.e2tot;
-              if (METHOD == SADMC_METHOD_WL) bk.c_wlh = P.wl_hist[bk.side(i2)];
-              bk.c_visited = bk.visited_flag(i2);
+    double recent_scale = 0.0, e2 = 0.0;
+    bool accepted = false;
+    int i2 = i1;
+    BinRec r2;
+    r2.lnw = 0.0;
+    r2.hist = 0;
+    r2.etot = 0.0;
+    r2.e2tot = 0.0;
+    if (!halted) {
+      recent_scale = sqrt(1.0 / (double)moves); // energy.rs:913
+      bk.acc_rate *= 1.0 - recent_scale;
+      if (sys.plan_move(rng, bk.tscale, zx, zf, e2)) { // energy.rs:915
+        bool out_of_bounds = false;
+        if (P.has_max) out_of_bounds = e2 > P.max_allowed && e2 > e1;
+        if (P.has_min) out_of_bounds = out_of_bounds || (e2 < P.min_allowed && e2 < e1);
+        if (!out_of_bounds) {
+          if (!bk.prepare_for_state(e2)) { // energy.rs:925
+            bk.status = SADMC_ERR_WINDOW;
+            halted = true;
+          } else {
+            i2 = bk.widx(e2);
+            double lnw2;
+            unsigned long long hist2;
+            if (i2 == i1) {
+              lnw2 = bk.c_lnw;
+              hist2 = bk.c_hist;
             } else {
-              if (inew < bk.lo || inew >= bk.lo + bk.len) {
-                bk.status = SADMC_ERR_WINDOW;
-                break;
-              }
-              bk.load_bin(inew);
+              r2 = bk.rec[i2];
+              lnw2 = r2.lnw;
+              hist2 = r2.hist;
+            }
+            if (!bk.reject_move(e1, e2, i2, lnw2, hist2, moves, rng)) { // energy.rs:927-931
+              accepted = true;
+              bk.accepted += 1;
+              bk.acc_rate += recent_scale;
+              sys.confirm();
             }
           }
         }
       }
     }
-    const double energy = sys.energy(); // energy.rs:934
-    const bool first_visit = bk.c_hist == 0;
-    if (first_visit) { // energy.rs:938-940
-      if (bk.writer) P.t_found[bk.side(bk.ci)] = moves;
-      if (METHOD == SADMC_METHOD_SAD && bk.ci >= bk.ilo && bk.ci <= bk.ihi) bk.tfmax = moves;
-    }
-    bk.c_hist += 1;
-    bk.c_etot += energy;
-    bk.c_e2 += energy * energy;
-    {
-      double xv;
-      if (sys.extra(moves, xv) && bk.writer) { // energy.rs:944-946, Bins::accumulate_extra 374-386
-        P.extra_count[bk.side(bk.ci)] += 1;
-        P.extra_total[bk.side(bk.ci)] += xv;
+    if (Sys::COOP) sys.finish_move(); // converged point: warp-cooperative energy recomputation
+    if (accepted) {
+      const double e_now = sys.energy();
+      const int inew = e_now == e2 ? i2 : bk.widx(e_now); // set_energy may have recomputed E (lj.rs:117-120)
+      if (inew != i1) {
+        bk.flush();
+        if (inew == i2) {
+          bk.ci = i2;
+          bk.c_lnw = r2.lnw;
+          bk.c_hist = r2.hist;
+          bk.c_etot = r2.etot;
+          bk.c_e2 = r2.e2tot;
+          if (METHOD == SADMC_METHOD_WL) bk.c_wlh = P.wl_hist[bk.side(i2)];
+          bk.c_visited = bk.visited_flag(i2);
+        } else if (inew < bk.lo || inew >= bk.lo + bk.len) {
+          bk.status = SADMC_ERR_WINDOW;
+          halted = true;
+        } else {
+          bk.load_bin(inew);
+        }
       }
     }
-    if (METHOD == SADMC_METHOD_SAD) bk.update_weights_sad(energy, moves); // energy.rs:948
-    if (METHOD == SADMC_METHOD_SAMC) bk.c_lnw += bk.gamma(moves);
-    if (METHOD == SADMC_METHOD_WL) bk.update_weights_wl(energy, moves, first_visit);
-    bk.round_trips(i1 - bk.lo, moves); // energy.rs:950-965
+    if (!halted) {
+      const double energy = sys.energy(); // energy.rs:934
+      const bool first_visit = bk.c_hist == 0;
+      if (first_visit) { // energy.rs:938-940
+        if (bk.writer) P.t_found[bk.side(bk.ci)] = moves;
+        if (METHOD == SADMC_METHOD_SAD && bk.ci >= bk.ilo && bk.ci <= bk.ihi) bk.tfmax = moves;
+      }
+      bk.c_hist += 1;
+      bk.c_etot += energy;
+      bk.c_e2 += energy * energy;
+      {
+        double xv;
+        if (sys.extra(moves, xv) && bk.writer) { // energy.rs:944-946, Bins::accumulate_extra 374-386
+          P.extra_count[bk.side(bk.ci)] += 1;
+          P.extra_total[bk.side(bk.ci)] += xv;
+        }
+      }
+      if (METHOD == SADMC_METHOD_SAD) bk.update_weights_sad(energy, moves); // energy.rs:948
+      if (METHOD == SADMC_METHOD_SAMC) bk.c_lnw += bk.gamma(moves);
+      if (METHOD == SADMC_METHOD_WL) bk.update_weights_wl(energy, moves, first_visit);
+      bk.round_trips(i1 - bk.lo, moves); // energy.rs:950-965
+    }
   }
+  if (ghost) return;
+  if (wr.status != 0) return; // was halted before this launch: leave its state alone
   bk.store(wr);
   sys.store(P, w, wr, lane == 0);
   if (lane == 0) {

@@ -64,7 +64,7 @@ struct Rng {
 
   // rand_distr 0.2 StandardNormal (ziggurat, symmetric); zx/zf are the 257-entry
   // tables staged in shared memory.  (src/rng.rs:111-117, fake.rs:131, erfinv.rs:104)
-  __host__ __device__ __noinline__ double normal_slow(const double* zx, const double* zf, uint32_t i, double u, double x) {
+  __host__ __device__ __forceinline__ double normal_slow(const double* zx, const double* zf, uint32_t i, double u, double x) {
     for (;;) {
       if (i == 0) {
         double xx = 1.0, yy = 0.0;

@@ -16,6 +16,10 @@ namespace sadmc {
 struct IsingSys {
   static constexpr int G = 1;
   static constexpr int BLOCK = 128;
+  static constexpr int MIN_BLOCKS = 4;
+  static constexpr bool COOP = false;
+  __device__ __forceinline__ void set_cooperative(bool) {}
+  __device__ __forceinline__ void finish_move() {}
   uint32_t* sp; // this thread's words: sp[k * stride]
   int stride, N, words;
   int E, ch_site, ch_e;

@@ -25,6 +25,10 @@ struct LjSys {
   static constexpr int G = G_;
   static constexpr int A = A_;
   static constexpr int BLOCK = 128;
+  static constexpr int MIN_BLOCKS = 4;
+  static constexpr bool COOP = false;
+  __device__ __forceinline__ void set_cooperative(bool) {}
+  __device__ __forceinline__ void finish_move() {}
   double px[A], py[A], pz[A];
   double E, err;
   int N, lane;

@@ -129,3 +129,72 @@ def test_lj_hard_wall_returns_none():
     eng = WalkerEngine(cfg)
     nones = sum(eng.plan_move(0, 3.0) is None for _ in range(200))
     assert nones > 50
+
+
+# ---- one thread per walker (lanes_per_walker = 1), cluster resident in shared memory ----------------------------
+
+@pytest.mark.parametrize("N,R,walkers", [(31, 2.5, 70), (38, 3.0, 33), (7, 2.0, 64)])
+def test_lj_thread_per_walker_exact_mode_is_bit_exact_with_the_reference_order_oracle(N, R, walkers):
+    """EXACT arithmetic: sequential pair sum, IEEE divide, no FMA == the reference's own operation order, so the
+    plain (reference-order) oracle must agree bit for bit -- positions, energies, lnw, histograms, RNG state."""
+    cfg = lj_cfg(N=N, R=R, lanes=1, n_walkers=walkers)
+    eng = WalkerEngine(cfg)
+    ws = (0, 31, walkers - 1)
+    oracles = {w: OracleMC(cfg, walker=w) for w in ws}
+    for w, o in oracles.items():
+        assert_walker_equal(eng, w, o, exact=True, context="init")
+    for n in (1500, 40000):
+        eng.run(n)
+        for w, o in oracles.items():
+            o.run(n)
+            assert_walker_equal(eng, w, o, exact=True, context="N=%d thread/walker after %d" % (N, eng.num_moves()))
+
+
+@pytest.mark.parametrize("method,kw", [("samc", dict(samc_t0=1e4)), ("wl", dict(min_allowed_energy=-110.0)),
+                                       ("canonical", dict(canonical_T=0.3))])
+def test_lj_thread_per_walker_exact_other_methods(method, kw):
+    cfg = lj_cfg(method=method, lanes=1, n_walkers=40, energy_bin=0.5, **kw)
+    eng = WalkerEngine(cfg)
+    oracles = {w: OracleMC(cfg, walker=w) for w in (0, 39)}
+    eng.run(30000)
+    for w, o in oracles.items():
+        o.run(30000)
+        assert_walker_equal(eng, w, o, exact=True, context=method)
+
+
+def test_lj_thread_per_walker_fast_math_per_move_energy_within_1e12():
+    cfg = lj_cfg(n_walkers=4, lanes=1, flags=_abi.FLAG_FAST_MATH)
+    eng = WalkerEngine(cfg)
+    o = OracleMC(lj_cfg(n_walkers=4, lanes=1), walker=1)
+    worst = 0.0
+    rng = np.random.default_rng(1)
+    for step in range(2500):
+        eng.set_system(1, o.system())
+        st = o.walker()
+        rngs = eng.rngs()
+        rngs[1] = (st.rng_s0, st.rng_s1)
+        eng.set_rngs(rngs)
+        scale = 0.05 if step % 3 else 0.3
+        eg, eo = eng.plan_move(1, scale), o.plan_move(scale)
+        assert (eg is None) == (eo is None)
+        if eo is not None:
+            worst = max(worst, abs(eg - eo) / max(1.0, abs(eo)))
+            assert abs(eg - eo) <= RTOL * max(1.0, abs(eo)), (step, eg, eo)
+            if eo < o.energy() or rng.random() < 0.3:
+                o.confirm()
+    print("fast-math worst relative per-move energy error: %.3g" % worst)
+
+
+def test_lj_thread_per_walker_fast_math_tracks_reference_trajectory():
+    cfg = lj_cfg(n_walkers=100, lanes=1, flags=_abi.FLAG_FAST_MATH)
+    eng = WalkerEngine(cfg)
+    oracles = {w: OracleMC(lj_cfg(n_walkers=100, lanes=1), walker=w) for w in (0, 50, 99)}
+    eng.run(60000)  # long enough for several warp-cooperative energy recomputations per walker
+    for w, o in oracles.items():
+        o.run(60000)
+        g, s = eng.walker(w), o.walker()
+        assert abs(g.energy - s.energy) <= RTOL * abs(s.energy)
+        assert (g.rng_s0, g.rng_s1) == (s.rng_s0, s.rng_s1)
+        assert np.array_equal(eng.bins(w)["histogram"], o.bins()["histogram"])
+        assert np.allclose(eng.system(w)[:-2], o.system()[:-2], rtol=0, atol=0)
+        assert abs(eng.compute_energy(w) - g.energy) <= 1e-14 * 31 * 31 * abs(g.energy)
