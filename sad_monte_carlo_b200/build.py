@@ -40,7 +40,8 @@ def needs_build():
 def build(force=False, verbose=False, extra=()):
     if not force and not needs_build():
         return OUT
-    cmd = ["nvcc"] + NVCC_FLAGS + list(extra) + ["-o", OUT] + SRC
+    extra = list(extra) + os.environ.get("SADMC_NVCC_EXTRA", "").split()
+    cmd = ["nvcc"] + NVCC_FLAGS + extra + ["-o", OUT] + SRC
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd, cwd=HERE)

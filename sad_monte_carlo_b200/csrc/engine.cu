@@ -125,8 +125,10 @@ static int pick_kernels(sadmc_engine* e) {
     e->ks = make_set<LjSys<g, a>>(P);          \
     return 0;                                  \
   }
+#ifndef SADMC_LEAN /* -DSADMC_LEAN: experiment builds with only the thread-per-walker LJ kernels */
       LJ_CASE(32, 1) LJ_CASE(32, 2) LJ_CASE(16, 2) LJ_CASE(16, 3) LJ_CASE(8, 1) LJ_CASE(8, 2) LJ_CASE(8, 4) LJ_CASE(8, 5) LJ_CASE(4, 4)
       LJ_CASE(4, 8)
+#endif
 #undef LJ_CASE
       return fail(SADMC_ERR_UNSUPPORTED, "lj: no kernel instance for N=%u with lanes_per_walker=%d (atoms per lane %d)", c.N, G, A);
     }
