@@ -161,7 +161,7 @@ def run_ours(args):
     lib = load_library()
     W = args.walkers
     cfg = lj31_config(W, walker_offset=rank * W, device=local, lanes=args.lanes,
-                      flags=(1 if args.no_round_trips else 0))
+                      flags=(1 if args.no_round_trips else 0) | (0 if args.exact else 4))
     eng = WalkerEngine(cfg)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
@@ -254,7 +254,8 @@ def run_ours(args):
             "metric": "LJ31 SAD MC moves/sec", "value": value, "unit": "moves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(W, args.moves_per_step, lanes_per_walker=eng.cfg.lanes_per_walker or 8,
+            "config": workload_config(W, args.moves_per_step, lanes_per_walker=args.lanes,
+                                      arithmetic="exact (reference operation order)" if args.exact else "fast-math (<= 1e-12 rel. per move)",
                                       burn_in_moves=args.burn_in, round_trip_diagnostics=not args.no_round_trips),
             "clocks": clocks, "gpu_launches": int(gpu_launches),
             "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -289,11 +290,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--walkers", type=int, default=int(os.environ.get("SADMC_BENCH_WALKERS", 32768)), help="walkers per GPU")
+    ap.add_argument("--walkers", type=int, default=int(os.environ.get("SADMC_BENCH_WALKERS", 75776)), help="walkers per GPU")
     ap.add_argument("--moves-per-step", type=int, default=int(os.environ.get("SADMC_BENCH_MOVES", 20000)))
     ap.add_argument("--burn-in", type=int, default=int(os.environ.get("SADMC_BENCH_BURN_IN", 200000)))
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("SADMC_BENCH_LANES", 0)))
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("SADMC_BENCH_LANES", 1)))
     ap.add_argument("--no-round-trips", action="store_true")
+    ap.add_argument("--exact", action="store_true", help="reference operation order (bit-exact vs the oracle) instead of fast-math")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--cpu-moves-per-step", type=int, default=2000000)

@@ -111,14 +111,25 @@ static int pick_kernels(sadmc_engine* e) {
     case SADMC_SYS_LJ: {
       int G = c.lanes_per_walker;
       if (G == 0) G = c.n_walkers >= 16384 ? 1 : (c.n_walkers >= 4096 ? 8 : 32);
-      if (G == 1) {
-        if (c.N > 64) return fail(SADMC_ERR_UNSUPPORTED, "lj: thread-per-walker kernel holds N <= 64 atoms (N=%u)", c.N);
-        if (c.flags & SADMC_FLAG_FAST_MATH)
-          e->ks = make_set<LjThreadSys<true>>(P);
-        else
-          e->ks = make_set<LjThreadSys<false>>(P);
-        return 0;
+      const bool fast = (c.flags & SADMC_FLAG_FAST_MATH) != 0;
+      if (G == 1 || (fast && (G == 2 || G == 4))) { // configuration in shared memory (sys_lj_thread.cuh)
+        if (c.N > 64) return fail(SADMC_ERR_UNSUPPORTED, "lj: shared-memory kernels hold N <= 64 atoms (N=%u)", c.N);
+#define LJT_CASE(nt)                                                  \
+  if (c.N == nt || nt == 0) {                                         \
+    if (!fast)                                                        \
+      e->ks = make_set<LjThreadSys<false, nt, 1>>(P);                 \
+    else if (G == 1)                                                  \
+      e->ks = make_set<LjThreadSys<true, nt, 1>>(P);                  \
+    else if (G == 2)                                                  \
+      e->ks = make_set<LjThreadSys<true, nt, 2>>(P);                  \
+    else                                                              \
+      e->ks = make_set<LjThreadSys<true, nt, 4>>(P);                  \
+    return 0;                                                         \
+  }
+        LJT_CASE(31) LJT_CASE(38) LJT_CASE(0)
+#undef LJT_CASE
       }
+      if (G == 2) return fail(SADMC_ERR_UNSUPPORTED, "lj: lanes_per_walker = 2 needs SADMC_FLAG_FAST_MATH");
       const int A = ((int)c.N + G - 1) / G;
 #define LJ_CASE(g, a)                          \
   if (G == g && A == a) {                      \

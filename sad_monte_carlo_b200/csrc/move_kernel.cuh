@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
   const bool ghost = w_raw >= P.n_walkers;
   if (ghost && !Sys::COOP) return;
   const uint32_t w = ghost ? P.n_walkers - 1 : w_raw;
-  const unsigned gmask = Sys::COOP ? 0xffffffffu : group_mask<G>();
+  const unsigned gmask = group_mask<G>();
   WalkerRec& wr = P.walkers[w];
   bool halted = ghost || wr.status != 0; // a walker that left the window stays halted
   if (halted && !Sys::COOP) return;
