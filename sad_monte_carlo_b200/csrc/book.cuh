@@ -30,11 +30,24 @@
 
 namespace sadmc {
 
-struct __align__(32) BinRec {
+// One energy bin of one walker: 64 bytes = two 32-byte sectors of the same 64-byte DRAM atom.
+// The first sector is what every proposal needs (lnw, histogram) and what every move updates;
+// the second holds what is touched on first visits / bin changes only.
+struct __align__(32) BinLo {
   double lnw;
   unsigned long long hist;
   double etot;
   double e2tot;
+};
+struct __align__(32) BinHi {
+  unsigned long long t_found;
+  unsigned long long rt_stamp;    // move at which have_visited_since_maxentropy[i] was last set individually
+  unsigned long long round_trips; // stored minus one (new bins start at 1, energy.rs:418,432)
+  unsigned long long wl_hist;     // Method::WL::hist
+};
+struct __align__(64) BinRec {
+  BinLo lo;
+  BinHi hi;
 };
 
 // Per-walker scalars as they sit in HBM between launches.
@@ -71,10 +84,6 @@ struct __align__(16) WalkerRec {
 
 struct DevParams {
   BinRec* rec;
-  unsigned long long* t_found;
-  unsigned long long* rt_stamp;
-  unsigned long long* round_trips; // stored minus one (new bins start at 1, energy.rs:418,432)
-  unsigned long long* wl_hist;
   double* extra_total;
   unsigned long long* extra_count;
   WalkerRec* walkers;
@@ -136,8 +145,8 @@ struct Book {
   // cached current bin
   int ci;
   double c_lnw, c_etot, c_e2;
-  unsigned long long c_hist, c_wlh;
-  bool c_visited;
+  unsigned long long c_hist, c_tfound, c_stamp, c_rt, c_wlh;
+  bool c_visited, hi_dirty;
 
   __device__ Book(const DevParams& p, uint32_t walker, bool is_writer, unsigned mask)
       : P(p), w(walker), writer(is_writer), gmask(mask), rec(p.rec + (size_t)walker * p.cap) {}
@@ -182,6 +191,7 @@ struct Book {
     rt_fill_lo = r.rt_fill_lo;
     rt_fill_hi = r.rt_fill_hi;
     ci = -1;
+    hi_dirty = false;
   }
   __device__ void store(WalkerRec& r) {
     flush();
@@ -227,35 +237,51 @@ struct Book {
   // Bins::index_to_state (energy.rs:366-370) for window index j.
   __device__ __forceinline__ double centre(int j) const { return bmin + ((double)(j - lo) + 0.5) * P.width; }
 
-  __device__ __forceinline__ bool visited_flag(int i) const {
+  __device__ __forceinline__ bool visited_flag(int i, unsigned long long stamp) const {
     if (P.flags & SADMC_FLAG_NO_ROUND_TRIPS) return true;
     if (i < rt_fill_lo || i >= rt_fill_hi) return true; // created after the last bulk fill (energy.rs:417,431)
-    return P.rt_stamp[side(i)] > rt_fill_time ? true : (rt_fill_val != 0);
+    return stamp > rt_fill_time ? true : (rt_fill_val != 0);
+  }
+  // make bin i the cached current bin from an already loaded record
+  __device__ __forceinline__ void adopt_bin(int i, const BinLo& l, const BinHi& h) {
+    ci = i;
+    c_lnw = l.lnw;
+    c_hist = l.hist;
+    c_etot = l.etot;
+    c_e2 = l.e2tot;
+    c_tfound = h.t_found;
+    c_stamp = h.rt_stamp;
+    c_rt = h.round_trips;
+    c_wlh = h.wl_hist;
+    c_visited = visited_flag(i, h.rt_stamp);
+    hi_dirty = false;
   }
   __device__ __forceinline__ void load_bin(int i) {
-    const BinRec r = rec[i];
-    ci = i;
-    c_lnw = r.lnw;
-    c_hist = r.hist;
-    c_etot = r.etot;
-    c_e2 = r.e2tot;
-    if (METHOD == SADMC_METHOD_WL) c_wlh = P.wl_hist[side(i)];
-    c_visited = visited_flag(i);
+    const BinLo l = rec[i].lo;
+    const BinHi h = rec[i].hi;
+    adopt_bin(i, l, h);
   }
   __device__ __forceinline__ void flush() {
     if (ci >= 0 && writer) {
-      BinRec r;
-      r.lnw = c_lnw;
-      r.hist = c_hist;
-      r.etot = c_etot;
-      r.e2tot = c_e2;
-      rec[ci] = r;
-      if (METHOD == SADMC_METHOD_WL) P.wl_hist[side(ci)] = c_wlh;
+      BinLo l;
+      l.lnw = c_lnw;
+      l.hist = c_hist;
+      l.etot = c_etot;
+      l.e2tot = c_e2;
+      rec[ci].lo = l;
+      if (hi_dirty) {
+        BinHi h;
+        h.t_found = c_tfound;
+        h.rt_stamp = c_stamp;
+        h.round_trips = c_rt;
+        h.wl_hist = c_wlh;
+        rec[ci].hi = h;
+      }
     }
+    hi_dirty = false;
     sync();
   }
-  __device__ __forceinline__ double lnw_at(int i) const { return i == ci ? c_lnw : rec[i].lnw; }
-  __device__ __forceinline__ unsigned long long hist_at(int i) const { return i == ci ? c_hist : rec[i].hist; }
+  __device__ __forceinline__ double lnw_at(int i) const { return i == ci ? c_lnw : rec[i].lo.lnw; }
 
   // energy.rs:400-434.  Returns false when the fixed window cannot hold e.
   __device__ __forceinline__ bool prepare_for_state(double e) {
@@ -323,20 +349,20 @@ struct Book {
     flush();
     const int i = ci;
     if (energy > too_hi) {
-      const double lnw_hi = rec[ihi].lnw;
+      const double lnw_hi = rec[ihi].lo.lnw;
       // energy.rs:544-555 loops over every bin; only bins from ihi up to the walker's bin can satisfy
       // `ej > too_hi && ej <= energy`.
       for (int j = ihi; j <= i; j++) {
         const double ej = centre(j);
         if (ej > too_hi && ej <= energy) {
-          if (rec[j].hist != 0) {
-            if (writer) rec[j].lnw = lnw_hi;
+          if (rec[j].lo.hist != 0) {
+            if (writer) rec[j].lo.lnw = lnw_hi;
             num_states += 1;
           } else if (writer) {
-            rec[j].lnw = 0.0;
+            rec[j].lo.lnw = 0.0;
           }
         }
-        const unsigned long long tf = P.t_found[side(j)];
+        const unsigned long long tf = rec[j].hi.t_found;
         if (j > ihi && tf > tfmax) tfmax = tf;
       }
       latest_parameter = (energy - too_lo) / P.min_T;
@@ -344,20 +370,20 @@ struct Book {
       too_hi = centre(i);
       ihi = i;
     } else { // energy < too_lo
-      const double lnw_lo = rec[ilo].lnw;
+      const double lnw_lo = rec[ilo].lo.lnw;
       for (int j = i; j <= ilo; j++) {
         const double ej = centre(j);
         if (ej < too_lo && ej >= energy) {
-          if (rec[j].hist != 0) {
+          if (rec[j].lo.hist != 0) {
             double v = lnw_lo + (ej - too_lo) / P.min_T;
             if (v < 0.0) v = 0.0;
-            if (writer) rec[j].lnw = v;
+            if (writer) rec[j].lo.lnw = v;
             num_states += 1;
           } else if (writer) {
-            rec[j].lnw = 0.0;
+            rec[j].lo.lnw = 0.0;
           }
         }
-        const unsigned long long tf = P.t_found[side(j)];
+        const unsigned long long tf = rec[j].hi.t_found;
         if (j < ilo && tf > tfmax) tfmax = tf;
       }
       latest_parameter = (too_hi - energy) / P.min_T;
@@ -366,7 +392,7 @@ struct Book {
       ilo = i;
     }
     sync();
-    c_lnw = rec[i].lnw; // the walker's own bin may have been overwritten
+    c_lnw = rec[i].lo.lnw; // the walker's own bin may have been overwritten
   }
 
   __device__ __forceinline__ void update_weights_sad(double energy, unsigned long long moves) {
@@ -394,7 +420,7 @@ struct Book {
   __device__ __forceinline__ long long wl_count_low() {
     long long n = 0;
     for (int j = lo; j < lo + len; j++)
-      if (rec[j].hist != 0 && P.wl_hist[side(j)] <= wl_lowest) n++;
+      if (rec[j].lo.hist != 0 && rec[j].hi.wl_hist <= wl_lowest) n++;
     return n;
   }
   __device__ __forceinline__ void wl_regroup(unsigned long long moves) {
@@ -406,21 +432,21 @@ struct Book {
       wl_highest = 0;
       wl_total = 0;
       if (writer)
-        for (int j = lo; j < lo + len; j++) P.wl_hist[side(j)] = 0;
+        for (int j = lo; j < lo + len; j++) rec[j].hi.wl_hist = 0;
       wl_min_energy = bmin;
     } else {
       // the window keeps zeros where the reference pads; replay the min_energy arithmetic
       while (wl_min_energy > bmin) wl_min_energy -= P.width;
       unsigned long long mn = ~0ull;
       for (int j = lo; j < lo + len; j++) {
-        const unsigned long long h = P.wl_hist[side(j)];
+        const unsigned long long h = rec[j].hi.wl_hist;
         if (h < mn) mn = h;
       }
       wl_lowest = mn;
     }
     wl_hist_len = len;
     sync();
-    c_wlh = P.wl_hist[side(ci)];
+    c_wlh = rec[ci].hi.wl_hist;
     wl_low_count = wl_count_low();
     (void)moves;
   }
@@ -430,6 +456,7 @@ struct Book {
     if (method == SADMC_METHOD_SAMC) return; // 1/t-WL after its switch (energy.rs:754-756)
     if (P.has_min_gamma && wl_gamma < P.min_gamma) { // production run, energy.rs:649-655
       c_wlh += 1;
+      hi_dirty = true;
       return;
     }
     if (wl_hist_len != len) {
@@ -439,6 +466,7 @@ struct Book {
     }
     if (c_wlh == wl_lowest) wl_low_count -= 1; // it is about to exceed wl_lowest
     c_wlh += 1;
+    hi_dirty = true;
     if (c_wlh > wl_highest) wl_highest = c_wlh;
     wl_total += 1;
     const double max_energy = wl_min_energy + (double)wl_hist_len * P.width;
@@ -451,9 +479,10 @@ struct Book {
         wl_gamma *= 0.5;
         flush();
         if (writer)
-          for (int j = lo; j < lo + len; j++) P.wl_hist[side(j)] = 0;
+          for (int j = lo; j < lo + len; j++) rec[j].hi.wl_hist = 0;
         sync();
         c_wlh = 0;
+        hi_dirty = true;
         wl_total = 0;
         wl_lowest = 0;
         wl_highest = 0;
@@ -462,6 +491,7 @@ struct Book {
       if (rescan) {
         flush();
         wl_low_count = wl_count_low();
+        hi_dirty = true;
       }
       if (P.inv_t && wl_gamma < wl_num_states / (double)moves) {
         method = SADMC_METHOD_SAMC;
@@ -492,10 +522,9 @@ struct Book {
       }
     } else if (!c_visited) {
       c_visited = true;
-      if (writer) {
-        P.rt_stamp[side(ci)] = moves;
-        P.round_trips[side(ci)] += 1;
-      }
+      c_stamp = moves;
+      c_rt += 1;
+      hi_dirty = true;
     }
   }
 };

@@ -345,11 +345,7 @@ int sadmc_create(const sadmc_config* cfg, sadmc_engine** out) {
   CKB(cudaEventCreate(&e->ev1));
   DevParams& P = e->P;
   const size_t nb = (size_t)P.n_walkers * P.cap;
-  size_t need = nb * (sizeof(BinRec) + 8) + (size_t)P.n_walkers * (sizeof(WalkerRec) + e->sys_len * 8 + P.ising_words * 4);
-  const bool rt = !(P.flags & SADMC_FLAG_NO_ROUND_TRIPS);
-  if (rt) need += nb * 16;
-  const bool wl = cfg->method == SADMC_METHOD_WL || cfg->method == SADMC_METHOD_INV_T_WL;
-  if (wl) need += nb * 8;
+  size_t need = nb * sizeof(BinRec) + (size_t)P.n_walkers * (sizeof(WalkerRec) + e->sys_len * 8 + P.ising_words * 4);
   size_t free_b = 0, total_b = 0;
   CKB(cudaMemGetInfo(&free_b, &total_b));
   if (need > free_b) {
@@ -359,12 +355,6 @@ int sadmc_create(const sadmc_config* cfg, sadmc_engine** out) {
     return SADMC_ERR_INVALID;
   }
   BAIL(dev_alloc(e, (void**)&P.rec, nb * sizeof(BinRec), true));
-  BAIL(dev_alloc(e, (void**)&P.t_found, nb * 8, true));
-  if (rt) {
-    BAIL(dev_alloc(e, (void**)&P.rt_stamp, nb * 8, true));
-    BAIL(dev_alloc(e, (void**)&P.round_trips, nb * 8, true));
-  }
-  if (wl) BAIL(dev_alloc(e, (void**)&P.wl_hist, nb * 8, true));
   BAIL(dev_alloc(e, (void**)&P.walkers, (size_t)P.n_walkers * sizeof(WalkerRec), true));
   BAIL(dev_alloc(e, (void**)&P.sys, (size_t)P.n_walkers * (P.sys_stride ? P.sys_stride : 1) * 8, true));
   BAIL(dev_alloc(e, (void**)&P.sys_words, (size_t)P.n_walkers * (P.ising_words ? P.ising_words : 1) * 4, true));
@@ -548,50 +538,24 @@ int sadmc_get_bins(sadmc_engine* e, uint32_t w, uint32_t cap, uint64_t* histogra
   if (cap < n) return fail(SADMC_ERR_INVALID, "capacity %u < bins_len %zu", cap, n);
   const size_t base = (size_t)w * e->P.cap + (size_t)r.lo;
   std::vector<BinRec> recs(n);
-  std::vector<unsigned long long> tmp(n), stamps(n);
   CK(cudaMemcpyAsync(recs.data(), e->P.rec + base, n * sizeof(BinRec), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  for (size_t i = 0; i < n; i++) {
-    if (histogram) histogram[i] = recs[i].hist;
-    if (lnw) lnw[i] = recs[i].lnw;
-    if (energy_total) energy_total[i] = recs[i].etot;
-    if (energy_squared_total) energy_squared_total[i] = recs[i].e2tot;
-  }
-  if (t_found) {
-    CK(cudaMemcpyAsync(t_found, e->P.t_found + base, n * 8, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-  }
   const bool rt = !(e->P.flags & SADMC_FLAG_NO_ROUND_TRIPS);
-  if (round_trips) {
-    if (rt) {
-      CK(cudaMemcpyAsync(round_trips, e->P.round_trips + base, n * 8, cudaMemcpyDeviceToHost, e->stream));
-      CK(cudaStreamSynchronize(e->stream));
-      for (size_t i = 0; i < n; i++) round_trips[i] += 1; // stored minus one
-    } else
-      for (size_t i = 0; i < n; i++) round_trips[i] = 1;
-  }
-  if (have_visited) {
-    if (rt) {
-      CK(cudaMemcpyAsync(stamps.data(), e->P.rt_stamp + base, n * 8, cudaMemcpyDeviceToHost, e->stream));
-      CK(cudaStreamSynchronize(e->stream));
-      for (size_t i = 0; i < n; i++) {
-        const int j = r.lo + (int)i;
-        bool v;
-        if (j < r.rt_fill_lo || j >= r.rt_fill_hi)
-          v = true;
-        else
-          v = stamps[i] > r.rt_fill_time ? true : (r.rt_fill_val != 0);
-        have_visited[i] = v ? 1 : 0;
-      }
-    } else
-      for (size_t i = 0; i < n; i++) have_visited[i] = 1;
-  }
-  if (wl_hist) {
-    if (e->P.wl_hist && r.wl_hist_len > 0) {
-      CK(cudaMemcpyAsync(wl_hist, e->P.wl_hist + base, n * 8, cudaMemcpyDeviceToHost, e->stream));
-      CK(cudaStreamSynchronize(e->stream));
-    } else
-      for (size_t i = 0; i < n; i++) wl_hist[i] = 0;
+  for (size_t i = 0; i < n; i++) {
+    const BinRec& b = recs[i];
+    if (histogram) histogram[i] = b.lo.hist;
+    if (lnw) lnw[i] = b.lo.lnw;
+    if (energy_total) energy_total[i] = b.lo.etot;
+    if (energy_squared_total) energy_squared_total[i] = b.lo.e2tot;
+    if (t_found) t_found[i] = b.hi.t_found;
+    if (round_trips) round_trips[i] = rt ? b.hi.round_trips + 1 : 1; // stored minus one
+    if (wl_hist) wl_hist[i] = r.wl_hist_len > 0 ? b.hi.wl_hist : 0;
+    if (have_visited) {
+      const int j = r.lo + (int)i;
+      bool v = true;
+      if (rt && j >= r.rt_fill_lo && j < r.rt_fill_hi) v = b.hi.rt_stamp > r.rt_fill_time ? true : (r.rt_fill_val != 0);
+      have_visited[i] = v ? 1 : 0;
+    }
   }
   if (extra_total) {
     if (e->P.extra_total) {

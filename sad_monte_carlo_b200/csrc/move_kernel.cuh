@@ -49,12 +49,15 @@ __device__ void first_bin(const DevParams& P, uint32_t w, WalkerRec& r, double e
   }
   r.lo = (int)lo;
   BinRec b;
-  b.lnw = 0.0;
-  b.hist = 1;
-  b.etot = e0;
-  b.e2tot = e0 * e0;
+  b.lo.lnw = 0.0;
+  b.lo.hist = 1;
+  b.lo.etot = e0;
+  b.lo.e2tot = e0 * e0;
+  b.hi.t_found = 0;
+  b.hi.rt_stamp = 0;
+  b.hi.round_trips = 0;
+  b.hi.wl_hist = 0;
   P.rec[(size_t)w * P.cap + lo] = b;
-  P.t_found[(size_t)w * P.cap + lo] = 0;
   r.method = method_param == SADMC_METHOD_INV_T_WL ? SADMC_METHOD_WL : method_param;
   r.too_lo = e0;
   r.too_hi = e0;
@@ -162,11 +165,16 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
     double recent_scale = 0.0, e2 = 0.0;
     bool accepted = false;
     int i2 = i1;
-    BinRec r2;
+    BinLo r2;
+    BinHi h2;
     r2.lnw = 0.0;
     r2.hist = 0;
     r2.etot = 0.0;
     r2.e2tot = 0.0;
+    h2.t_found = 0;
+    h2.rt_stamp = 0;
+    h2.round_trips = 0;
+    h2.wl_hist = 0;
     if (!halted) {
       recent_scale = sqrt(1.0 / (double)moves); // energy.rs:913
       bk.acc_rate *= 1.0 - recent_scale;
@@ -186,7 +194,8 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
               lnw2 = bk.c_lnw;
               hist2 = bk.c_hist;
             } else {
-              r2 = bk.rec[i2];
+              r2 = bk.rec[i2].lo; // both sectors of the record are requested together: one DRAM access,
+              h2 = bk.rec[i2].hi; // and no second dependent load if the walker moves there
               lnw2 = r2.lnw;
               hist2 = r2.hist;
             }
@@ -207,13 +216,7 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
       if (inew != i1) {
         bk.flush();
         if (inew == i2) {
-          bk.ci = i2;
-          bk.c_lnw = r2.lnw;
-          bk.c_hist = r2.hist;
-          bk.c_etot = r2.etot;
-          bk.c_e2 = r2.e2tot;
-          if (METHOD == SADMC_METHOD_WL) bk.c_wlh = P.wl_hist[bk.side(i2)];
-          bk.c_visited = bk.visited_flag(i2);
+          bk.adopt_bin(i2, r2, h2);
         } else if (inew < bk.lo || inew >= bk.lo + bk.len) {
           bk.status = SADMC_ERR_WINDOW;
           halted = true;
@@ -226,7 +229,8 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
       const double energy = sys.energy(); // energy.rs:934
       const bool first_visit = bk.c_hist == 0;
       if (first_visit) { // energy.rs:938-940
-        if (bk.writer) P.t_found[bk.side(bk.ci)] = moves;
+        bk.c_tfound = moves;
+        bk.hi_dirty = true;
         if (METHOD == SADMC_METHOD_SAD && bk.ci >= bk.ilo && bk.ci <= bk.ihi) bk.tfmax = moves;
       }
       bk.c_hist += 1;
@@ -321,7 +325,7 @@ __global__ void __launch_bounds__(256) walker_max_lnw_kernel(const DevParams P, 
   const WalkerRec& r = P.walkers[w];
   double m = -1e300;
   for (int j = r.lo + (int)threadIdx.x; j < r.lo + r.len; j += blockDim.x) {
-    const BinRec b = P.rec[(size_t)w * P.cap + j];
+    const BinLo b = P.rec[(size_t)w * P.cap + j].lo;
     if (b.hist != 0 && b.lnw > m) m = b.lnw;
   }
   __shared__ double sm[256];
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(256) fold_kernel(const DevParams P, const doub
   for (uint32_t w = 0; w < P.n_walkers; w++) {
     const WalkerRec& r = P.walkers[w];
     if ((int)j < r.lo || (int)j >= r.lo + r.len) continue;
-    const BinRec b = P.rec[(size_t)w * P.cap + j];
+    const BinLo b = P.rec[(size_t)w * P.cap + j].lo;
     h += b.hist;
     et += b.etot;
     e2 += b.e2tot;

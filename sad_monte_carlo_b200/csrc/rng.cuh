@@ -64,25 +64,47 @@ struct Rng {
 
   // rand_distr 0.2 StandardNormal (ziggurat, symmetric); zx/zf are the 257-entry
   // tables staged in shared memory.  (src/rng.rs:111-117, fake.rs:131, erfinv.rs:104)
-  __host__ __device__ __forceinline__ double normal_slow(const double* zx, const double* zf, uint32_t i, double u, double x) {
+  // The rare part (tail + wedge tests, ~1.2 % of draws) is one out-of-line copy that takes and
+  // returns the generator state BY VALUE: its exp/log bodies stay out of the hot loop's
+  // instruction footprint and the state never has its address taken (it stays in registers).
+  struct SlowOut {
+    double x;
+    uint64_t s0, s1;
+  };
+  static __host__ __device__ __noinline__ SlowOut normal_slow(uint64_t s0_, uint64_t s1_, const double* zx, const double* zf, uint32_t i,
+                                                            double u, double x) {
+    Rng r;
+    r.s0 = s0_;
+    r.s1 = s1_;
+    SlowOut o;
     for (;;) {
       if (i == 0) {
         double xx = 1.0, yy = 0.0;
         while (-2.0 * yy < xx * xx) {
-          const double a = open01();
-          const double b = open01();
+          const double a = r.open01();
+          const double b = r.open01();
           xx = sadmc_log(a) / SADMC_ZIG_NORM_R;
           yy = sadmc_log(b);
         }
-        return u < 0.0 ? xx - SADMC_ZIG_NORM_R : SADMC_ZIG_NORM_R - xx;
+        o.x = u < 0.0 ? xx - SADMC_ZIG_NORM_R : SADMC_ZIG_NORM_R - xx;
+        break;
       }
-      if (zf[i + 1] + (zf[i] - zf[i + 1]) * gen_f64() < sadmc_exp(-x * x / 2.0)) return x;
-      const uint64_t bits = next();
+      if (zf[i + 1] + (zf[i] - zf[i + 1]) * r.gen_f64() < sadmc_exp(-x * x / 2.0)) {
+        o.x = x;
+        break;
+      }
+      const uint64_t bits = r.next();
       i = (uint32_t)(bits & 0xff);
       u = sadmc_bits_f64((bits >> 12) | 0x4000000000000000ull) - 3.0;
       x = u * zx[i];
-      if (fabs(x) < zx[i + 1]) return x;
+      if (fabs(x) < zx[i + 1]) {
+        o.x = x;
+        break;
+      }
     }
+    o.s0 = r.s0;
+    o.s1 = r.s1;
+    return o;
   }
   __host__ __device__ __forceinline__ double normal(const double* zx, const double* zf) {
     const uint64_t bits = next();
@@ -90,7 +112,10 @@ struct Rng {
     const double u = sadmc_bits_f64((bits >> 12) | 0x4000000000000000ull) - 3.0;
     const double x = u * zx[i];
     if (fabs(x) < zx[i + 1]) return x;
-    return normal_slow(zx, zf, i, u, x);
+    const SlowOut o = normal_slow(s0, s1, zx, zf, i, u, x);
+    s0 = o.s0;
+    s1 = o.s1;
+    return o.x;
   }
 };
 
