@@ -147,6 +147,10 @@ struct Book {
   double c_lnw, c_etot, c_e2;
   unsigned long long c_hist, c_tfound, c_stamp, c_rt, c_wlh;
   bool c_visited, hi_dirty;
+  // cached `extra` BinCounts of the current bin (energy.rs:136-142, 374-386)
+  double c_xtot;
+  unsigned long long c_xcnt;
+  bool x_dirty;
 
   __device__ Book(const DevParams& p, uint32_t walker, bool is_writer, unsigned mask)
       : P(p), w(walker), writer(is_writer), gmask(mask), rec(p.rec + (size_t)walker * p.cap) {}
@@ -192,6 +196,9 @@ struct Book {
     rt_fill_hi = r.rt_fill_hi;
     ci = -1;
     hi_dirty = false;
+    x_dirty = false;
+    c_xtot = 0.0;
+    c_xcnt = 0;
   }
   __device__ void store(WalkerRec& r) {
     flush();
@@ -255,6 +262,11 @@ struct Book {
     c_wlh = h.wl_hist;
     c_visited = visited_flag(i, h.rt_stamp);
     hi_dirty = false;
+    if (P.extra_total) {
+      c_xtot = P.extra_total[side(i)];
+      c_xcnt = P.extra_count[side(i)];
+    }
+    x_dirty = false;
   }
   __device__ __forceinline__ void load_bin(int i) {
     const BinLo l = rec[i].lo;
@@ -277,8 +289,13 @@ struct Book {
         h.wl_hist = c_wlh;
         rec[ci].hi = h;
       }
+      if (x_dirty) {
+        P.extra_total[side(ci)] = c_xtot;
+        P.extra_count[side(ci)] = c_xcnt;
+      }
     }
     hi_dirty = false;
+    x_dirty = false;
     sync();
   }
   __device__ __forceinline__ double lnw_at(int i) const { return i == ci ? c_lnw : rec[i].lo.lnw; }

@@ -18,6 +18,7 @@
 #include "host_ctor.hpp"
 #include "move_kernel.cuh"
 #include "rng.cuh"
+#include "sys_fake.cuh"
 #include "sys_ising.cuh"
 #include "sys_lj.cuh"
 #include "sys_lj_thread.cuh"
@@ -82,6 +83,7 @@ struct sadmc_engine {
   long long k_base = 0;
   size_t sys_len = 0; // doubles per walker in the ABI image
   bool started = false;
+  bool has_extra = false; // the system reports data_to_collect values (two-wells `which`, WCA `pressure`)
   double* d_zig = nullptr;
   ShimOut* d_shim = nullptr;
   double* d_pending = nullptr;
@@ -108,6 +110,9 @@ static int pick_kernels(sadmc_engine* e) {
   DevParams& P = e->P;
   switch (c.system) {
     case SADMC_SYS_ISING: e->ks = make_set<IsingSys>(P); return 0;
+    case SADMC_SYS_FAKE: e->ks = make_set<FakeSys>(P); return 0;
+    case SADMC_SYS_TWO_WELLS: e->ks = make_set<TwoWellsSys>(P); return 0;
+    case SADMC_SYS_FAKE_ERFINV: e->ks = make_set<ErfInvSys>(P); return 0;
     case SADMC_SYS_LJ: {
       int G = c.lanes_per_walker;
       if (G == 0) G = c.n_walkers >= 16384 ? 1 : (c.n_walkers >= 4096 ? 8 : 32);
@@ -194,6 +199,51 @@ static int setup_params(sadmc_engine* e) {
       e->sys_len = 3 * (size_t)c.N + 2;
       P.sys_stride = (uint32_t)e->sys_len;
       break;
+    case SADMC_SYS_FAKE: {
+      P.fake_fn = c.fake_function;
+      P.fake_dim = c.fake_function == SADMC_FAKE_LINEAR ? 1 : (c.fake_function == SADMC_FAKE_QUADRATIC ? (int)c.N : 3); // fake.rs:39-46
+      if (P.fake_dim < 1 || P.fake_dim > FAKE_MAX_DIM) return fail(SADMC_ERR_UNSUPPORTED, "fake: dimensions must be 1..%d", FAKE_MAX_DIM);
+      P.fake_a = c.fake_a;
+      P.fake_b = c.fake_b;
+      P.fake_e1 = c.fake_e1;
+      P.fake_e2 = c.fake_e2;
+      P.fake_sigma = c.fake_sigma;
+      P.zone_a = zone_single(P.fake_dim);
+      if (c.fake_function == SADMC_FAKE_LINEAR || c.fake_function == SADMC_FAKE_QUADRATIC) {
+        lowest = 0.0;
+        greatest = 1.0;
+      } else if (c.fake_function == SADMC_FAKE_GAUSSIAN) {
+        lowest = -1.0;
+        greatest = 0.0;
+      } else {
+        const double f1 = ((1.0 - c.fake_b) / (c.fake_b - c.fake_a)) * ((1.0 - c.fake_b) / (c.fake_b - c.fake_a)) * c.fake_e2 - c.fake_e2;
+        lowest = std::fmin(-c.fake_e1, -c.fake_e2);
+        greatest = std::fmax(0.0, f1);
+      }
+      e->sys_len = P.fake_dim;
+      P.sys_stride = (uint32_t)e->sys_len;
+      break;
+    }
+    case SADMC_SYS_TWO_WELLS:
+      if (c.N % 3 != 0 || c.N == 0) return fail(SADMC_ERR_INVALID, "The number of dimensions %u is not divisible by three! (two_wells.rs:240-245)", c.N);
+      if (c.N > TW_MAX_DIM) return fail(SADMC_ERR_UNSUPPORTED, "two-wells: N <= %d", TW_MAX_DIM);
+      P.tw_h2h1 = c.tw_h2_to_h1;
+      P.tw_r2 = c.tw_r2;
+      P.tw_rw = std::sqrt(c.tw_barrier_over_h1) * 1.0 + c.tw_r2 * std::sqrt(1.0 + c.tw_barrier_over_h1 - 1.0 / c.tw_h2_to_h1); // two_wells.rs:246-247
+      P.zone_a = zone_single(c.N / 3);
+      lowest = std::fmin(-1.0, -c.tw_h2_to_h1);
+      greatest = 0.0;
+      e->sys_len = (size_t)c.N + 1;
+      P.sys_stride = (uint32_t)e->sys_len;
+      e->has_extra = true;
+      break;
+    case SADMC_SYS_FAKE_ERFINV:
+      if (c.N < 1 || c.N > ERFINV_MAX_DIM) return fail(SADMC_ERR_UNSUPPORTED, "erfinv: N must be 1..%d", ERFINV_MAX_DIM);
+      P.erfinv_mean = c.erfinv_mean_energy;
+      P.zone_a = zone_single(c.N);
+      e->sys_len = c.N;
+      P.sys_stride = (uint32_t)e->sys_len;
+      break;
     default: return fail(SADMC_ERR_UNSUPPORTED, "system kind %d has no kernel yet", c.system);
   }
   P.width = !is_none(c.energy_bin) ? c.energy_bin : (!is_none(native_de) ? native_de : 1.0); // energy.rs:831-833
@@ -226,6 +276,16 @@ static int upload_initial_systems(sadmc_engine* e) {
   switch (c.system) {
     case SADMC_SYS_ISING: img = hostctor::ising_image(c.N); break;
     case SADMC_SYS_LJ: img = hostctor::lj_image(c.N, c.lj_radius); break;
+    case SADMC_SYS_FAKE: img.assign(e->sys_len, 0.0); break;       // fake.rs:85-93: the origin
+    case SADMC_SYS_FAKE_ERFINV: img.assign(e->sys_len, 0.5); break; // erfinv.rs:50-58
+    case SADMC_SYS_TWO_WELLS: {                                   // two_wells.rs:248-250
+      img.assign(e->sys_len, 0.0);
+      img[0] = -0.99;
+      double d2 = 0.0;
+      for (uint32_t k = 0; k < c.N; k++) d2 += img[k] * img[k];
+      img[c.N] = d2;
+      break;
+    }
     default: return fail(SADMC_ERR_UNSUPPORTED, "no reference constructor for system %d yet", c.system);
   }
   std::vector<double> all((size_t)c.n_walkers * e->sys_len);
@@ -345,7 +405,7 @@ int sadmc_create(const sadmc_config* cfg, sadmc_engine** out) {
   CKB(cudaEventCreate(&e->ev1));
   DevParams& P = e->P;
   const size_t nb = (size_t)P.n_walkers * P.cap;
-  size_t need = nb * sizeof(BinRec) + (size_t)P.n_walkers * (sizeof(WalkerRec) + e->sys_len * 8 + P.ising_words * 4);
+  size_t need = nb * (sizeof(BinRec) + (e->has_extra ? 16 : 0)) + (size_t)P.n_walkers * (sizeof(WalkerRec) + e->sys_len * 8 + P.ising_words * 4);
   size_t free_b = 0, total_b = 0;
   CKB(cudaMemGetInfo(&free_b, &total_b));
   if (need > free_b) {
@@ -355,6 +415,10 @@ int sadmc_create(const sadmc_config* cfg, sadmc_engine** out) {
     return SADMC_ERR_INVALID;
   }
   BAIL(dev_alloc(e, (void**)&P.rec, nb * sizeof(BinRec), true));
+  if (e->has_extra) {
+    BAIL(dev_alloc(e, (void**)&P.extra_total, nb * 8, true));
+    BAIL(dev_alloc(e, (void**)&P.extra_count, nb * 8, true));
+  }
   BAIL(dev_alloc(e, (void**)&P.walkers, (size_t)P.n_walkers * sizeof(WalkerRec), true));
   BAIL(dev_alloc(e, (void**)&P.sys, (size_t)P.n_walkers * (P.sys_stride ? P.sys_stride : 1) * 8, true));
   BAIL(dev_alloc(e, (void**)&P.sys_words, (size_t)P.n_walkers * (P.ising_words ? P.ising_words : 1) * 4, true));

@@ -238,9 +238,10 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
       bk.c_e2 += energy * energy;
       {
         double xv;
-        if (sys.extra(moves, xv) && bk.writer) { // energy.rs:944-946, Bins::accumulate_extra 374-386
-          P.extra_count[bk.side(bk.ci)] += 1;
-          P.extra_total[bk.side(bk.ci)] += xv;
+        if (sys.extra(moves, xv)) { // energy.rs:944-946, Bins::accumulate_extra 374-386
+          bk.c_xcnt += 1;
+          bk.c_xtot += xv;
+          bk.x_dirty = true;
         }
       }
       if (METHOD == SADMC_METHOD_SAD) bk.update_weights_sad(energy, moves); // energy.rs:948
