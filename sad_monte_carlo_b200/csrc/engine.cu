@@ -18,6 +18,7 @@
 #include "host_ctor.hpp"
 #include "move_kernel.cuh"
 #include "rng.cuh"
+#include "sys_cell_fluid.cuh"
 #include "sys_fake.cuh"
 #include "sys_ising.cuh"
 #include "sys_lj.cuh"
@@ -111,6 +112,8 @@ static int pick_kernels(sadmc_engine* e) {
   switch (c.system) {
     case SADMC_SYS_ISING: e->ks = make_set<IsingSys>(P); return 0;
     case SADMC_SYS_FAKE: e->ks = make_set<FakeSys>(P); return 0;
+    case SADMC_SYS_WCA: e->ks = make_set<CellFluidSys<false>>(P); return 0;
+    case SADMC_SYS_SW: e->ks = make_set<CellFluidSys<true>>(P); return 0;
     case SADMC_SYS_TWO_WELLS: e->ks = make_set<TwoWellsSys>(P); return 0;
     case SADMC_SYS_FAKE_ERFINV: e->ks = make_set<ErfInvSys>(P); return 0;
     case SADMC_SYS_LJ: {
@@ -199,6 +202,43 @@ static int setup_params(sadmc_engine* e) {
       e->sys_len = 3 * (size_t)c.N + 2;
       P.sys_stride = (uint32_t)e->sys_len;
       break;
+    case SADMC_SYS_WCA:
+    case SADMC_SYS_SW: {
+      const bool sw = c.system == SADMC_SYS_SW;
+      if (c.N < 1 || c.N > 4096) return fail(SADMC_ERR_UNSUPPORTED, "cell fluids hold 1..4096 atoms per walker (N=%u)", c.N);
+      double box[3];
+      if (c.cell_width[0] > 0) { // CellDimensions::CellWidth, optcell.rs:46
+        for (int k = 0; k < 3; k++) box[k] = std::fabs(c.cell_width[k]);
+      } else {
+        // ReducedDensity -> CellVolume(N / rho) (wca.rs:399-401); FillingFraction -> CellVolume(N pi/6 / eta) (optsquare.rs:365-367)
+        const double vol = sw ? (double)c.N * (M_PI * 1.0 * 1.0 * 1.0 / 6.0) / c.filling_fraction : (double)c.N / c.reduced_density;
+        if (!(vol > 0)) return fail(SADMC_ERR_INVALID, "cell volume must be positive");
+        box[0] = box[1] = box[2] = std::cbrt(vol); // optcell.rs:47-50
+      }
+      const double r_cut = sw ? c.sw_well_width * 1.0 : std::pow(2.0, 1.0 / 6.0); // optsquare.rs:155, wca.rs:61-63
+      for (int k = 0; k < 3; k++) {
+        if (r_cut > box[k]) return fail(SADMC_ERR_INVALID, "The cell is not large enough for the well width, sorry! (wca.rs:186-191)");
+        P.box[k] = box[k];
+        P.ncell[k] = (int)std::floor(box[k] / r_cut); // optcell.rs:64-66
+        if (P.ncell[k] < 3)
+          return fail(SADMC_ERR_UNSUPPORTED, "box of %.3f holds %d subcells along axis %d; the device cell list needs >= 3", box[k], P.ncell[k], k);
+      }
+      if ((long long)P.ncell[0] * P.ncell[1] * P.ncell[2] > 32000) return fail(SADMC_ERR_UNSUPPORTED, "too many subcells for the 16-bit cell list");
+      P.r_cut2 = r_cut * r_cut;
+      P.well2 = r_cut * r_cut;
+      P.zone_b = zone_uniform(c.N);
+      if (sw) {
+        native_de = 1.0; // optsquare.rs:190-192
+        lowest = -(double)c.N * (double)hostctor::max_balls_within(r_cut); // optsquare.rs:196-198
+        greatest = 0.0;
+      } else {
+        lowest = 0.0; // wca.rs:234-236
+        e->has_extra = true;
+      }
+      e->sys_len = 3 * (size_t)c.N + 2;
+      P.sys_stride = (uint32_t)e->sys_len;
+      break;
+    }
     case SADMC_SYS_FAKE: {
       P.fake_fn = c.fake_function;
       P.fake_dim = c.fake_function == SADMC_FAKE_LINEAR ? 1 : (c.fake_function == SADMC_FAKE_QUADRATIC ? (int)c.N : 3); // fake.rs:39-46
@@ -277,6 +317,15 @@ static int upload_initial_systems(sadmc_engine* e) {
     case SADMC_SYS_ISING: img = hostctor::ising_image(c.N); break;
     case SADMC_SYS_LJ: img = hostctor::lj_image(c.N, c.lj_radius); break;
     case SADMC_SYS_FAKE: img.assign(e->sys_len, 0.0); break;       // fake.rs:85-93: the origin
+    case SADMC_SYS_SW: {
+      std::string why;
+      img = hostctor::sw_image(c.N, e->P.box, why);
+      if (img.empty()) return fail(SADMC_ERR_INVALID, "sw: %s", why.c_str());
+      break;
+    }
+    case SADMC_SYS_WCA:
+      return fail(SADMC_ERR_UNSUPPORTED, "wca: the reference constructor (N*N random attempts, wca.rs:448-496) is not built; use "
+                                         "SADMC_INIT_RANDOMIZE or SADMC_INIT_EXTERNAL");
     case SADMC_SYS_FAKE_ERFINV: img.assign(e->sys_len, 0.5); break; // erfinv.rs:50-58
     case SADMC_SYS_TWO_WELLS: {                                   // two_wells.rs:248-250
       img.assign(e->sys_len, 0.0);

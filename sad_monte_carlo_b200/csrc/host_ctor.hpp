@@ -136,5 +136,73 @@ inline std::vector<double> ising_image(uint32_t N) {
   return img;
 }
 
+// optsquare.rs:290-322
+inline uint64_t max_balls_within(double distance) {
+  distance += 1e-10;
+  const double a = std::sqrt(2.0);
+  const long c = (long)std::ceil(distance / a) + 1;
+  long num = -1;
+  const double d2 = distance * distance;
+  for (long n = -c; n < c + 1; n++)
+    for (long m = -c; m < c + 1; m++)
+      for (long l = -c; l < c + 1; l++) {
+        const double x0 = (double)(m + l) * a, y0 = (double)(n + l) * a, z0 = (double)(m + n) * a;
+        if (x0 * x0 + y0 * y0 + z0 * z0 <= d2) num++;
+        if ((x0 + 0.5 * a) * (x0 + 0.5 * a) + (y0 + 0.5 * a) * (y0 + 0.5 * a) + z0 * z0 <= d2) num++;
+        if ((x0 + 0.5 * a) * (x0 + 0.5 * a) + y0 * y0 + (z0 + 0.5 * a) * (z0 + 0.5 * a) <= d2) num++;
+        if (x0 * x0 + (y0 + 0.5 * a) * (y0 + 0.5 * a) + (z0 + 0.5 * a) * (z0 + 0.5 * a) <= d2) num++;
+      }
+  return (uint64_t)num;
+}
+
+// From<SquareWellNParams>, optsquare.rs:357-436: N distinct random sites of a stretched FCC grid.
+// The energy is left as NaN: the device counts the well overlaps when it loads the image.
+inline std::vector<double> sw_image(uint32_t n, const double box[3], std::string& why) {
+  const double min_cell_width = 2.0 * std::sqrt(2.0) * 0.5; // units::R = sigma / 2
+  size_t cells[3];
+  double cw[3];
+  for (int k = 0; k < 3; k++) {
+    cells[k] = (size_t)(box[k] / min_cell_width);
+    if (cells[k] == 0) {
+      why = "box too small for an fcc cell";
+      return {};
+    }
+    cw[k] = box[k] / (double)cells[k];
+    if (!(cw[k] >= min_cell_width)) {
+      why = "fcc cell narrower than 2 sqrt(2) R";
+      return {};
+    }
+  }
+  const double off[4][3] = {{0, 0, 0}, {0.0, cw[1] / 2.0, cw[2] / 2.0}, {cw[0] / 2.0, 0.0, cw[2] / 2.0}, {cw[0] / 2.0, cw[1] / 2.0, 0.0}};
+  const size_t total_spots = 4 * cells[0] * cells[1] * cells[1]; // sic (optsquare.rs:402)
+  if (total_spots < n || 4 * cells[0] * cells[1] * cells[2] < n) {
+    why = "not enough fcc spots for N atoms";
+    return {};
+  }
+  std::vector<char> reserved(cells[0] * cells[1] * cells[2] * 4, 0);
+  Rng rng;
+  seed_from_u64(0, &rng.s0, &rng.s1);
+  std::vector<double> img;
+  for (uint32_t a = 0; a < n; a++) {
+    for (;;) {
+      const size_t i = rng.below((uint32_t)cells[0], zone_uniform(cells[0]));
+      const size_t j = rng.below((uint32_t)cells[1], zone_uniform(cells[1]));
+      const size_t k = rng.below((uint32_t)cells[2], zone_uniform(cells[2]));
+      const size_t l = rng.below(4, zone_uniform(4));
+      char& spot = reserved[((i * cells[1] + j) * cells[2] + k) * 4 + l];
+      if (!spot) {
+        spot = 1;
+        img.push_back((double)i * cw[0] + off[l][0]);
+        img.push_back((double)j * cw[1] + off[l][1]);
+        img.push_back((double)k * cw[2] + off[l][2]);
+        break;
+      }
+    }
+  }
+  img.push_back(std::nan(""));
+  img.push_back(0.0);
+  return img;
+}
+
 } // namespace hostctor
 } // namespace sadmc

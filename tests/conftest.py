@@ -24,3 +24,10 @@ def oracle():
 def gpu_lib():
     import sad_monte_carlo_b200 as pkg
     return pkg.load_library()
+
+
+def pytest_collection_modifyitems(config, items):
+    # every GPU test is bounded: a hung kernel must fail the test, not eat the GPU budget
+    for item in items:
+        if "gpu" in item.keywords and not any(m.name == "timeout" for m in item.iter_markers()):
+            item.add_marker(pytest.mark.timeout(300))
