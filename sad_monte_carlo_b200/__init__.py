@@ -13,7 +13,8 @@ from . import _abi
 from ._abi import make_config, Config, WalkerState  # noqa: F401
 
 _HERE = _os.path.dirname(_os.path.abspath(__file__))
-LIB_PATH = _os.path.join(_HERE, "libsadmc_gpu.so")
+# SADMC_GPU_LIB: another build of the same library (kernel experiments); never a different implementation
+LIB_PATH = _os.environ.get("SADMC_GPU_LIB") or _os.path.join(_HERE, "libsadmc_gpu.so")
 _lib = None
 
 

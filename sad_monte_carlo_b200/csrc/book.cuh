@@ -27,6 +27,7 @@
 
 #include "../../include/sadmc_gpu.h"
 #include "../../include/sadmc_math.h"
+#include "fastmath.cuh"
 
 namespace sadmc {
 
@@ -49,6 +50,25 @@ struct __align__(64) BinRec {
   BinLo lo;
   BinHi hi;
 };
+
+// Both sectors of a record in one go.  The asm is volatile so that the compiler cannot sink the
+// second load to its first use (it did: the `hi` half is only consumed when the walker moves into
+// the bin, and a load issued there exposes a second full DRAM latency per accepted move).
+__device__ __forceinline__ void load_rec(const BinRec* p, BinLo& l, BinHi& h) {
+  unsigned long long a0, a1, a2, a3, b0, b1, b2, b3;
+  asm volatile("ld.global.v2.u64 {%0, %1}, [%2];" : "=l"(a0), "=l"(a1) : "l"(p));
+  asm volatile("ld.global.v2.u64 {%0, %1}, [%2+16];" : "=l"(a2), "=l"(a3) : "l"(p));
+  asm volatile("ld.global.v2.u64 {%0, %1}, [%2+32];" : "=l"(b0), "=l"(b1) : "l"(p));
+  asm volatile("ld.global.v2.u64 {%0, %1}, [%2+48];" : "=l"(b2), "=l"(b3) : "l"(p));
+  l.lnw = __longlong_as_double((long long)a0);
+  l.hist = a1;
+  l.etot = __longlong_as_double((long long)a2);
+  l.e2tot = __longlong_as_double((long long)a3);
+  h.t_found = b0;
+  h.rt_stamp = b1;
+  h.round_trips = b2;
+  h.wl_hist = b3;
+}
 
 // Per-walker scalars as they sit in HBM between launches.
 struct __align__(16) WalkerRec {
@@ -120,7 +140,11 @@ __device__ __forceinline__ int f64_as_index(double x) {
   return (int)x;
 }
 
-template <int METHOD, int G>
+// FAST (tolerance tier, SADMC_FLAG_FAST_MATH): bin indices by multiplication with 1/width and the SAD
+// gamma with cached reciprocals of tF and num_states instead of three IEEE divides per move.  Results
+// differ from the reference's arithmetic by a few ulp (gamma) / for energies within an ulp of a bin
+// edge (index); the bit-exact tier never uses it.
+template <int METHOD, int G, bool FAST = false>
 struct Book {
   const DevParams& P;
   const uint32_t w;
@@ -151,9 +175,16 @@ struct Book {
   double c_xtot;
   unsigned long long c_xcnt;
   bool x_dirty;
+  // SAD: ln w of the two boundary bins (ilo, ihi) as they sit in HBM; reject_move needs them for every walker
+  // outside [too_lo, too_hi] and a dependent global load there would sit on the critical path of the move
+  double b_lnw_lo, b_lnw_hi;
+  // FAST only
+  double inv_width, inv_tF, inv_ns, inv_min_T;
+  unsigned long long g_tF, g_ns;
 
   __device__ Book(const DevParams& p, uint32_t walker, bool is_writer, unsigned mask)
-      : P(p), w(walker), writer(is_writer), gmask(mask), rec(p.rec + (size_t)walker * p.cap) {}
+      : P(p), w(walker), writer(is_writer), gmask(mask), rec(p.rec + (size_t)walker * p.cap), inv_width(1.0 / p.width), inv_tF(0.0),
+        inv_ns(0.0), inv_min_T(1.0 / p.min_T), g_tF(0), g_ns(0) {}
 
   __device__ __forceinline__ void sync() const {
     if (G > 1) __syncwarp(gmask);
@@ -179,6 +210,10 @@ struct Book {
     tfmax = r.tfmax;
     ilo = r.ilo;
     ihi = r.ihi;
+    if (METHOD == SADMC_METHOD_SAD) {
+      b_lnw_lo = rec[ilo].lo.lnw;
+      b_lnw_hi = rec[ihi].lo.lnw;
+    }
     samc_t0 = r.samc_t0;
     wl_gamma = r.wl_gamma;
     wl_num_states = r.wl_num_states;
@@ -240,7 +275,9 @@ struct Book {
 
   // ---- bins ------------------------------------------------------------
   // Bins::state_to_index (energy.rs:371-373) shifted into the window.
-  __device__ __forceinline__ int widx(double e) const { return lo + f64_as_index((e - bmin) / P.width); }
+  __device__ __forceinline__ int widx(double e) const {
+    return lo + f64_as_index(FAST ? (e - bmin) * inv_width : (e - bmin) / P.width);
+  }
   // Bins::index_to_state (energy.rs:366-370) for window index j.
   __device__ __forceinline__ double centre(int j) const { return bmin + ((double)(j - lo) + 0.5) * P.width; }
 
@@ -269,11 +306,16 @@ struct Book {
     x_dirty = false;
   }
   __device__ __forceinline__ void load_bin(int i) {
-    const BinLo l = rec[i].lo;
-    const BinHi h = rec[i].hi;
+    BinLo l;
+    BinHi h;
+    load_rec(rec + i, l, h);
     adopt_bin(i, l, h);
   }
   __device__ __forceinline__ void flush() {
+    if (METHOD == SADMC_METHOD_SAD) {
+      if (ci == ilo) b_lnw_lo = c_lnw;
+      if (ci == ihi) b_lnw_hi = c_lnw;
+    }
     if (ci >= 0 && writer) {
       BinLo l;
       l.lnw = c_lnw;
@@ -298,7 +340,9 @@ struct Book {
     x_dirty = false;
     sync();
   }
-  __device__ __forceinline__ double lnw_at(int i) const { return i == ci ? c_lnw : rec[i].lo.lnw; }
+  __device__ __forceinline__ double lnw_lo() const { return ci == ilo ? c_lnw : b_lnw_lo; }
+  __device__ __forceinline__ double lnw_hi() const { return ci == ihi ? c_lnw : b_lnw_hi; }
+  __device__ __forceinline__ double over_min_T(double x) const { return FAST ? x * inv_min_T : x / P.min_T; }
 
   // energy.rs:400-434.  Returns false when the fixed window cannot hold e.
   __device__ __forceinline__ bool prepare_for_state(double e) {
@@ -316,11 +360,21 @@ struct Book {
   }
 
   // ---- gamma (energy.rs:799-824) ------------------------------------------
-  __device__ __forceinline__ double gamma(unsigned long long moves) const {
+  __device__ __forceinline__ double gamma(unsigned long long moves) {
     if (METHOD == SADMC_METHOD_CANONICAL) return 0.0;
     if (METHOD == SADMC_METHOD_SAD) {
       const double t = (double)moves, tf = (double)tF, ns = (double)num_states;
       if (latest_parameter * tf * ns == 0.0) return 0.0; // energy.rs:23-25
+      if (FAST) {
+        if (tF != g_tF || num_states != g_ns) { // both change rarely: keep their reciprocals
+          g_tF = tF;
+          g_ns = num_states;
+          inv_tF = 1.0 / tf;
+          inv_ns = 1.0 / ns;
+        }
+        const double ttf = t * inv_tF;
+        return (latest_parameter + ttf) * rcp_newton(fma(t * inv_ns, ttf, latest_parameter));
+      }
       return (latest_parameter + t / tf) / (latest_parameter + t / ns * (t / tf));
     }
     if (METHOD == SADMC_METHOD_SAMC || method == SADMC_METHOD_SAMC) {
@@ -337,17 +391,17 @@ struct Book {
                                               unsigned long long moves, RNG& rng) {
     if (METHOD == SADMC_METHOD_CANONICAL) {
       if (e1 >= e2) return false;
-      return rng.gen_f64() > sadmc_exp((e1 - e2) / P.canonical_T);
+      return exp_cmp(rng.gen_f64(), (e1 - e2) / P.canonical_T) > 0; // u > exp(...), decided exactly
     }
     double lnw1, lnw2;
     if (METHOD == SADMC_METHOD_SAD) {
-      lnw1 = e1 < too_lo ? lnw_at(ilo) + (e1 - too_lo) / P.min_T : (e1 > too_hi ? lnw_at(ihi) : c_lnw);
-      lnw2 = e2 < too_lo ? lnw_at(ilo) + (e2 - too_lo) / P.min_T : (e2 > too_hi ? lnw_at(ihi) : lnw_i2);
+      lnw1 = e1 < too_lo ? lnw_lo() + over_min_T(e1 - too_lo) : (e1 > too_hi ? lnw_hi() : c_lnw);
+      lnw2 = e2 < too_lo ? lnw_lo() + over_min_T(e2 - too_lo) : (e2 > too_hi ? lnw_hi() : lnw_i2);
     } else {
       lnw1 = c_lnw;
       lnw2 = lnw_i2;
     }
-    const bool rejected = lnw2 > lnw1 && rng.gen_f64() > sadmc_exp(lnw1 - lnw2);
+    const bool rejected = lnw2 > lnw1 && exp_cmp(rng.gen_f64(), lnw1 - lnw2) > 0; // u > exp(lnw1 - lnw2), decided exactly
     if (METHOD == SADMC_METHOD_SAD) {
       if (!rejected && hist_i2 == 0 && e2 < too_hi && e2 > too_lo) { // energy.rs:466-483
         latest_parameter = (too_hi - too_lo) / P.min_T;
@@ -368,19 +422,30 @@ struct Book {
     if (energy > too_hi) {
       const double lnw_hi = rec[ihi].lo.lnw;
       // energy.rs:544-555 loops over every bin; only bins from ihi up to the walker's bin can satisfy
-      // `ej > too_hi && ej <= energy`.
-      for (int j = ihi; j <= i; j++) {
-        const double ej = centre(j);
-        if (ej > too_hi && ej <= energy) {
-          if (rec[j].lo.hist != 0) {
-            if (writer) rec[j].lo.lnw = lnw_hi;
-            num_states += 1;
-          } else if (writer) {
-            rec[j].lo.lnw = 0.0;
-          }
+      // `ej > too_hi && ej <= energy`.  The records are loaded four at a time (independent DRAM accesses).
+      for (int j0 = ihi; j0 <= i; j0 += 4) {
+        unsigned long long hs[4], tfs[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int j = j0 + u <= i ? j0 + u : i;
+          hs[u] = rec[j].lo.hist;
+          tfs[u] = rec[j].hi.t_found;
         }
-        const unsigned long long tf = rec[j].hi.t_found;
-        if (j > ihi && tf > tfmax) tfmax = tf;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int j = j0 + u;
+          if (j > i) break;
+          const double ej = centre(j);
+          if (ej > too_hi && ej <= energy) {
+            if (hs[u] != 0) {
+              if (writer) rec[j].lo.lnw = lnw_hi;
+              num_states += 1;
+            } else if (writer) {
+              rec[j].lo.lnw = 0.0;
+            }
+          }
+          if (j > ihi && tfs[u] > tfmax) tfmax = tfs[u];
+        }
       }
       latest_parameter = (energy - too_lo) / P.min_T;
       tL = moves;
@@ -388,20 +453,31 @@ struct Book {
       ihi = i;
     } else { // energy < too_lo
       const double lnw_lo = rec[ilo].lo.lnw;
-      for (int j = i; j <= ilo; j++) {
-        const double ej = centre(j);
-        if (ej < too_lo && ej >= energy) {
-          if (rec[j].lo.hist != 0) {
-            double v = lnw_lo + (ej - too_lo) / P.min_T;
-            if (v < 0.0) v = 0.0;
-            if (writer) rec[j].lo.lnw = v;
-            num_states += 1;
-          } else if (writer) {
-            rec[j].lo.lnw = 0.0;
-          }
+      for (int j0 = i; j0 <= ilo; j0 += 4) {
+        unsigned long long hs[4], tfs[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int j = j0 + u <= ilo ? j0 + u : ilo;
+          hs[u] = rec[j].lo.hist;
+          tfs[u] = rec[j].hi.t_found;
         }
-        const unsigned long long tf = rec[j].hi.t_found;
-        if (j < ilo && tf > tfmax) tfmax = tf;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int j = j0 + u;
+          if (j > ilo) break;
+          const double ej = centre(j);
+          if (ej < too_lo && ej >= energy) {
+            if (hs[u] != 0) {
+              double v = lnw_lo + (ej - too_lo) / P.min_T;
+              if (v < 0.0) v = 0.0;
+              if (writer) rec[j].lo.lnw = v;
+              num_states += 1;
+            } else if (writer) {
+              rec[j].lo.lnw = 0.0;
+            }
+          }
+          if (j < ilo && tfs[u] > tfmax) tfmax = tfs[u];
+        }
       }
       latest_parameter = (too_hi - energy) / P.min_T;
       tL = moves;
@@ -410,10 +486,12 @@ struct Book {
     }
     sync();
     c_lnw = rec[i].lo.lnw; // the walker's own bin may have been overwritten
+    b_lnw_lo = rec[ilo].lo.lnw;
+    b_lnw_hi = rec[ihi].lo.lnw;
   }
 
-  __device__ __forceinline__ void update_weights_sad(double energy, unsigned long long moves) {
-    const double g = gamma(moves);
+  // g = gamma(moves), evaluated by the caller before anything of this move touched its inputs
+  __device__ __forceinline__ void update_weights_sad(double energy, unsigned long long moves, double g) {
     const double old_lnw = c_lnw;
     c_lnw += g;
     if (too_lo > too_hi || energy < too_lo || energy > too_hi) c_lnw = old_lnw; // energy.rs:535-538
@@ -467,9 +545,9 @@ struct Book {
     wl_low_count = wl_count_low();
     (void)moves;
   }
-  __device__ __forceinline__ void update_weights_wl(double energy, unsigned long long moves, bool first_visit) {
+  __device__ __forceinline__ void update_weights_wl(double energy, unsigned long long moves, bool first_visit, double g) {
     (void)energy;
-    c_lnw += gamma(moves);
+    c_lnw += g;
     if (method == SADMC_METHOD_SAMC) return; // 1/t-WL after its switch (energy.rs:754-756)
     if (P.has_min_gamma && wl_gamma < P.min_gamma) { // production run, energy.rs:649-655
       c_wlh += 1;

@@ -109,6 +109,16 @@ static int dev_alloc(sadmc_engine* e, void** p, size_t bytes, bool zero) {
 static int pick_kernels(sadmc_engine* e) {
   const sadmc_config& c = e->cfg;
   DevParams& P = e->P;
+#ifdef SADMC_EXPERIMENT_LJ31 /* quick-turnaround experiment builds: only the LJ31 thread-per-walker kernels */
+  if (c.system == SADMC_SYS_LJ && c.N == 31) {
+    if (c.flags & SADMC_FLAG_FAST_MATH)
+      e->ks = make_set<LjThreadSys<true, 31, 1>>(P);
+    else
+      e->ks = make_set<LjThreadSys<false, 31, 1>>(P);
+    return 0;
+  }
+  return fail(SADMC_ERR_UNSUPPORTED, "experiment build: LJ31 only");
+#else
   switch (c.system) {
     case SADMC_SYS_ISING: e->ks = make_set<IsingSys>(P); return 0;
     case SADMC_SYS_FAKE: e->ks = make_set<FakeSys>(P); return 0;
@@ -153,6 +163,7 @@ static int pick_kernels(sadmc_engine* e) {
     }
     default: return fail(SADMC_ERR_UNSUPPORTED, "system kind %d has no kernel yet", c.system);
   }
+#endif
 }
 
 static bool is_none(double x) { return std::isnan(x); }

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
   Sys sys(P, w, lane, gmask, smem + ZIG_SMEM_BYTES);
   sys.load(P, w, wr);
   sys.set_cooperative(true);
-  Book<METHOD, G> bk(P, w, lane == 0 && !ghost, gmask);
+  Book<METHOD, G, Sys::FAST_BOOK> bk(P, w, lane == 0 && !ghost, gmask);
   bk.load(wr);
   Rng rng;
   rng.s0 = wr.s0;
@@ -157,13 +157,17 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
   if (!halted) bk.load_bin(bk.widx(sys.energy()));
 
   unsigned long long moves = moves0;
+  // sqrt(1 / moves) of the NEXT move is evaluated one move ahead, in the shadow of the bin-record load
+  // (it depends on nothing but the move counter); same IEEE operations, so the value is unchanged.
+  double recent_next = sqrt(1.0 / (double)(moves0 + 1)); // energy.rs:913
 #pragma unroll 1
   for (unsigned long long m = 0; m < n_moves; m++) {
     moves += 1; // energy.rs:905
     const double e1 = sys.energy();
     const int i1 = bk.ci;
-    double recent_scale = 0.0, e2 = 0.0;
-    bool accepted = false;
+    const double recent_scale = recent_next;
+    double e2 = 0.0;
+    bool accepted = false, proposing = false;
     int i2 = i1;
     BinLo r2;
     BinHi h2;
@@ -176,7 +180,6 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
     h2.round_trips = 0;
     h2.wl_hist = 0;
     if (!halted) {
-      recent_scale = sqrt(1.0 / (double)moves); // energy.rs:913
       bk.acc_rate *= 1.0 - recent_scale;
       if (sys.plan_move(rng, bk.tscale, zx, zf, e2)) { // energy.rs:915
         bool out_of_bounds = false;
@@ -188,26 +191,31 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
             halted = true;
           } else {
             i2 = bk.widx(e2);
-            double lnw2;
-            unsigned long long hist2;
-            if (i2 == i1) {
-              lnw2 = bk.c_lnw;
-              hist2 = bk.c_hist;
-            } else {
-              r2 = bk.rec[i2].lo; // both sectors of the record are requested together: one DRAM access,
-              h2 = bk.rec[i2].hi; // and no second dependent load if the walker moves there
-              lnw2 = r2.lnw;
-              hist2 = r2.hist;
-            }
-            if (!bk.reject_move(e1, e2, i2, lnw2, hist2, moves, rng)) { // energy.rs:927-931
-              accepted = true;
-              bk.accepted += 1;
-              bk.acc_rate += recent_scale;
-              sys.confirm();
-            }
+            proposing = true;
           }
         }
       }
+    }
+    // The one access of a move that goes to HBM: the record of the proposed bin.  Both sectors are
+    // requested together (one DRAM access, no second dependent load if the walker moves there) ...
+    const bool other_bin = proposing && i2 != i1;
+    if (other_bin) load_rec(bk.rec + i2, r2, h2);
+    // ... and what does not depend on it is computed while it is in flight: next move's sqrt(1/moves)
+    // and this move's gamma (energy.rs:799-824; re-evaluated below in the rare case that reject_move's
+    // first-visit hook changes its inputs).
+    recent_next = sqrt(1.0 / (double)(moves + 1));
+    double gamma_now = bk.gamma(moves);
+    if (proposing) {
+      const double lnw2 = other_bin ? r2.lnw : bk.c_lnw;
+      const unsigned long long hist2 = other_bin ? r2.hist : bk.c_hist;
+      const unsigned long long tL_before = bk.tL;
+      if (!bk.reject_move(e1, e2, i2, lnw2, hist2, moves, rng)) { // energy.rs:927-931
+        accepted = true;
+        bk.accepted += 1;
+        bk.acc_rate += recent_scale;
+        sys.confirm();
+      }
+      if (METHOD == SADMC_METHOD_SAD && bk.tL != tL_before) gamma_now = bk.gamma(moves); // energy.rs:466-483 fired
     }
     if (Sys::COOP) sys.finish_move(); // converged point: warp-cooperative energy recomputation
     if (accepted) {
@@ -244,9 +252,9 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
           bk.x_dirty = true;
         }
       }
-      if (METHOD == SADMC_METHOD_SAD) bk.update_weights_sad(energy, moves); // energy.rs:948
-      if (METHOD == SADMC_METHOD_SAMC) bk.c_lnw += bk.gamma(moves);
-      if (METHOD == SADMC_METHOD_WL) bk.update_weights_wl(energy, moves, first_visit);
+      if (METHOD == SADMC_METHOD_SAD) bk.update_weights_sad(energy, moves, gamma_now); // energy.rs:948
+      if (METHOD == SADMC_METHOD_SAMC) bk.c_lnw += gamma_now;
+      if (METHOD == SADMC_METHOD_WL) bk.update_weights_wl(energy, moves, first_visit, gamma_now);
       bk.round_trips(i1 - bk.lo, moves); // energy.rs:950-965
     }
   }

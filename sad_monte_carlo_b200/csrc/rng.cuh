@@ -11,6 +11,7 @@
 
 #include "../../include/sadmc_math.h"
 #include "../../include/sadmc_zig_tables.h"
+#include "fastmath.cuh"
 
 namespace sadmc {
 
@@ -89,7 +90,7 @@ struct Rng {
         o.x = u < 0.0 ? xx - SADMC_ZIG_NORM_R : SADMC_ZIG_NORM_R - xx;
         break;
       }
-      if (zf[i + 1] + (zf[i] - zf[i + 1]) * r.gen_f64() < sadmc_exp(-x * x / 2.0)) {
+      if (exp_cmp(zf[i + 1] + (zf[i] - zf[i + 1]) * r.gen_f64(), -x * x / 2.0) < 0) { // lhs < exp(-x^2/2), decided exactly
         o.x = x;
         break;
       }
@@ -116,6 +117,42 @@ struct Rng {
     s0 = o.s0;
     s1 = o.s1;
     return o.x;
+  }
+  // Three successive StandardNormal draws (crate::rng::vector, src/rng.rs:111-117) with the same
+  // stream semantics as three normal() calls.  The three raw words are drawn first and the three
+  // ziggurat fast paths evaluated side by side (independent chains); only when one of them leaves
+  // the fast path (3.6 % of calls) is the stream rewound to just after that word and finished
+  // serially: ONE out-of-line slow call, then the remaining draws.
+  __host__ __device__ __forceinline__ void normal3(const double* zx, const double* zf, double& v0, double& v1, double& v2) {
+    const uint64_t b0 = next();
+    const uint64_t p0 = s0, q0 = s1;
+    const uint64_t b1 = next();
+    const uint64_t p1 = s0, q1 = s1;
+    const uint64_t b2 = next();
+    const uint32_t i0 = (uint32_t)(b0 & 0xff), i1 = (uint32_t)(b1 & 0xff), i2 = (uint32_t)(b2 & 0xff);
+    const double u0 = sadmc_bits_f64((b0 >> 12) | 0x4000000000000000ull) - 3.0;
+    const double u1 = sadmc_bits_f64((b1 >> 12) | 0x4000000000000000ull) - 3.0;
+    const double u2 = sadmc_bits_f64((b2 >> 12) | 0x4000000000000000ull) - 3.0;
+    v0 = u0 * zx[i0];
+    v1 = u1 * zx[i1];
+    v2 = u2 * zx[i2];
+    const bool ok0 = fabs(v0) < zx[i0 + 1], ok1 = fabs(v1) < zx[i1 + 1], ok2 = fabs(v2) < zx[i2 + 1];
+    if (ok0 && ok1 && ok2) return;
+    const int f = !ok0 ? 0 : (!ok1 ? 1 : 2); // first draw that needs the slow path
+    const SlowOut o = normal_slow(f == 0 ? p0 : (f == 1 ? p1 : s0), f == 0 ? q0 : (f == 1 ? q1 : s1), zx, zf,
+                                  f == 0 ? i0 : (f == 1 ? i1 : i2), f == 0 ? u0 : (f == 1 ? u1 : u2),
+                                  f == 0 ? v0 : (f == 1 ? v1 : v2));
+    s0 = o.s0;
+    s1 = o.s1;
+    if (f == 0) {
+      v0 = o.x;
+      v1 = normal(zx, zf);
+    } else if (f == 1) {
+      v1 = o.x;
+    } else {
+      v2 = o.x;
+    }
+    if (f < 2) v2 = normal(zx, zf);
   }
 };
 

@@ -29,6 +29,7 @@ namespace sadmc {
 template <bool SW>
 struct CellFluidSys {
   static constexpr int G = 32;
+  static constexpr bool FAST_BOOK = false;
   static constexpr int BLOCK = 128;
   static constexpr int MIN_BLOCKS = 4;
   static constexpr bool COOP = false;

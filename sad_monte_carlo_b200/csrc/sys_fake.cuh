@@ -22,6 +22,7 @@ constexpr int FAKE_MAX_DIM = 16;
 
 struct FakeSys {
   static constexpr int G = 1;
+  static constexpr bool FAST_BOOK = false;
   static constexpr int BLOCK = 128;
   static constexpr int MIN_BLOCKS = 4;
   static constexpr bool COOP = false;
@@ -109,6 +110,7 @@ constexpr int TW_MAX_DIM = 48;
 
 struct TwoWellsSys {
   static constexpr int G = 1;
+  static constexpr bool FAST_BOOK = false;
   static constexpr int BLOCK = 128;
   static constexpr int MIN_BLOCKS = 4;
   static constexpr bool COOP = false;
@@ -263,6 +265,7 @@ constexpr int ERFINV_MAX_DIM = 32;
 
 struct ErfInvSys {
   static constexpr int G = 1;
+  static constexpr bool FAST_BOOK = false;
   static constexpr int BLOCK = 128;
   static constexpr int MIN_BLOCKS = 4;
   static constexpr bool COOP = false;

@@ -15,6 +15,7 @@ namespace sadmc {
 
 struct IsingSys {
   static constexpr int G = 1;
+  static constexpr bool FAST_BOOK = false;
   static constexpr int BLOCK = 128;
   static constexpr int MIN_BLOCKS = 4;
   static constexpr bool COOP = false;

@@ -23,6 +23,7 @@ namespace sadmc {
 template <int G_, int A_>
 struct LjSys {
   static constexpr int G = G_;
+  static constexpr bool FAST_BOOK = false;
   static constexpr int A = A_;
   static constexpr int BLOCK = 128;
   static constexpr int MIN_BLOCKS = 4;

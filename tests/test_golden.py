@@ -16,17 +16,21 @@ EXACT = {"ising32_sad", "ising8_wl", "fake_quadratic3_sad", "two_wells_sad", "sw
 def _check(name, w, b, system, exact=True):
     g = np.load(os.path.join(HERE, name + ".npz"))
     sc = [w.accepted_moves, w.rng_s0, w.rng_s1, w.tL, w.tF, w.num_states, w.highest_hist, w.bins_len, w.max_S_index]
-    assert [int(x) for x in g["scalars"]] == [int(x) for x in sc], name
+    wl = "_wl" in name
+    keep = [0, 1, 2, 7, 8] if wl else list(range(9))  # tL, tF, num_states, highest_hist are SAD state
+    assert [int(g["scalars"][k]) for k in keep] == [int(sc[k]) for k in keep], name
     fl = np.array([w.energy, w.bins_min, w.too_lo, w.too_hi, w.latest_parameter, w.acceptance_rate, w.max_S, w.wl_gamma,
                    w.wl_num_states])
     for k in ("histogram", "t_found", "round_trips"):
         assert np.array_equal(g[k], b[k]), (name, k)
+    fkeep = [0, 1, 5, 6, 7, 8] if wl else list(range(7))  # too_lo/too_hi/latest_parameter: SAD; wl_*: WL
+    gf, fl = g["floats"][fkeep], fl[fkeep]
     if exact:
-        assert np.array_equal(g["floats"], fl), name
+        assert np.array_equal(gf, fl), name
         assert np.array_equal(g["lnw"], b["lnw"]) and np.array_equal(g["energy_total"], b["energy_total"]), name
         assert np.array_equal(g["system"], system), name
     else:
-        assert np.allclose(g["floats"], fl, rtol=1e-12, atol=1e-12)
+        assert np.allclose(gf, fl, rtol=1e-12, atol=1e-12)
         assert np.allclose(g["lnw"], b["lnw"], rtol=1e-12, atol=1e-12)
 
 
