@@ -237,6 +237,11 @@ int sadmc_window(sadmc_engine* e, double* lo, double* width, uint32_t* nbins);
  * energy_squared_total (f64), lnw_sum / lnw_sq_sum / lnw_count: sum, sum of
  * squares and number of walkers contributing their max-aligned lnw
  * (plotting/parse-binning.py:169 alignment).  Any pointer may be NULL. */
+/* Which walkers the following folds merge: first_walker, first_walker + walker_stride, ... (default 0, 1 =
+ * all; interleaved groups give ensemble error bars).  sad_range_only != 0: a SAD walker contributes its
+ * ln w only for bins inside its own [too_lo, too_hi], the range in which SAD defines ln w
+ * (plotting/parse-binning.py:150-164 reconstructs the rest from the histogram). */
+int sadmc_fold_select(sadmc_engine* e, uint32_t first_walker, uint32_t walker_stride, int sad_range_only);
 int sadmc_fold_device(sadmc_engine* e, void* d_histogram, void* d_energy_total, void* d_energy_squared_total,
                       void* d_lnw_sum, void* d_lnw_sq_sum, void* d_lnw_count);
 /* Same into HOST buffers (single-GPU convenience). */
@@ -257,6 +262,12 @@ int sadmc_sys_verify_energy(sadmc_engine* e, uint32_t w);                     /*
 /* Achievable FP64 FMA throughput of `device` in TFLOP/s (independent DFMA chains,
  * best of `reps`): the denominator of the FP64 roofline fraction. */
 int sadmc_measure_fp64_peak(int device, int reps, double* tflops);
+
+/* Self-test of the exact exp-comparison filter used by the accept test (csrc/fastmath.cuh): evaluates n
+ * random and adversarial (v, d) pairs on `device`; *mismatches counts decisions that differ from the plain
+ * `v <=> sadmc_exp(d)` comparison or estimates outside the proven bound (must be 0), *exact_evaluations
+ * how many pairs needed the full exp. */
+int sadmc_selftest_exp_cmp(int device, uint64_t seed, uint64_t n, uint64_t* mismatches, uint64_t* exact_evaluations);
 
 #ifdef __cplusplus
 }

@@ -12,8 +12,9 @@
  * with only IEEE +,-,*,/ -- no FMA, no tables -- so every operation rounds
  * identically on x86 and on sm_100a.  Build flags that keep it so:
  * `-fmad=false` (nvcc) and `-ffp-contract=off` (gcc).
- * tests/test_math.py bounds the distance to libm (<= 1 ulp) on the CPU and
- * checks CPU == GPU bit patterns on the GPU.
+ * tests/test_oracle_rng.py bounds the distance to libm (<= 1 ulp) on the CPU; the
+ * bit-exact GPU trajectory tests (tests/test_gpu_ising.py, test_gpu_lj.py, ...) pin
+ * CPU == GPU, because one differing accept decision makes the trajectories diverge.
  */
 #ifndef SADMC_MATH_H
 #define SADMC_MATH_H

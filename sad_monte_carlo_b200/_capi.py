@@ -35,6 +35,7 @@ PROTOTYPES = {
     "sadmc_get_rngs": (C.c_int, [vp, u64p]),
     "sadmc_set_rngs": (C.c_int, [vp, u64p]),
     "sadmc_window": (C.c_int, [vp, f64p, f64p, C.POINTER(C.c_uint32)]),
+    "sadmc_fold_select": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_int]),
     "sadmc_fold_device": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "sadmc_fold": (C.c_int, [vp, u64p, f64p, f64p, f64p, f64p, u64p]),
     "sadmc_sys_energy": (C.c_int, [vp, C.c_uint32, f64p]),
@@ -43,6 +44,7 @@ PROTOTYPES = {
     "sadmc_sys_confirm": (C.c_int, [vp, C.c_uint32]),
     "sadmc_sys_verify_energy": (C.c_int, [vp, C.c_uint32]),
     "sadmc_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, f64p]),
+    "sadmc_selftest_exp_cmp": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, u64p, u64p]),
 }
 
 

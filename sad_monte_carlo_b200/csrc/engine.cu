@@ -15,14 +15,11 @@
 
 #include "../../include/sadmc_gpu.h"
 #include "book.cuh"
+#include "fold_kernels.cuh"
 #include "host_ctor.hpp"
-#include "move_kernel.cuh"
+#include "kernel_set.cuh"
 #include "rng.cuh"
-#include "sys_cell_fluid.cuh"
-#include "sys_fake.cuh"
-#include "sys_ising.cuh"
-#include "sys_lj.cuh"
-#include "sys_lj_thread.cuh"
+#include "sys_limits.hpp"
 
 using namespace sadmc;
 
@@ -43,35 +40,6 @@ static int fail(int code, const char* fmt, ...) {
     if (_e != cudaSuccess) return fail(SADMC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
-typedef void (*move_fn)(const DevParams, unsigned long long, unsigned long long);
-typedef void (*init_fn)(const DevParams, unsigned long long, int, long long, int, double, unsigned long long);
-typedef void (*shim_fn)(const DevParams, uint32_t, int, double, ShimOut*, double*);
-
-struct KernelSet {
-  move_fn move[6]; // indexed by sadmc_method_kind (WL and INV_T_WL share)
-  init_fn init;
-  shim_fn shim;
-  int G, block;
-  size_t smem;
-};
-
-template <class Sys>
-static KernelSet make_set(const DevParams& P) {
-  KernelSet k;
-  memset(&k, 0, sizeof k);
-  k.move[SADMC_METHOD_SAD] = move_kernel<Sys, SADMC_METHOD_SAD>;
-  k.move[SADMC_METHOD_SAMC] = move_kernel<Sys, SADMC_METHOD_SAMC>;
-  k.move[SADMC_METHOD_WL] = move_kernel<Sys, SADMC_METHOD_WL>;
-  k.move[SADMC_METHOD_INV_T_WL] = move_kernel<Sys, SADMC_METHOD_WL>;
-  k.move[SADMC_METHOD_CANONICAL] = move_kernel<Sys, SADMC_METHOD_CANONICAL>;
-  k.init = init_kernel<Sys>;
-  k.shim = shim_kernel<Sys>;
-  k.G = Sys::G;
-  k.block = Sys::BLOCK;
-  k.smem = ZIG_SMEM_BYTES + Sys::smem_bytes(P, Sys::BLOCK);
-  return k;
-}
-
 struct sadmc_engine {
   sadmc_config cfg;
   DevParams P;
@@ -91,6 +59,7 @@ struct sadmc_engine {
   double* d_wmax = nullptr;
   void* d_fold = nullptr;
   float last_ms = 0.f;
+  FoldSel fold_sel = {0u, 1u, 0};
   std::vector<void*> allocs;
 };
 
@@ -109,61 +78,31 @@ static int dev_alloc(sadmc_engine* e, void** p, size_t bytes, bool zero) {
 static int pick_kernels(sadmc_engine* e) {
   const sadmc_config& c = e->cfg;
   DevParams& P = e->P;
-#ifdef SADMC_EXPERIMENT_LJ31 /* quick-turnaround experiment builds: only the LJ31 thread-per-walker kernels */
-  if (c.system == SADMC_SYS_LJ && c.N == 31) {
-    if (c.flags & SADMC_FLAG_FAST_MATH)
-      e->ks = make_set<LjThreadSys<true, 31, 1>>(P);
-    else
-      e->ks = make_set<LjThreadSys<false, 31, 1>>(P);
-    return 0;
-  }
-  return fail(SADMC_ERR_UNSUPPORTED, "experiment build: LJ31 only");
-#else
   switch (c.system) {
-    case SADMC_SYS_ISING: e->ks = make_set<IsingSys>(P); return 0;
-    case SADMC_SYS_FAKE: e->ks = make_set<FakeSys>(P); return 0;
-    case SADMC_SYS_WCA: e->ks = make_set<CellFluidSys<false>>(P); return 0;
-    case SADMC_SYS_SW: e->ks = make_set<CellFluidSys<true>>(P); return 0;
-    case SADMC_SYS_TWO_WELLS: e->ks = make_set<TwoWellsSys>(P); return 0;
-    case SADMC_SYS_FAKE_ERFINV: e->ks = make_set<ErfInvSys>(P); return 0;
+    case SADMC_SYS_ISING: e->ks = kernels_ising(P); return 0;
+    case SADMC_SYS_FAKE: e->ks = kernels_fake(P); return 0;
+    case SADMC_SYS_WCA: e->ks = kernels_cell_fluid(false, P); return 0;
+    case SADMC_SYS_SW: e->ks = kernels_cell_fluid(true, P); return 0;
+    case SADMC_SYS_TWO_WELLS: e->ks = kernels_two_wells(P); return 0;
+    case SADMC_SYS_FAKE_ERFINV: e->ks = kernels_erfinv(P); return 0;
     case SADMC_SYS_LJ: {
       int G = c.lanes_per_walker;
       if (G == 0) G = c.n_walkers >= 16384 ? 1 : (c.n_walkers >= 4096 ? 8 : 32);
       const bool fast = (c.flags & SADMC_FLAG_FAST_MATH) != 0;
       if (G == 1 || (fast && (G == 2 || G == 4))) { // configuration in shared memory (sys_lj_thread.cuh)
         if (c.N > 64) return fail(SADMC_ERR_UNSUPPORTED, "lj: shared-memory kernels hold N <= 64 atoms (N=%u)", c.N);
-#define LJT_CASE(nt)                                                  \
-  if (c.N == nt || nt == 0) {                                         \
-    if (!fast)                                                        \
-      e->ks = make_set<LjThreadSys<false, nt, 1>>(P);                 \
-    else if (G == 1)                                                  \
-      e->ks = make_set<LjThreadSys<true, nt, 1>>(P);                  \
-    else if (G == 2)                                                  \
-      e->ks = make_set<LjThreadSys<true, nt, 2>>(P);                  \
-    else                                                              \
-      e->ks = make_set<LjThreadSys<true, nt, 4>>(P);                  \
-    return 0;                                                         \
-  }
-        LJT_CASE(31) LJT_CASE(38) LJT_CASE(0)
-#undef LJT_CASE
+        const bool ok = !fast ? kernels_lj_thread_exact((int)c.N, P, &e->ks)
+                              : (G == 1 ? kernels_lj_thread_fast((int)c.N, G, P, &e->ks) : kernels_lj_thread_fast_multi((int)c.N, G, P, &e->ks));
+        if (ok) return 0;
+        return fail(SADMC_ERR_UNSUPPORTED, "lj: no shared-memory kernel instance for N=%u, lanes_per_walker=%d", c.N, G);
       }
       if (G == 2) return fail(SADMC_ERR_UNSUPPORTED, "lj: lanes_per_walker = 2 needs SADMC_FLAG_FAST_MATH");
       const int A = ((int)c.N + G - 1) / G;
-#define LJ_CASE(g, a)                          \
-  if (G == g && A == a) {                      \
-    e->ks = make_set<LjSys<g, a>>(P);          \
-    return 0;                                  \
-  }
-#ifndef SADMC_LEAN /* -DSADMC_LEAN: experiment builds with only the thread-per-walker LJ kernels */
-      LJ_CASE(32, 1) LJ_CASE(32, 2) LJ_CASE(16, 2) LJ_CASE(16, 3) LJ_CASE(8, 1) LJ_CASE(8, 2) LJ_CASE(8, 4) LJ_CASE(8, 5) LJ_CASE(4, 4)
-      LJ_CASE(4, 8)
-#endif
-#undef LJ_CASE
+      if (kernels_lj_warp(G, A, P, &e->ks) || kernels_lj_warp_small(G, A, P, &e->ks)) return 0;
       return fail(SADMC_ERR_UNSUPPORTED, "lj: no kernel instance for N=%u with lanes_per_walker=%d (atoms per lane %d)", c.N, G, A);
     }
     default: return fail(SADMC_ERR_UNSUPPORTED, "system kind %d has no kernel yet", c.system);
   }
-#endif
 }
 
 static bool is_none(double x) { return std::isnan(x); }
@@ -374,7 +313,57 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
   if (s == 12345.678) out[0] = s;
 }
 
+// ---- self-test of exp_cmp (fastmath.cuh): its decision must equal the plain comparison with sadmc_exp ----
+__global__ void __launch_bounds__(256) exp_cmp_test_kernel(unsigned long long seed, unsigned long long n, unsigned long long* mismatches,
+                                                         unsigned long long* filtered) {
+  const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  Rng r;
+  seed_from_u64(seed + tid, (uint64_t*)&r.s0, (uint64_t*)&r.s1);
+  unsigned long long bad = 0, slow = 0;
+  for (unsigned long long k = tid; k < n; k += (unsigned long long)gridDim.x * blockDim.x) {
+    // d spread over [-90, 0.5]; v uniform, or within a few ulp / a few 1e-5 of e^d (the adversarial cases)
+    const double d = (k % 7 == 0) ? -r.gen_f64() * 1e-3 : (0.5 - 90.5 * r.gen_f64());
+    const double ex = sadmc_exp(d);
+    double v;
+    switch (k % 5) {
+      case 0: v = r.gen_f64(); break;
+      case 1: v = ex; break;
+      case 2: v = sadmc_bits_f64(sadmc_f64_bits(ex) + (r.next() % 5) - 2); break;
+      case 3: v = ex * (1.0 + (r.gen_f64() - 0.5) * 4e-4); break;
+      default: v = ex * r.gen_f64() * 2.0; break;
+    }
+    const int want = v > ex ? 1 : (v < ex ? -1 : 0);
+    if (exp_cmp(v, d) != want) bad++;
+    if (d <= 0.0 && d > -80.0) {
+      const float t = __double2float_rn(d) * 1.4426950408889634f;
+      float a;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(t));
+      if (!(v > (double)a * 1.0001) && !(v < (double)a * 0.9999)) slow++;
+      // the bound itself: the float estimate must sit within 1e-4 of sadmc_exp
+      if (fabs((double)a - ex) > 0.99e-4 * ex) bad++;
+    }
+  }
+  atomicAdd(mismatches, bad);
+  atomicAdd(filtered, slow);
+}
+
 extern "C" {
+
+int sadmc_selftest_exp_cmp(int device, uint64_t seed, uint64_t n, uint64_t* mismatches, uint64_t* exact_evaluations) {
+  if (!mismatches) return fail(SADMC_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(device));
+  unsigned long long* d = nullptr;
+  CK(cudaMalloc(&d, 16));
+  CK(cudaMemset(d, 0, 16));
+  exp_cmp_test_kernel<<<1024, 256>>>(seed, n, d, d + 1);
+  CK(cudaGetLastError());
+  unsigned long long h[2];
+  CK(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  *mismatches = h[0];
+  if (exact_evaluations) *exact_evaluations = h[1];
+  return 0;
+}
 
 // TFLOP/s of dependent-chain-free DFMA (2 flops each) on `device`; best of `reps`.
 int sadmc_measure_fp64_peak(int device, int reps, double* tflops) {
@@ -818,6 +807,14 @@ int sadmc_window(sadmc_engine* e, double* lo, double* width, uint32_t* nbins) {
 }
 
 // ---- merge for reporting -------------------------------------------------------
+int sadmc_fold_select(sadmc_engine* e, uint32_t first_walker, uint32_t walker_stride, int sad_range_only) {
+  if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  if (walker_stride == 0 || first_walker >= e->P.n_walkers) return fail(SADMC_ERR_INVALID, "fold selection (%u, %u) holds no walker", first_walker, walker_stride);
+  e->fold_sel.first = first_walker;
+  e->fold_sel.stride = walker_stride;
+  e->fold_sel.sad_range_only = sad_range_only ? 1 : 0;
+  return 0;
+}
 int sadmc_fold_device(sadmc_engine* e, void* d_histogram, void* d_energy_total, void* d_energy_squared_total, void* d_lnw_sum,
                       void* d_lnw_sq_sum, void* d_lnw_count) {
   if (!e) return fail(SADMC_ERR_INVALID, "null engine");
@@ -826,11 +823,14 @@ int sadmc_fold_device(sadmc_engine* e, void* d_histogram, void* d_energy_total, 
     int rc = dev_alloc(e, (void**)&e->d_wmax, (size_t)e->P.n_walkers * 8, false);
     if (rc) return rc;
   }
-  walker_max_lnw_kernel<<<e->P.n_walkers, 256, 0, e->stream>>>(e->P, e->d_wmax);
+  const FoldSel sel = e->fold_sel;
+  const uint32_t n_sel = sel.first < e->P.n_walkers ? (e->P.n_walkers - sel.first + sel.stride - 1) / sel.stride : 0;
+  if (n_sel == 0) return fail(SADMC_ERR_INVALID, "fold selection holds no walker");
+  walker_max_lnw_kernel<<<n_sel, 256, 0, e->stream>>>(e->P, e->d_wmax, sel);
   CK(cudaGetLastError());
   fold_kernel<<<(e->P.cap + 255) / 256, 256, 0, e->stream>>>(e->P, e->d_wmax, (unsigned long long*)d_histogram, (double*)d_energy_total,
                                                            (double*)d_energy_squared_total, (double*)d_lnw_sum, (double*)d_lnw_sq_sum,
-                                                           (unsigned long long*)d_lnw_count);
+                                                           (unsigned long long*)d_lnw_count, sel);
   CK(cudaGetLastError());
   e->launches += 2;
   return 0;

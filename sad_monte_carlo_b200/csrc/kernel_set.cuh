@@ -1,0 +1,45 @@
+// kernel_set.cuh -- the kernels of one system type, as function pointers the host code launches.
+//
+// Each system family is instantiated in its own translation unit (kernels_*.cu) so that the library
+// builds in parallel; engine.cu only sees these factory functions.
+#pragma once
+#include <cstring>
+
+#include "book.cuh"
+
+namespace sadmc {
+
+// trait-shaped single-walker shims (src/system/mod.rs:54-120)
+enum SysOp { OP_ENERGY = 0, OP_COMPUTE_ENERGY = 1, OP_PLAN_MOVE = 2, OP_CONFIRM = 3, OP_VERIFY = 4 };
+
+struct ShimOut {
+  double value;
+  int some;
+  int ok;
+};
+
+typedef void (*move_fn)(const DevParams, unsigned long long, unsigned long long);
+typedef void (*init_fn)(const DevParams, unsigned long long, int, long long, int, double, unsigned long long);
+typedef void (*shim_fn)(const DevParams, uint32_t, int, double, ShimOut*, double*);
+
+struct KernelSet {
+  move_fn move[6]; // indexed by sadmc_method_kind (WL and INV_T_WL share)
+  init_fn init;
+  shim_fn shim;
+  int G, block;
+  size_t smem;
+};
+
+// factories, one per translation unit; the bool ones return false when no instance was built
+KernelSet kernels_ising(const DevParams& P);
+KernelSet kernels_fake(const DevParams& P);
+KernelSet kernels_two_wells(const DevParams& P);
+KernelSet kernels_erfinv(const DevParams& P);
+KernelSet kernels_cell_fluid(bool square_well, const DevParams& P);
+bool kernels_lj_thread_exact(int N, const DevParams& P, KernelSet* out);
+bool kernels_lj_thread_fast(int N, int G, const DevParams& P, KernelSet* out);
+bool kernels_lj_thread_fast_multi(int N, int G, const DevParams& P, KernelSet* out);
+bool kernels_lj_warp(int G, int A, const DevParams& P, KernelSet* out);
+bool kernels_lj_warp_small(int G, int A, const DevParams& P, KernelSet* out);
+
+} // namespace sadmc

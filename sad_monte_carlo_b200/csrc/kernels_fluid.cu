@@ -1,0 +1,8 @@
+// kernels_fluid.cu -- WCA and square-well fluids on shared-memory cell lists.
+#include "make_set.cuh"
+#include "sys_cell_fluid.cuh"
+namespace sadmc {
+KernelSet kernels_cell_fluid(bool square_well, const DevParams& P) {
+  return square_well ? make_set<CellFluidSys<true>>(P) : make_set<CellFluidSys<false>>(P);
+}
+} // namespace sadmc

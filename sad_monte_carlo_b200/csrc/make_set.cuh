@@ -1,0 +1,25 @@
+// make_set.cuh -- instantiates every kernel of one system type (included by the kernels_*.cu units).
+#pragma once
+#include "kernel_set.cuh"
+#include "move_kernel.cuh"
+
+namespace sadmc {
+
+template <class Sys>
+static KernelSet make_set(const DevParams& P) {
+  KernelSet k;
+  memset(&k, 0, sizeof k);
+  k.move[SADMC_METHOD_SAD] = move_kernel<Sys, SADMC_METHOD_SAD>;
+  k.move[SADMC_METHOD_SAMC] = move_kernel<Sys, SADMC_METHOD_SAMC>;
+  k.move[SADMC_METHOD_WL] = move_kernel<Sys, SADMC_METHOD_WL>;
+  k.move[SADMC_METHOD_INV_T_WL] = move_kernel<Sys, SADMC_METHOD_WL>;
+  k.move[SADMC_METHOD_CANONICAL] = move_kernel<Sys, SADMC_METHOD_CANONICAL>;
+  k.init = init_kernel<Sys>;
+  k.shim = shim_kernel<Sys>;
+  k.G = Sys::G;
+  k.block = Sys::BLOCK;
+  k.smem = ZIG_SMEM_BYTES + Sys::smem_bytes(P, Sys::BLOCK);
+  return k;
+}
+
+} // namespace sadmc

@@ -7,6 +7,7 @@
 // times, and stored once.  Only bin records travel to and from HBM in between.
 #pragma once
 #include "book.cuh"
+#include "kernel_set.cuh"
 #include "rng.cuh"
 
 namespace sadmc {
@@ -269,14 +270,6 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
 }
 
 // ---- trait-shaped single-walker shims (src/system/mod.rs:54-120) ---------------
-enum SysOp { OP_ENERGY = 0, OP_COMPUTE_ENERGY = 1, OP_PLAN_MOVE = 2, OP_CONFIRM = 3, OP_VERIFY = 4 };
-
-struct ShimOut {
-  double value;
-  int some;
-  int ok;
-};
-
 template <class Sys>
 __global__ void __launch_bounds__(Sys::BLOCK) shim_kernel(const DevParams P, uint32_t w, int op, double arg, ShimOut* out, double* pending) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -318,62 +311,6 @@ __global__ void __launch_bounds__(Sys::BLOCK) shim_kernel(const DevParams P, uin
       break;
   }
   if (lane == 0) *out = o;
-}
-
-} // namespace sadmc
-
-namespace sadmc {
-
-// ---- merge for reporting ---------------------------------------------------
-// One thread per window bin; loops over the local walkers (each warp reads 32
-// consecutive bins of one walker: coalesced 1 KB).  lnw is aligned per walker by
-// subtracting that walker's maximum lnw (plotting/parse-binning.py:169) before
-// it is summed; bins a walker never visited do not contribute to the lnw sums.
-__global__ void __launch_bounds__(256) walker_max_lnw_kernel(const DevParams P, double* wmax) {
-  const uint32_t w = blockIdx.x;
-  const WalkerRec& r = P.walkers[w];
-  double m = -1e300;
-  for (int j = r.lo + (int)threadIdx.x; j < r.lo + r.len; j += blockDim.x) {
-    const BinLo b = P.rec[(size_t)w * P.cap + j].lo;
-    if (b.hist != 0 && b.lnw > m) m = b.lnw;
-  }
-  __shared__ double sm[256];
-  sm[threadIdx.x] = m;
-  __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if ((int)threadIdx.x < s && sm[threadIdx.x + s] > sm[threadIdx.x]) sm[threadIdx.x] = sm[threadIdx.x + s];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) wmax[w] = sm[0];
-}
-
-__global__ void __launch_bounds__(256) fold_kernel(const DevParams P, const double* wmax, unsigned long long* histogram, double* energy_total,
-                                                  double* energy_squared_total, double* lnw_sum, double* lnw_sq_sum,
-                                                  unsigned long long* lnw_count) {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= P.cap) return;
-  unsigned long long h = 0, cnt = 0;
-  double et = 0.0, e2 = 0.0, ls = 0.0, lq = 0.0;
-  for (uint32_t w = 0; w < P.n_walkers; w++) {
-    const WalkerRec& r = P.walkers[w];
-    if ((int)j < r.lo || (int)j >= r.lo + r.len) continue;
-    const BinLo b = P.rec[(size_t)w * P.cap + j].lo;
-    h += b.hist;
-    et += b.etot;
-    e2 += b.e2tot;
-    if (b.hist != 0) {
-      const double a = b.lnw - wmax[w];
-      ls += a;
-      lq += a * a;
-      cnt += 1;
-    }
-  }
-  if (histogram) histogram[j] = h;
-  if (energy_total) energy_total[j] = et;
-  if (energy_squared_total) energy_squared_total[j] = e2;
-  if (lnw_sum) lnw_sum[j] = ls;
-  if (lnw_sq_sum) lnw_sq_sum[j] = lq;
-  if (lnw_count) lnw_count[j] = cnt;
 }
 
 } // namespace sadmc

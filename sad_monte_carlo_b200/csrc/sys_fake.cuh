@@ -14,11 +14,11 @@
 // tolerance-tier system (as it is between two builds of the reference itself).
 #pragma once
 #include "book.cuh"
+#include "sys_limits.hpp"
 #include "rng.cuh"
 
 namespace sadmc {
 
-constexpr int FAKE_MAX_DIM = 16;
 
 struct FakeSys {
   static constexpr int G = 1;
@@ -106,7 +106,6 @@ struct FakeSys {
   }
 };
 
-constexpr int TW_MAX_DIM = 48;
 
 struct TwoWellsSys {
   static constexpr int G = 1;
@@ -261,7 +260,6 @@ __device__ __forceinline__ double erf_inv_dev(double x) {
   return y;
 }
 
-constexpr int ERFINV_MAX_DIM = 32;
 
 struct ErfInvSys {
   static constexpr int G = 1;

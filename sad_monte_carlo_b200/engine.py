@@ -157,6 +157,11 @@ class WalkerEngine:
         self._check(self.L.sadmc_window(self.h, C.byref(lo), C.byref(width), C.byref(n)))
         return lo.value, width.value, n.value
 
+    def fold_select(self, first_walker=0, walker_stride=1, sad_range_only=False):
+        """Which walkers the following folds merge (interleaved groups: ensemble error bars) and whether SAD
+        walkers contribute ln w only inside their own [too_lo, too_hi]."""
+        self._check(self.L.sadmc_fold_select(self.h, first_walker, walker_stride, 1 if sad_range_only else 0))
+
     def fold(self):
         """Window-aligned sums over the local walkers (device fold kernel), as host arrays."""
         _, _, n = self.window()
