@@ -110,3 +110,36 @@ def load_lj31_reference(path):
     """(T, Cv) of one literature curve; `path` is one of the CSVs named in LJ31_REFERENCES."""
     T, c = np.loadtxt(path, delimiter=",", unpack=True)
     return T, LJ31_REFERENCES[os.path.basename(path)](c)
+
+
+# ---- heat capacity of a folded multi-walker SAD run (tools/lj31_cv_run.py) -------------------------------------------
+
+def cv_from_grouped_folds(folds, T, min_fraction=0.5):
+    """Cv(T) per interleaved walker group from SAD-range-only folds, and the ensemble mean / standard error.
+
+    `folds` is the mapping tools/lj31_cv_run.py saves: window_lo, width, walkers, groups and, per group g,
+    lnw_sum_g / lnw_count_g (max-aligned ln w summed over the group's walkers, and how many walkers' SAD range
+    covers each bin).  A bin takes part when at least `min_fraction` of the group's walkers cover it; the entropy
+    is the walker mean of the aligned ln w (each walker is an independent SAD estimate of the same S(E)).
+    """
+    G = int(folds["groups"])
+    nb = len(folds["lnw_sum_0"])
+    E = float(folds["window_lo"]) + (np.arange(nb) + 0.5) * float(folds["width"])
+    per_group = int(folds["walkers"]) // G
+    cvs = []
+    for g in range(G):
+        cnt = np.asarray(folds["lnw_count_%d" % g], dtype=np.float64)
+        ok = cnt >= min_fraction * per_group
+        S = np.asarray(folds["lnw_sum_%d" % g], dtype=np.float64)[ok] / cnt[ok]
+        cvs.append(heat_capacity(T, E[ok], S))
+    cvs = np.array(cvs)
+    return cvs.mean(0), cvs.std(0, ddof=1) / np.sqrt(G), cvs
+
+
+def cv_error_vs_reference(folds, ref_csv, T_min, T_max=np.inf):
+    """The reference's own error metric (plotting/final_heat_capacity.py:185-194): Err = (Cv - Cv_ref) / Cv_ref at
+    the literature curve's own temperatures, restricted to [T_min, T_max].  Returns (T, Cv, sem, Cv_ref, Err)."""
+    Tr, Cr = load_lj31_reference(ref_csv)
+    m = (Tr >= T_min) & (Tr <= T_max)
+    mean, sem, _ = cv_from_grouped_folds(folds, Tr[m])
+    return Tr[m], mean, sem, Cr[m], (mean - Cr[m]) / Cr[m]

@@ -204,3 +204,35 @@ def test_lj_thread_per_walker_fast_math_tracks_reference_trajectory():
         assert np.array_equal(eng.bins(w)["histogram"], o.bins()["histogram"])
         assert np.allclose(eng.system(w)[:-2], o.system()[:-2], rtol=0, atol=0)
         assert abs(eng.compute_energy(w) - g.energy) <= 1e-14 * 31 * 31 * abs(g.energy)
+
+
+# ---- converged physics: heat capacity of LJ31 against the literature curves the reference ships -------------------
+
+@pytest.mark.timeout(600)
+def test_lj31_heat_capacity_short_run_approaches_the_reference_curve():
+    """A 15-second version of tools/lj31_cv_run.py (the full 1e8-move run is pinned on the CPU side by
+    tests/test_analysis.py from its committed folds): 37 888 SAD walkers x 3e6 moves, min_T 0.15, energy bin 0.1.
+    Stated tolerance for this SHORT run: within 12 % of tRem_Ref.csv (the curve of the reference's own error metric,
+    plotting/final_heat_capacity.py:185) for T in [0.28, 0.40]; walker-group standard error below 2 %."""
+    import os
+    from sad_monte_carlo_b200 import analysis
+    W, G = 37888, 8
+    cfg = make_config("lj", "sad", N=31, lj_radius=2.5, max_allowed_energy=0.0, sad_min_T=0.15, energy_bin=0.1,
+                      move_value=0.05, n_walkers=W, init_mode=_abi.INIT_RANDOMIZE, lanes_per_walker=1, seed=0,
+                      flags=_abi.FLAG_FAST_MATH, bin_window_lo=-133.7, bin_window_hi=0.2)
+    eng = WalkerEngine(cfg)
+    for _ in range(3):
+        eng.run(1_000_000)
+    lo, width, nb = eng.window()
+    folds = {"window_lo": lo, "width": width, "walkers": W, "groups": G}
+    for g in range(G):
+        eng.fold_select(g, G, True)
+        f = eng.fold()
+        folds["lnw_sum_%d" % g], folds["lnw_count_%d" % g] = f["lnw_sum"], f["lnw_count"]
+    assert all(eng.walker(w).status == 0 for w in range(0, W, 997))
+    ref = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lj31_literature", "tRem_Ref.csv")
+    T, cv, sem, cref, err = analysis.cv_error_vs_reference(folds, ref, 0.28, 0.40)
+    print("T", T, "Cv", cv, "ref", cref, "err", err)
+    assert len(T) >= 3
+    assert np.abs(err).max() < 0.12
+    assert (sem / cv).max() < 0.02
