@@ -28,6 +28,9 @@ sys.path.insert(0, ROOT)
 
 FLOPS_PER_MOVE = 900.0  # 30 (N - 1) FP64 flops for N = 31 (a divide counted as one flop)
 BYTES_PER_MOVE = 80.0   # 2 lnw reads + RMW of histogram, energy_total, energy_squared_total, lnw
+# dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the move kernel
+# (profiles/r01_lj31_sad_thread_fast_v3.txt: 29.97 GB for 75 776 walkers x 3 000 moves), per move
+NCU_DRAM_BYTES_PER_MOVE = 29.974067e9 / (75776 * 3000)
 
 
 def lj31_config(n_walkers, walker_offset=0, device=0, lanes=0, flags=0):
@@ -262,12 +265,16 @@ def run_ours(args):
                     "what": "sadmc_set_systems + sadmc_set_rngs (pinned host) -> sadmc_run -> sadmc_fold + sadmc_get_energies (host)"},
             "roofline": {"bound": "fp64", "achieved": per_gpu_moves_s * FLOPS_PER_MOVE / 1e12, "peak": fp64.value,
                          "unit": "TFLOP/s", "frac": (per_gpu_moves_s * FLOPS_PER_MOVE / 1e12) / fp64.value if fp64.value else None,
-                         "traffic": None, "per_unit": "900 FP64 flop per move (30 per pair x 30 pairs), divide = 1 flop",
+                         "traffic": None, "per_unit": "900 FP64 flop per move (30 per pair x 30 pairs), divide = 1 flop; "
+                                                      "`achieved` = 900 x moves per launch / average launch duration",
                          "peak_source": "DFMA microkernel in this library, measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                         "kernel": "move_kernel<LjSys<G,A>, SAD>"},
+                         "kernel": "move_kernel<LjThreadSys<fast, 31, 1>, SAD>", "ms_per_launch": ms_max / args.steps},
             "roofline_hbm": {"bound": "hbm", "achieved": per_gpu_moves_s * BYTES_PER_MOVE / 1e9, "peak": peaks.get("hbm_gbs"),
                              "unit": "GB/s", "frac": per_gpu_moves_s * BYTES_PER_MOVE / 1e9 / peaks.get("hbm_gbs"),
-                             "traffic": None, "per_unit": "80 B of bin traffic per move", "peak_source": peak_src},
+                             "traffic": NCU_DRAM_BYTES_PER_MOVE * W * args.moves_per_step,
+                             "per_unit": "80 B of bin traffic per move (algorithmic); traffic = DRAM bytes per launch scaled from "
+                                         "the ncu capture in profiles/ (131.8 B per move: 64-byte records, sector granularity)",
+                             "peak_source": peak_src},
             "fold_allreduce_ms": fold_ms,
             "checks": {"merged_histogram_total": hist_total, "expected": int(world * W * (moves_now + 1)),
                        "walkers_halted_in_sample": statuses},

@@ -58,6 +58,8 @@ struct sadmc_engine {
   double* d_pending = nullptr;
   double* d_wmax = nullptr;
   void* d_fold = nullptr;
+  double* d_fold_part = nullptr; // per-chunk partial sums of the two-stage fold
+  size_t fold_part_bytes = 0;
   float last_ms = 0.f;
   FoldSel fold_sel = {0u, 1u, 0};
   std::vector<void*> allocs;
@@ -828,11 +830,27 @@ int sadmc_fold_device(sadmc_engine* e, void* d_histogram, void* d_energy_total, 
   if (n_sel == 0) return fail(SADMC_ERR_INVALID, "fold selection holds no walker");
   walker_max_lnw_kernel<<<n_sel, 256, 0, e->stream>>>(e->P, e->d_wmax, sel);
   CK(cudaGetLastError());
-  fold_kernel<<<(e->P.cap + 255) / 256, 256, 0, e->stream>>>(e->P, e->d_wmax, (unsigned long long*)d_histogram, (double*)d_energy_total,
-                                                           (double*)d_energy_squared_total, (double*)d_lnw_sum, (double*)d_lnw_sq_sum,
-                                                           (unsigned long long*)d_lnw_count, sel);
+  // chunks of walkers so that the grid covers the chip several times over (148 SMs x 8 blocks)
+  const uint32_t nbx = (e->P.cap + 255) / 256;
+  uint32_t n_chunks = (1184 + nbx - 1) / nbx;
+  const uint32_t max_chunks = (n_sel + 63) / 64;
+  if (n_chunks > max_chunks) n_chunks = max_chunks;
+  if (n_chunks > 65535) n_chunks = 65535;
+  const uint32_t per_chunk = (n_sel + n_chunks - 1) / n_chunks;
+  n_chunks = (n_sel + per_chunk - 1) / per_chunk;
+  const size_t part_bytes = (size_t)n_chunks * FOLD_FIELDS * e->P.cap * 8;
+  if (part_bytes > e->fold_part_bytes) {
+    int rc = dev_alloc(e, (void**)&e->d_fold_part, part_bytes, false);
+    if (rc) return rc;
+    e->fold_part_bytes = part_bytes;
+  }
+  fold_partial_kernel<<<dim3(nbx, n_chunks), 256, 0, e->stream>>>(e->P, e->d_wmax, e->d_fold_part, sel, n_sel, per_chunk);
   CK(cudaGetLastError());
-  e->launches += 2;
+  fold_final_kernel<<<nbx, 256, 0, e->stream>>>(e->P, e->d_fold_part, n_chunks, (unsigned long long*)d_histogram, (double*)d_energy_total,
+                                               (double*)d_energy_squared_total, (double*)d_lnw_sum, (double*)d_lnw_sq_sum,
+                                               (unsigned long long*)d_lnw_count);
+  CK(cudaGetLastError());
+  e->launches += 3;
   return 0;
 }
 int sadmc_fold(sadmc_engine* e, uint64_t* histogram, double* energy_total, double* energy_squared_total, double* lnw_sum,

@@ -5,8 +5,8 @@
 namespace sadmc {
 
 // ---- merge for reporting ---------------------------------------------------
-// One thread per window bin; loops over the local walkers (each warp reads 32
-// consecutive bins of one walker: coalesced 1 KB).  lnw is aligned per walker by
+// One thread per window bin and walker chunk (each warp reads 32 consecutive bins of
+// one walker: the 32-byte `lo` sectors of 32 adjacent records).  lnw is aligned per walker by
 // subtracting that walker's maximum lnw (plotting/parse-binning.py:169) before
 // it is summed; bins a walker never visited do not contribute to the lnw sums.
 //
@@ -40,26 +40,92 @@ __global__ void __launch_bounds__(256) walker_max_lnw_kernel(const DevParams P, 
   if (threadIdx.x == 0) wmax[w] = sm[0];
 }
 
-__global__ void __launch_bounds__(256) fold_kernel(const DevParams P, const double* wmax, unsigned long long* histogram, double* energy_total,
-                                                  double* energy_squared_total, double* lnw_sum, double* lnw_sq_sum,
-                                                  unsigned long long* lnw_count, const FoldSel sel) {
+// Stage 1: grid (bin blocks, walker chunks).  A block walks its chunk of the selected walkers in tiles of
+// 256 whose window extents are staged in shared memory, every thread owns one bin and keeps eight record
+// loads in flight (the loop is bound by HBM latency otherwise: one 32-byte sector per walker and thread).
+// Stage 2 adds the chunk partials in chunk order, so the result does not depend on scheduling.
+struct FoldMeta {
+  int lo, end, ilo, ihi; // window extent [lo, end) and the extent in which ln w counts
+  double wmax;
+};
+constexpr int FOLD_FIELDS = 6;
+__global__ void __launch_bounds__(256) fold_partial_kernel(const DevParams P, const double* wmax, double* partial, const FoldSel sel,
+                                                          uint32_t n_sel, uint32_t per_chunk) {
+  __shared__ FoldMeta meta[256];
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t c = blockIdx.y;
+  const uint32_t s_begin = c * per_chunk;
+  const uint32_t s_end = s_begin + per_chunk < n_sel ? s_begin + per_chunk : n_sel;
+  unsigned long long h = 0, cnt = 0;
+  double et = 0.0, e2 = 0.0, ls = 0.0, lq = 0.0;
+  for (uint32_t s0 = s_begin; s0 < s_end; s0 += 256) {
+    __syncthreads();
+    const uint32_t s = s0 + threadIdx.x;
+    if (s < s_end) {
+      const uint32_t w = sel.first + s * sel.stride;
+      const WalkerRec& r = P.walkers[w];
+      FoldMeta m;
+      m.lo = r.lo;
+      m.end = r.lo + r.len;
+      const bool ranged = sel.sad_range_only && r.method == SADMC_METHOD_SAD;
+      m.ilo = ranged ? r.ilo : m.lo;
+      m.ihi = ranged ? r.ihi : m.end - 1;
+      m.wmax = wmax[w];
+      meta[threadIdx.x] = m;
+    }
+    __syncthreads();
+    const uint32_t n_tile = s_end - s0 < 256 ? s_end - s0 : 256;
+    if (j >= P.cap) continue;
+    for (uint32_t k0 = 0; k0 < n_tile; k0 += 8) {
+      BinLo b[8];
+      bool in[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const uint32_t k = k0 + u;
+        in[u] = k < n_tile && (int)j >= meta[k < n_tile ? k : 0].lo && (int)j < meta[k < n_tile ? k : 0].end;
+        if (in[u]) b[u] = P.rec[(size_t)(sel.first + (s0 + k) * sel.stride) * P.cap + j].lo;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        if (!in[u]) continue;
+        const FoldMeta m = meta[k0 + u];
+        h += b[u].hist;
+        et += b[u].etot;
+        e2 += b[u].e2tot;
+        if (b[u].hist != 0 && (int)j >= m.ilo && (int)j <= m.ihi) {
+          const double a = b[u].lnw - m.wmax;
+          ls += a;
+          lq += a * a;
+          cnt += 1;
+        }
+      }
+    }
+  }
+  if (j >= P.cap) return;
+  double* p = partial + ((size_t)c * FOLD_FIELDS) * P.cap + j;
+  p[0] = __longlong_as_double((long long)h);
+  p[(size_t)1 * P.cap] = et;
+  p[(size_t)2 * P.cap] = e2;
+  p[(size_t)3 * P.cap] = ls;
+  p[(size_t)4 * P.cap] = lq;
+  p[(size_t)5 * P.cap] = __longlong_as_double((long long)cnt);
+}
+
+__global__ void __launch_bounds__(256) fold_final_kernel(const DevParams P, const double* partial, uint32_t n_chunks, unsigned long long* histogram,
+                                                        double* energy_total, double* energy_squared_total, double* lnw_sum, double* lnw_sq_sum,
+                                                        unsigned long long* lnw_count) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= P.cap) return;
   unsigned long long h = 0, cnt = 0;
   double et = 0.0, e2 = 0.0, ls = 0.0, lq = 0.0;
-  for (uint32_t w = sel.first; w < P.n_walkers; w += sel.stride) {
-    const WalkerRec& r = P.walkers[w];
-    if ((int)j < r.lo || (int)j >= r.lo + r.len) continue;
-    const BinLo b = P.rec[(size_t)w * P.cap + j].lo;
-    h += b.hist;
-    et += b.etot;
-    e2 += b.e2tot;
-    if (fold_lnw_counts(r, b, (int)j, sel)) {
-      const double a = b.lnw - wmax[w];
-      ls += a;
-      lq += a * a;
-      cnt += 1;
-    }
+  for (uint32_t c = 0; c < n_chunks; c++) {
+    const double* p = partial + ((size_t)c * FOLD_FIELDS) * P.cap + j;
+    h += (unsigned long long)__double_as_longlong(p[0]);
+    et += p[(size_t)1 * P.cap];
+    e2 += p[(size_t)2 * P.cap];
+    ls += p[(size_t)3 * P.cap];
+    lq += p[(size_t)4 * P.cap];
+    cnt += (unsigned long long)__double_as_longlong(p[(size_t)5 * P.cap]);
   }
   if (histogram) histogram[j] = h;
   if (energy_total) energy_total[j] = et;
