@@ -135,9 +135,8 @@ struct DevParams {
 
 // Rust `x as usize` for f64 (saturating, NaN -> 0), clipped to int range.
 __device__ __forceinline__ int f64_as_index(double x) {
-  if (!(x > 0.0)) return 0;
-  if (x >= 2147483647.0) return 2147483647;
-  return (int)x;
+  // cvt.rzi.s32.f64 saturates and maps NaN to 0 by itself; only negative values need the clamp (branch-free)
+  return max(__double2int_rz(x), 0);
 }
 
 // FAST (tolerance tier, SADMC_FLAG_FAST_MATH): bin indices by multiplication with 1/width and the SAD

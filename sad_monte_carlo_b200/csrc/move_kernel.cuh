@@ -199,7 +199,11 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
     }
     // The one access of a move that goes to HBM: the record of the proposed bin.  Both sectors are
     // requested together (one DRAM access, no second dependent load if the walker moves there) ...
+#ifdef SADMC_ABL_NOLOAD /* ablation experiment only */
+    const bool other_bin = false;
+#else
     const bool other_bin = proposing && i2 != i1;
+#endif
     if (other_bin) load_rec(bk.rec + i2, r2, h2);
     // ... and what does not depend on it is computed while it is in flight: next move's sqrt(1/moves)
     // and this move's gamma (energy.rs:799-824; re-evaluated below in the rare case that reject_move's
@@ -256,7 +260,9 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
       if (METHOD == SADMC_METHOD_SAD) bk.update_weights_sad(energy, moves, gamma_now); // energy.rs:948
       if (METHOD == SADMC_METHOD_SAMC) bk.c_lnw += gamma_now;
       if (METHOD == SADMC_METHOD_WL) bk.update_weights_wl(energy, moves, first_visit, gamma_now);
+#ifndef SADMC_ABL_NORT
       bk.round_trips(i1 - bk.lo, moves); // energy.rs:950-965
+#endif
     }
   }
   if (ghost) return;

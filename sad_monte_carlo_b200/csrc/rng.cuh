@@ -118,41 +118,73 @@ struct Rng {
     s1 = o.s1;
     return o.x;
   }
-  // Three successive StandardNormal draws (crate::rng::vector, src/rng.rs:111-117) with the same
-  // stream semantics as three normal() calls.  The three raw words are drawn first and the three
-  // ziggurat fast paths evaluated side by side (independent chains); only when one of them leaves
-  // the fast path (3.6 % of calls) is the stream rewound to just after that word and finished
-  // serially: ONE out-of-line slow call, then the remaining draws.
+  // Three successive StandardNormal draws (crate::rng::vector, src/rng.rs:111-117) with the same stream
+  // semantics as three normal() calls.
+  //
+  // 3.6 % of the calls leave the ziggurat's fast path somewhere, i.e. 69 % of all warps per move: a
+  // divergent serial slow path costs every warp what it costs the slowest lane (measured: 13 % of the LJ
+  // kernel).  So the stream is evaluated speculatively instead.  Words w0..w4 of the generator are taken
+  // as they come; each is turned into a fast-path normal n_k (valid when ok_k).  If word f is the first
+  // to fail, the reference's next steps are fixed: w_{f+1} is the uniform of the wedge test
+  // (zf[i+1] + (zf[i] - zf[i+1]) u < exp(-x^2/2)); if it accepts, x_f stands and the later draws shift by
+  // one word; if it rejects, w_{f+2} is the redraw and they shift by two.  Everything is selected from
+  // registers without a branch.  Only a second irregular event in the same call (tail layer i == 0, two
+  // failures, a failing redraw: ~0.1 % of calls) rewinds the stream and replays it serially.
   __host__ __device__ __forceinline__ void normal3(const double* zx, const double* zf, double& v0, double& v1, double& v2) {
-    const uint64_t b0 = next();
-    const uint64_t p0 = s0, q0 = s1;
-    const uint64_t b1 = next();
-    const uint64_t p1 = s0, q1 = s1;
-    const uint64_t b2 = next();
-    const uint32_t i0 = (uint32_t)(b0 & 0xff), i1 = (uint32_t)(b1 & 0xff), i2 = (uint32_t)(b2 & 0xff);
-    const double u0 = sadmc_bits_f64((b0 >> 12) | 0x4000000000000000ull) - 3.0;
-    const double u1 = sadmc_bits_f64((b1 >> 12) | 0x4000000000000000ull) - 3.0;
-    const double u2 = sadmc_bits_f64((b2 >> 12) | 0x4000000000000000ull) - 3.0;
-    v0 = u0 * zx[i0];
-    v1 = u1 * zx[i1];
-    v2 = u2 * zx[i2];
-    const bool ok0 = fabs(v0) < zx[i0 + 1], ok1 = fabs(v1) < zx[i1 + 1], ok2 = fabs(v2) < zx[i2 + 1];
-    if (ok0 && ok1 && ok2) return;
-    const int f = !ok0 ? 0 : (!ok1 ? 1 : 2); // first draw that needs the slow path
-    const SlowOut o = normal_slow(f == 0 ? p0 : (f == 1 ? p1 : s0), f == 0 ? q0 : (f == 1 ? q1 : s1), zx, zf,
-                                  f == 0 ? i0 : (f == 1 ? i1 : i2), f == 0 ? u0 : (f == 1 ? u1 : u2),
-                                  f == 0 ? v0 : (f == 1 ? v1 : v2));
-    s0 = o.s0;
-    s1 = o.s1;
-    if (f == 0) {
-      v0 = o.x;
-      v1 = normal(zx, zf);
-    } else if (f == 1) {
-      v1 = o.x;
-    } else {
-      v2 = o.x;
+    const uint64_t a0 = s0, a1 = s1; // for the replay
+    const uint64_t w0 = next();
+    const uint64_t w1 = next();
+    const uint64_t w2 = next();
+#define SADMC_ZIG_FAST(k)                                                                 \
+  const uint32_t i##k = (uint32_t)(w##k & 0xff);                                           \
+  const double n##k = (sadmc_bits_f64((w##k >> 12) | 0x4000000000000000ull) - 3.0) * zx[i##k]; \
+  const bool ok##k = fabs(n##k) < zx[i##k + 1];
+    SADMC_ZIG_FAST(0)
+    SADMC_ZIG_FAST(1)
+    SADMC_ZIG_FAST(2)
+    if (ok0 && ok1 && ok2) {
+      v0 = n0;
+      v1 = n1;
+      v2 = n2;
+      return;
     }
-    if (f < 2) v2 = normal(zx, zf);
+#ifdef SADMC_ABL_NOSLOW /* ablation experiment only: wrong statistics */
+    v0 = n0;
+    v1 = n1;
+    v2 = n2;
+    return;
+#endif
+    const uint64_t p2 = s0, q2 = s1;
+    (void)p2;
+    (void)q2;
+    const uint64_t w3 = next();
+    const uint64_t p3 = s0, q3 = s1;
+    const uint64_t w4 = next();
+    const uint64_t p4 = s0, q4 = s1;
+    SADMC_ZIG_FAST(3)
+    SADMC_ZIG_FAST(4)
+#undef SADMC_ZIG_FAST
+    const int f = !ok0 ? 0 : (!ok1 ? 1 : 2); // first word that left the fast path
+    const uint32_t fi = f == 0 ? i0 : (f == 1 ? i1 : i2);
+    const double fx = f == 0 ? n0 : (f == 1 ? n1 : n2);
+    const uint64_t fu = f == 0 ? w1 : (f == 1 ? w2 : w3); // the word the wedge test draws its uniform from
+    const double u01 = (double)(fu >> 11) * (1.0 / 9007199254740992.0);
+    const bool acc = exp_cmp(zf[fi + 1] + (zf[fi] - zf[fi + 1]) * u01, -fx * fx / 2.0) < 0;
+    // fast-path validity of the words that the shifted stream turns into normals
+    const bool need_ok = f == 0 ? (acc ? (ok2 && ok3) : (ok2 && ok3 && ok4)) : (f == 1 ? (acc ? ok3 : (ok3 && ok4)) : (acc ? true : ok4));
+    if (fi != 0 && need_ok) {
+      v0 = f == 0 ? (acc ? n0 : n2) : n0;
+      v1 = f == 0 ? (acc ? n2 : n3) : (f == 1 ? (acc ? n1 : n3) : n1);
+      v2 = f == 2 ? (acc ? n2 : n4) : (acc ? n3 : n4);
+      s0 = acc ? p3 : p4;
+      s1 = acc ? q3 : q4;
+      return;
+    }
+    s0 = a0; // replay serially from the start of the call
+    s1 = a1;
+    v0 = normal(zx, zf);
+    v1 = normal(zx, zf);
+    v2 = normal(zx, zf);
   }
 };
 
