@@ -226,6 +226,19 @@ int sadmc_set_systems(sadmc_engine* e, const double* buf, size_t n);
 int sadmc_get_rngs(sadmc_engine* e, uint64_t* s /* [n_walkers][2] */);
 int sadmc_set_rngs(sadmc_engine* e, const uint64_t* s /* [n_walkers][2] */);
 
+/* ---- resume (mc/mod.rs:70-84: the reference deserialises the whole EnergyMC and calls update_caches) ----
+ * On an engine created with SADMC_INIT_EXTERNAL: for every walker sadmc_set_system(s) and sadmc_set_walker_bins
+ * (the inverse of sadmc_get_walker + sadmc_get_bins: same field meanings, reference index order, element 0 = bin at
+ * s->bins_min; t_found, round_trips, have_visited, wl_hist, extra_* may be NULL), then sadmc_resume(e, moves)
+ * instead of sadmc_start.  A resumed engine continues bit for bit like the one that was checkpointed
+ * (tests/resume-sad.rs). */
+int sadmc_set_walker_bins(sadmc_engine* e, uint32_t w, const sadmc_walker_state* s, const uint64_t* histogram,
+                          const uint64_t* t_found, const double* lnw, const double* energy_total,
+                          const double* energy_squared_total, const uint64_t* round_trips,
+                          const uint8_t* have_visited_since_maxentropy, const uint64_t* wl_hist,
+                          const double* extra_total, const uint64_t* extra_count);
+int sadmc_resume(sadmc_engine* e, uint64_t moves);
+
 /* ---- window geometry ---------------------------------------------------- */
 /* Device window: bin j of every walker covers [lo + j*width, lo + (j+1)*width). */
 int sadmc_window(sadmc_engine* e, double* lo, double* width, uint32_t* nbins);

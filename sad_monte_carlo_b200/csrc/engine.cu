@@ -689,6 +689,117 @@ int sadmc_get_bins(sadmc_engine* e, uint32_t w, uint32_t cap, uint64_t* histogra
   return 0;
 }
 
+// ---- resume: the inverse of sadmc_get_walker / sadmc_get_bins (mc/mod.rs:70-84 deserialises a whole EnergyMC) ----
+int sadmc_set_walker_bins(sadmc_engine* e, uint32_t w, const sadmc_walker_state* s, const uint64_t* histogram, const uint64_t* t_found,
+                          const double* lnw, const double* energy_total, const double* energy_squared_total, const uint64_t* round_trips,
+                          const uint8_t* have_visited, const uint64_t* wl_hist, const double* extra_total, const uint64_t* extra_count) {
+  if (!e || !s || !histogram || !lnw || !energy_total || !energy_squared_total)
+    return fail(SADMC_ERR_INVALID, "null argument (histogram, lnw, energy_total, energy_squared_total are required)");
+  if (w >= e->P.n_walkers) return fail(SADMC_ERR_INVALID, "walker %u out of range", w);
+  if (e->started && e->cfg.init_mode != SADMC_INIT_EXTERNAL) return fail(SADMC_ERR_INVALID, "resume needs an engine created with SADMC_INIT_EXTERNAL");
+  const DevParams& P = e->P;
+  if (s->bins_width != P.width) return fail(SADMC_ERR_INVALID, "checkpoint bin width %g differs from the engine's %g", s->bins_width, P.width);
+  const size_t n = s->bins_len;
+  // window index of reference bin 0: bin j of the window covers [(k_base + j - 0.5) w, (k_base + j + 0.5) w)
+  const long long lo = (long long)std::floor(s->bins_min / P.width + 0.5 + 0.5) - e->k_base;
+  if (n == 0 || lo < 0 || lo + (long long)n > (long long)P.cap)
+    return fail(SADMC_ERR_WINDOW, "checkpointed bins [%g, %g) do not fit the device window", s->bins_min, s->bins_min + n * P.width);
+  WalkerRec r;
+  memset(&r, 0, sizeof r);
+  r.s0 = s->rng_s0;
+  r.s1 = s->rng_s1;
+  r.accepted = s->accepted_moves;
+  r.acc_rate = s->acceptance_rate;
+  r.tscale = s->translation_scale;
+  r.E = s->energy;
+  r.bmin = s->bins_min;
+  r.lo = (int)lo;
+  r.len = (int)n;
+  r.method = s->method == SADMC_METHOD_INV_T_WL ? SADMC_METHOD_WL : s->method;
+  r.status = 0;
+  r.too_lo = s->too_lo;
+  r.too_hi = s->too_hi;
+  r.latest_parameter = s->latest_parameter;
+  r.tL = s->tL;
+  r.tF = s->tF;
+  r.num_states = s->num_states;
+  r.highest_hist = s->highest_hist;
+  r.samc_t0 = s->samc_t0;
+  r.wl_gamma = s->wl_gamma;
+  r.wl_num_states = s->wl_num_states;
+  r.wl_min_energy = s->wl_min_energy;
+  r.wl_lowest = s->wl_lowest_hist;
+  r.wl_highest = s->wl_highest_hist;
+  r.wl_total = s->wl_total_hist;
+  r.wl_hist_len = (int)s->wl_hist_len;
+  r.max_S = s->max_S;
+  r.max_S_index = (int)s->max_S_index;
+  // derived device fields
+  auto ref_index = [&](double energy) { // Bins::state_to_index, energy.rs:371-373 (saturating cast)
+    const double x = (energy - s->bins_min) / P.width;
+    long long i = !(x > 0.0) ? 0 : (x >= 2147483647.0 ? 2147483647ll : (long long)x);
+    if (i >= (long long)n) i = (long long)n - 1;
+    return (int)i;
+  };
+  r.ilo = r.lo + ref_index(s->too_lo);
+  r.ihi = r.lo + ref_index(s->too_hi);
+  unsigned long long tfmax = 0;
+  if (t_found)
+    for (int j = r.ilo - r.lo; j <= r.ihi - r.lo; j++)
+      if (j >= 0 && j < (int)n && t_found[j] > tfmax) tfmax = t_found[j];
+  r.tfmax = tfmax;
+  long long low = 0;
+  if (wl_hist && r.wl_hist_len > 0)
+    for (size_t j = 0; j < n; j++)
+      if (histogram[j] != 0 && wl_hist[j] <= r.wl_lowest) low++;
+  r.wl_low_count = low;
+  // have_visited_since_maxentropy as "all false since move 0" plus individual stamps at move 1
+  r.rt_fill_val = 0;
+  r.rt_fill_time = 0;
+  r.rt_fill_lo = r.lo;
+  r.rt_fill_hi = r.lo + r.len;
+  // keep the system-side fields that sadmc_set_system(s) already placed in the record
+  WalkerRec old;
+  int rc = fetch_walker(e, w, &old);
+  if (rc) return rc;
+  r.err = old.err;
+  r.d_squared = old.d_squared;
+  std::vector<BinRec> recs(n);
+  for (size_t j = 0; j < n; j++) {
+    BinRec& b = recs[j];
+    b.lo.lnw = lnw[j];
+    b.lo.hist = histogram[j];
+    b.lo.etot = energy_total[j];
+    b.lo.e2tot = energy_squared_total[j];
+    b.hi.t_found = t_found ? t_found[j] : 0;
+    b.hi.rt_stamp = (have_visited && have_visited[j]) ? 1 : 0;
+    b.hi.round_trips = round_trips ? (round_trips[j] > 0 ? round_trips[j] - 1 : 0) : 0; // stored minus one
+    b.hi.wl_hist = (wl_hist && r.wl_hist_len > 0) ? wl_hist[j] : 0;
+  }
+  CK(cudaSetDevice(e->cfg.device));
+  const size_t base = (size_t)w * P.cap;
+  CK(cudaMemsetAsync(P.rec + base, 0, (size_t)P.cap * sizeof(BinRec), e->stream));
+  CK(cudaMemcpyAsync(P.rec + base + lo, recs.data(), n * sizeof(BinRec), cudaMemcpyHostToDevice, e->stream));
+  if (P.extra_total) {
+    CK(cudaMemsetAsync(P.extra_total + base, 0, (size_t)P.cap * 8, e->stream));
+    CK(cudaMemsetAsync(P.extra_count + base, 0, (size_t)P.cap * 8, e->stream));
+    if (extra_total) CK(cudaMemcpyAsync(P.extra_total + base + lo, extra_total, n * 8, cudaMemcpyHostToDevice, e->stream));
+    if (extra_count) CK(cudaMemcpyAsync(P.extra_count + base + lo, extra_count, n * 8, cudaMemcpyHostToDevice, e->stream));
+  }
+  CK(cudaMemcpyAsync(P.walkers + w, &r, sizeof r, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int sadmc_resume(sadmc_engine* e, uint64_t moves) {
+  if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  if (e->started) return fail(SADMC_ERR_INVALID, "engine already started");
+  if (e->cfg.init_mode != SADMC_INIT_EXTERNAL) return fail(SADMC_ERR_INVALID, "resume needs an engine created with SADMC_INIT_EXTERNAL");
+  e->started = true;
+  e->moves = moves;
+  return 0;
+}
+
 int sadmc_system_len(sadmc_engine* e, size_t* n) {
   if (!e || !n) return fail(SADMC_ERR_INVALID, "null argument");
   *n = e->sys_len;

@@ -152,6 +152,22 @@ class WalkerEngine:
         assert s.shape == (self.n_walkers, 2)
         self._check(self.L.sadmc_set_rngs(self.h, _p(s, u64p)))
 
+    # -- resume (mc/mod.rs:70-84) ---------------------------------------------
+    def set_walker_bins(self, w, state: WalkerState, bins):
+        """Inverse of walker(w) + bins(w) on an engine created with INIT_EXTERNAL."""
+        def arr(k, dt):
+            a = bins.get(k)
+            return None if a is None else np.ascontiguousarray(a, dtype=dt)
+        keep = [arr("histogram", np.uint64), arr("t_found", np.uint64), arr("lnw", np.float64), arr("energy_total", np.float64),
+                arr("energy_squared_total", np.float64), arr("round_trips", np.uint64), arr("have_visited", np.uint8),
+                arr("wl_hist", np.uint64), arr("extra_total", np.float64), arr("extra_count", np.uint64)]
+        types = [u64p, u64p, f64p, f64p, f64p, u64p, u8p, u64p, f64p, u64p]
+        self._check(self.L.sadmc_set_walker_bins(self.h, w, C.byref(state), *[_p(a, t) for a, t in zip(keep, types)]))
+
+    def resume(self, moves):
+        """Instead of start(): continue from restored walkers at move count `moves`."""
+        self._check(self.L.sadmc_resume(self.h, int(moves)))
+
     def window(self):
         lo, width, n = C.c_double(), C.c_double(), C.c_uint32()
         self._check(self.L.sadmc_window(self.h, C.byref(lo), C.byref(width), C.byref(n)))
