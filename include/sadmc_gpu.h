@@ -183,6 +183,14 @@ void sadmc_destroy(sadmc_engine* e);
 const char* sadmc_last_error(void);
 int sadmc_abi_version(void);
 
+/* The reference's system constructor `Any::from(AnyParams)` (any.rs:80-93: lj.rs:126-205,
+ * ising.rs:31-53, optsquare.rs:357-436, wca.rs:392-498 with fcc = false, fake.rs:85-93,
+ * two_wells.rs:248-250, erfinv.rs:50-58) run on the HOST: one system image in the layout of
+ * sadmc_get_system.  It is what SADMC_INIT_REFERENCE replicates to every walker, exported so a
+ * host can write the `system` of a checkpoint before any move.  Needs no device.  `*needed`
+ * (optional) receives the image length in doubles; buf == NULL only queries it. */
+int sadmc_reference_system(const sadmc_config* cfg, double* buf, size_t n, size_t* needed);
+
 /* With SADMC_INIT_EXTERNAL: finish from_params (relaxation + first bin) after
  * the systems were supplied. */
 int sadmc_start(sadmc_engine* e);

@@ -14,6 +14,7 @@ PROTOTYPES = {
     "sadmc_destroy": (None, [vp]),
     "sadmc_last_error": (C.c_char_p, []),
     "sadmc_abi_version": (C.c_int, []),
+    "sadmc_reference_system": (C.c_int, [C.POINTER(Config), f64p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "sadmc_start": (C.c_int, [vp]),
     "sadmc_set_stream": (C.c_int, [vp, vp]),
     "sadmc_get_stream": (vp, [vp]),

@@ -52,6 +52,7 @@ struct sadmc_engine {
   long long k_base = 0;
   size_t sys_len = 0; // doubles per walker in the ABI image
   bool started = false;
+  bool host_only = false; // sadmc_reference_system: system parameters only, no bin window, no device
   bool has_extra = false; // the system reports data_to_collect values (two-wells `which`, WCA `pressure`)
   double* d_zig = nullptr;
   ShimOut* d_shim = nullptr;
@@ -241,6 +242,7 @@ static int setup_params(sadmc_engine* e) {
   P.width = !is_none(c.energy_bin) ? c.energy_bin : (!is_none(native_de) ? native_de : 1.0); // energy.rs:831-833
   if (!(P.width > 0)) return fail(SADMC_ERR_INVALID, "energy_bin must be > 0 (energy.rs:402)");
 
+  if (e->host_only) return 0;
   double wlo = c.bin_window_lo, whi = c.bin_window_hi;
   if (is_none(wlo)) wlo = P.has_min ? c.min_allowed_energy - 2 * P.width : lowest;
   if (is_none(whi)) whi = P.has_max ? c.max_allowed_energy + 2 * P.width : greatest;
@@ -261,10 +263,9 @@ static int launch_cfg(const sadmc_engine* e, int* grid) {
   return 0;
 }
 
-static int upload_initial_systems(sadmc_engine* e) {
+// `Any::from(AnyParams)` (any.rs:80-93) on the host: one system image in sadmc_get_system's layout.
+static int reference_image(sadmc_engine* e, std::vector<double>& img) {
   const sadmc_config& c = e->cfg;
-  if (c.init_mode != SADMC_INIT_REFERENCE) return 0;
-  std::vector<double> img;
   switch (c.system) {
     case SADMC_SYS_ISING: img = hostctor::ising_image(c.N); break;
     case SADMC_SYS_LJ: img = hostctor::lj_image(c.N, c.lj_radius); break;
@@ -275,9 +276,10 @@ static int upload_initial_systems(sadmc_engine* e) {
       if (img.empty()) return fail(SADMC_ERR_INVALID, "sw: %s", why.c_str());
       break;
     }
-    case SADMC_SYS_WCA:
-      return fail(SADMC_ERR_UNSUPPORTED, "wca: the reference constructor (N*N random attempts, wca.rs:448-496) is not built; use "
-                                         "SADMC_INIT_RANDOMIZE or SADMC_INIT_EXTERNAL");
+    case SADMC_SYS_WCA: // From<WcaNParams>, fcc = false (wca.rs:448-496); the fcc start needs rand's choose_multiple
+      img = hostctor::wca_image(c.N, e->P.box, 0, getenv("SADMC_HOST_THREADS") ? (unsigned)atoi(getenv("SADMC_HOST_THREADS")) : 0u);
+      if (img.empty()) return fail(SADMC_ERR_INVALID, "wca: no random placement of %u atoms below 1e80 epsilon", c.N);
+      break;
     case SADMC_SYS_FAKE_ERFINV: img.assign(e->sys_len, 0.5); break; // erfinv.rs:50-58
     case SADMC_SYS_TWO_WELLS: {                                   // two_wells.rs:248-250
       img.assign(e->sys_len, 0.0);
@@ -289,6 +291,15 @@ static int upload_initial_systems(sadmc_engine* e) {
     }
     default: return fail(SADMC_ERR_UNSUPPORTED, "no reference constructor for system %d yet", c.system);
   }
+  return 0;
+}
+
+static int upload_initial_systems(sadmc_engine* e) {
+  const sadmc_config& c = e->cfg;
+  if (c.init_mode != SADMC_INIT_REFERENCE) return 0;
+  std::vector<double> img;
+  const int rc = reference_image(e, img);
+  if (rc) return rc;
   std::vector<double> all((size_t)c.n_walkers * e->sys_len);
   for (uint32_t w = 0; w < c.n_walkers; w++) memcpy(&all[(size_t)w * e->sys_len], img.data(), e->sys_len * sizeof(double));
   return sadmc_set_systems(e, all.data(), all.size());
@@ -401,6 +412,27 @@ const char* sadmc_last_error(void) { return g_err.c_str(); }
 int sadmc_abi_version(void) { return SADMC_ABI_VERSION; }
 size_t sadmc_sizeof_config(void) { return sizeof(sadmc_config); }
 size_t sadmc_sizeof_walker_state(void) { return sizeof(sadmc_walker_state); }
+
+int sadmc_reference_system(const sadmc_config* cfg, double* buf, size_t n, size_t* needed) {
+  if (!cfg) return fail(SADMC_ERR_INVALID, "null argument");
+  sadmc_engine e; // host fields only: no device, no stream
+  e.cfg = *cfg;
+  e.host_only = true;
+  int rc = setup_params(&e);
+  if (rc) return rc;
+  if (needed) *needed = e.sys_len;
+  if (!buf) return 0;
+  if (n < e.sys_len) return fail(SADMC_ERR_INVALID, "system image needs %zu doubles, buffer holds %zu", e.sys_len, n);
+  std::vector<double> img;
+  try {
+    rc = reference_image(&e, img);
+  } catch (const std::exception& ex) {
+    return fail(SADMC_ERR_INVALID, "%s", ex.what());
+  }
+  if (rc) return rc;
+  memcpy(buf, img.data(), e.sys_len * sizeof(double));
+  return 0;
+}
 
 void sadmc_destroy(sadmc_engine* e) {
   if (!e) return;

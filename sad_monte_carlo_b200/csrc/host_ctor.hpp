@@ -204,5 +204,178 @@ inline std::vector<double> sw_image(uint32_t n, const double box[3], std::string
   return img;
 }
 
+// From<WcaNParams> with fcc = false, wca.rs:448-496: N*N times, drop N atoms uniformly in the box
+// one after another (add_atom_at + confirm, so E is the running sum the reference keeps, with
+// set_energy's error budget, wca.rs:164-177), keep the attempt with the lowest E (strict <, first
+// wins).  The RNG stream is one sequential generator seeded 0 and every attempt uses 3N draws, so
+// the attempts are independent given the generator state at their start: the states are recorded
+// in one cheap sequential pass and the attempts are then scored on all host threads.
+struct WcaScratch {
+  // the 27-fold subcell lists of optcell.rs:131-160, flattened: list of (atom, image offset) per subcell
+  struct Entry {
+    uint32_t atom;
+    int8_t o[3];
+  };
+  long nc[3];
+  double box[3], rc2;
+  std::vector<std::vector<Entry>> lists;
+  std::vector<V3> pos;
+  double E = 0.0, error = 0.0;
+
+  WcaScratch(const double b[3], double r_cut) {
+    for (int k = 0; k < 3; k++) {
+      box[k] = b[k];
+      nc[k] = (long)std::floor(b[k] / r_cut); // optcell.rs:64-66
+    }
+    rc2 = r_cut * r_cut;
+    lists.resize((size_t)(nc[0] * nc[1] * nc[2]));
+  }
+  void clear() {
+    for (auto& l : lists) l.clear();
+    pos.clear();
+    E = error = 0.0;
+  }
+  void subcell(const V3& r, long sc[3]) const { // optcell.rs:112-124
+    sc[0] = (long)std::floor(r.x / box[0] * (double)nc[0]);
+    sc[1] = (long)std::floor(r.y / box[1] * (double)nc[1]);
+    sc[2] = (long)std::floor(r.z / box[2] * (double)nc[2]);
+  }
+  size_t flat(const long q[3]) const { // optcell.rs:343-359
+    return (size_t)(((q[0] + nc[0]) % nc[0]) * nc[1] * nc[2] + ((q[1] + nc[1]) % nc[1]) * nc[2] + ((q[2] + nc[2]) % nc[2]));
+  }
+  double potential(double r2) const { // wca.rs:66-76
+    if (r2 < rc2) {
+      const double s = 1.0 / r2;
+      const double s3 = s * s * s;
+      return 4.0 * (s3 * s3 - s3) + 1.0;
+    }
+    return 0.0;
+  }
+  template <class F>
+  void neighbours(const V3& r, long exclude, F&& f) const { // optcell.rs:75-110
+    long sc[3];
+    subcell(r, sc);
+    for (const Entry& en : lists[flat(sc)]) {
+      if ((long)en.atom == exclude) continue;
+      const V3& p = pos[en.atom];
+      const V3 img{p.x - (double)en.o[0] * box[0], p.y - (double)en.o[1] * box[1], p.z - (double)en.o[2] * box[2]};
+      f(norm2(sub(img, r)));
+    }
+  }
+  double compute_energy() const { // wca.rs:222-230
+    double e = 0.0;
+    for (size_t a = 0; a < pos.size(); a++) neighbours(pos[a], (long)a, [&](double r2) { e += potential(r2); });
+    return e * 0.5;
+  }
+  void add_and_confirm(const V3& r) { // wca.rs:104-116 + 290-297 + 164-177
+    static const int8_t NB[27][3] = {{0, 0, 0},   {1, 0, 0},   {-1, 0, 0},  {0, 1, 0},  {0, -1, 0},  {0, 0, 1},   {0, 0, -1},
+                                     {0, 1, 1},   {0, 1, -1},  {0, -1, 1},  {0, -1, -1}, {1, 0, 1},  {1, 0, -1},  {-1, 0, 1},
+                                     {-1, 0, -1}, {1, 1, 0},   {1, -1, 0},  {-1, 1, 0}, {-1, -1, 0}, {1, 1, 1},   {-1, 1, 1},
+                                     {1, -1, 1},  {1, 1, -1},  {1, -1, -1}, {-1, 1, -1}, {-1, -1, 1}, {-1, -1, -1}}; // optcell.rs:373-405
+    double dabse = 0.0;
+    neighbours(r, -1, [&](double r2) { dabse += potential(r2); });
+    const double new_e = E + dabse;
+    const uint32_t index = (uint32_t)pos.size();
+    pos.push_back(r);
+    long sc[3];
+    subcell(r, sc);
+    for (int n = 0; n < 27; n++) {
+      long q[3];
+      Entry en;
+      en.atom = index;
+      for (int k = 0; k < 3; k++) {
+        q[k] = sc[k] + NB[n][k];
+        en.o[k] = (int8_t)(q[k] < 0 ? -1 : (q[k] == nc[k] ? 1 : 0));
+      }
+      lists[flat(q)].push_back(en);
+    }
+    const double n_at = (double)pos.size();
+    const double single = dabse > std::fabs(new_e) ? 1e-14 * dabse * n_at : 1e-14 * std::fabs(new_e) * n_at;
+    error += single * n_at;
+    if (error > std::fabs(new_e) * 1e-13 * n_at * n_at) {
+      E = compute_energy();
+      error = 1e-15 * E * n_at;
+    } else {
+      E = new_e;
+    }
+  }
+};
+
+} // namespace hostctor
+} // namespace sadmc
+
+#include <thread>
+
+namespace sadmc {
+namespace hostctor {
+
+inline std::vector<double> wca_image(uint32_t n, const double box[3], uint64_t attempts, unsigned n_threads = 0) {
+  const double r_cut = std::pow(2.0, 1.0 / 6.0); // wca.rs:61-63
+  if (attempts == 0) attempts = (uint64_t)n * n;
+  std::vector<Rng> start(attempts);
+  {
+    Rng rng;
+    seed_from_u64(0, &rng.s0, &rng.s1);
+    for (uint64_t a = 0; a < attempts; a++) {
+      start[a] = rng;
+      for (uint32_t k = 0; k < 3 * n; k++) rng.next(); // Uniform<f64>::sample draws exactly one u64
+    }
+  }
+  auto place = [&](Rng rng, std::vector<V3>& out) {
+    out.resize(n);
+    for (uint32_t k = 0; k < n; k++) {
+      out[k].x = rng.uniform_f64(0.0, box[0]);
+      out[k].y = rng.uniform_f64(0.0, box[1]);
+      out[k].z = rng.uniform_f64(0.0, box[2]);
+    }
+  };
+  if (n_threads == 0) n_threads = std::thread::hardware_concurrency();
+  if (n_threads == 0) n_threads = 1;
+  if (n_threads > attempts) n_threads = (unsigned)attempts;
+  std::vector<double> best_e(n_threads, 1e80);
+  std::vector<uint64_t> best_a(n_threads, ~0ull);
+  auto worker = [&](unsigned t) {
+    WcaScratch w(box, r_cut);
+    std::vector<V3> p;
+    const uint64_t lo = attempts * t / n_threads, hi = attempts * (t + 1) / n_threads;
+    for (uint64_t a = lo; a < hi; a++) {
+      place(start[a], p);
+      w.clear();
+      for (const V3& r : p) w.add_and_confirm(r);
+      if (w.E < best_e[t]) {
+        best_e[t] = w.E;
+        best_a[t] = a;
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < n_threads; t++) pool.emplace_back(worker, t);
+  worker(0);
+  for (auto& th : pool) th.join();
+  // contiguous attempt ranges in order + strict '<' == the sequential scan's "first lowest wins"
+  double be = 1e80;
+  uint64_t ba = ~0ull;
+  for (unsigned t = 0; t < n_threads; t++)
+    if (best_e[t] < be) {
+      be = best_e[t];
+      ba = best_a[t];
+    }
+  std::vector<V3> p;
+  if (ba != ~0ull) place(start[ba], p); // (every attempt at 1e80 or above: the reference keeps no atoms)
+  if (p.size() != n) return {};
+  // wca.rs:488-495: the kept positions are added once more, then E = compute_energy()
+  WcaScratch w(box, r_cut);
+  for (const V3& r : p) w.add_and_confirm(r);
+  std::vector<double> img;
+  for (auto& r : p) {
+    img.push_back(r.x);
+    img.push_back(r.y);
+    img.push_back(r.z);
+  }
+  img.push_back(w.compute_energy());
+  img.push_back(w.error);
+  return img;
+}
+
 } // namespace hostctor
 } // namespace sadmc

@@ -155,3 +155,24 @@ def test_wca_randomize_matches_reference_randomize():
         assert np.array_equal(gs[:-2], osys[:-2])
         assert abs(gs[-2] - osys[-2]) <= RTOL * max(1.0, abs(osys[-2]))
         assert eng.walker(w).status == 0
+
+
+def test_wca_reference_constructor_start_tracks_oracle():
+    # SADMC_INIT_REFERENCE: every walker starts from the N*N-attempt configuration of wca.rs:448-496 (built on the
+    # host by the library), then from_params relaxes it below max_allowed_energy (energy.rs:840-851) on the device
+    cfg = make_config("wca", "samc", N=40, reduced_density=0.5, energy_bin=1.0, n_walkers=4, seed=9, samc_t0=1e3,
+                      max_allowed_energy=400.0)
+    eng = WalkerEngine(cfg)
+    for w in (0, 3):
+        o = OracleMC(cfg, walker=w)
+        g, s = eng.walker(w), o.walker()
+        assert g.status == 0 and g.energy < 400.0
+        assert (g.rng_s0, g.rng_s1) == (s.rng_s0, s.rng_s1)  # the relaxation used the same number of draws
+        assert np.array_equal(eng.system(w)[:-2], o.system()[:-2])
+        assert abs(g.energy - s.energy) <= RTOL * max(1.0, abs(s.energy))
+    eng.run(5000)
+    o.run(5000)
+    g, s = eng.walker(3), o.walker()
+    assert (g.rng_s0, g.rng_s1, g.accepted_moves) == (s.rng_s0, s.rng_s1, s.accepted_moves)
+    assert np.array_equal(eng.bins(3)["histogram"], o.bins()["histogram"])
+    assert eng.verify_energy(3)
