@@ -21,7 +21,8 @@ import numpy as np
 
 from . import _abi
 
-SYSTEM_TAGS = {_abi.SYS_LJ: "Lj", _abi.SYS_ISING: "Ising", _abi.SYS_FAKE: "Fake"}  # Any variants, src/system/any.rs:61-78
+SYSTEM_TAGS = {_abi.SYS_LJ: "Lj", _abi.SYS_ISING: "Ising", _abi.SYS_FAKE: "Fake", _abi.SYS_WCA: "Wca", _abi.SYS_SW: "Sw",
+               _abi.SYS_TWO_WELLS: "TwoWells", _abi.SYS_FAKE_ERFINV: "FakeErfinv"}  # Any variants, src/system/any.rs:61-78
 EXTRA_LABEL = {_abi.SYS_WCA: "pressure", _abi.SYS_TWO_WELLS: "which"}           # data_to_collect labels
 
 
@@ -53,7 +54,85 @@ def _system_document(cfg, image):
         else:
             function, dim = {"Gaussian": {"sigma": cfg.fake_sigma}}, 3
         return {"Fake": {"position": [float(x) for x in image[:dim]], "function": function, "possible_change": [0.0] * dim}}
-    raise NotImplementedError("checkpoint documents for system kind %d are not written yet (Lj, Ising, Fake are)" % cfg.system)
+    if cfg.system in (_abi.SYS_WCA, _abi.SYS_SW):  # wca.rs:23-33, optsquare.rs:24-31 around optcell.rs:27-40
+        n = cfg.N
+        pos = np.asarray(image[:3 * n]).reshape(n, 3)
+        box = box_diagonal(cfg)
+        sw = cfg.system == _abi.SYS_SW
+        cell = {"box_diagonal": {"x": box[0], "y": box[1], "z": box[2]},
+                "r_cutoff": cfg.sw_well_width * 1.0 if sw else 2.0 ** (1.0 / 6.0),
+                "positions": [{"x": float(p[0]), "y": float(p[1]), "z": float(p[2])} for p in pos]}  # subcells: #[serde(skip)]
+        if sw:
+            return {"Sw": {"E": float(image[3 * n]), "cell": cell, "possible_change": "None"}}
+        return {"Wca": {"E": float(image[3 * n]), "error": float(image[3 * n + 1]), "cell": cell, "possible_change": "None"}}
+    if cfg.system == _abi.SYS_TWO_WELLS:  # two_wells.rs:219-232
+        n = cfg.N
+        params = {"N": int(n), "h2_to_h1": cfg.tw_h2_to_h1, "barrier_over_h1": cfg.tw_barrier_over_h1, "r2": cfg.tw_r2}
+        well = math.sqrt(cfg.tw_barrier_over_h1) * 1.0 + cfg.tw_r2 * math.sqrt(1.0 + cfg.tw_barrier_over_h1 - 1.0 / cfg.tw_h2_to_h1)
+        return {"TwoWells": {"position": [float(x) for x in image[:n]], "d_squared": float(image[n]), "parameters": params,
+                             "change": {"index": 0, "values": {"x": 0.0, "y": 0.0, "z": 0.0}},
+                             "well_position": well, "invcdf": two_wells_invcdf(int(n), cfg.tw_r2)}}
+    if cfg.system == _abi.SYS_FAKE_ERFINV:  # erfinv.rs:29-38
+        return {"FakeErfinv": {"position": [float(x) for x in image[:cfg.N]], "parameters": {"mean_energy": cfg.erfinv_mean_energy},
+                               "possible_change": []}}
+    raise NotImplementedError("no checkpoint document for system kind %d" % cfg.system)
+
+
+def box_diagonal(cfg):
+    """Cell::new (optcell.rs:44-61) behind CellDimensionsGivenNumber (wca.rs:396-401, optsquare.rs:360-368)."""
+    if cfg.cell_width[0] > 0:
+        return [abs(cfg.cell_width[k]) for k in range(3)]
+    if cfg.system == _abi.SYS_SW:
+        vol = cfg.N * (math.pi * 1.0 * 1.0 * 1.0 / 6.0) / cfg.filling_fraction
+    else:
+        vol = cfg.N / cfg.reduced_density
+    w = float(np.cbrt(vol))
+    return [w, w, w]
+
+
+_INVCDF = {}
+
+
+def two_wells_invcdf(dim, r2, num_points=10000, mult=100):
+    """`SystemInvCdf::new` (two_wells.rs:46-137): cumulative distributions used only by TwoWells::randomize, which no
+    `EnergyMC` run calls.  They are derived data, written so that the reference can deserialise the document; the
+    midpoint sums are vectorised here, so the last digits may differ from the reference's sequential loop."""
+    key = (dim, r2)
+    if key in _INVCDF:
+        return _INVCDF[key]
+    r1 = 1.0
+
+    def V(n):  # two_wells.rs:211-213
+        return math.pi ** (0.5 * n) / math.gamma(n * 0.5 + 1.0)
+
+    def cumulative(grid, pdf):
+        a, b = grid[:-1, None], grid[1:, None]
+        i = np.arange(mult)[None, :]
+        us = ((mult - 1 - i) * a + i * b) / (mult - 1)  # linspace(x[w], x[w+1], mult), two_wells.rs:36-43
+        du = us[:, 1] - us[:, 0]
+        mid = 0.5 * (us[:, 1:] + us[:, :-1])
+        return np.concatenate([[0.0], np.cumsum((du[:, None] * pdf(mid)).sum(axis=1))])
+
+    def pdf_x1(x):
+        x = np.asarray(x)
+        first = np.sqrt(np.maximum(r1 * r1 - x * x, 0.0)) ** (dim - 1)
+        hemi = np.sqrt(np.maximum(r2 * r2 - (x - r1 - r2) ** 2, 0.0)) ** (dim - 1)
+        return np.where(x <= math.sqrt(r1 * r1 - r2 * r2), first, np.where(x < r1 + r2, r2 ** (dim - 1), hemi)) * V(dim - 1)
+
+    i = np.arange(num_points)
+    x1 = ((num_points - 1 - i) * (-r1) + i * (r1 + 2.0 * r2)) / (num_points - 1)
+    stencils = np.zeros(num_points * dim)
+    c = cumulative(x1, pdf_x1)
+    stencils[:num_points] = c / c[-1]
+    xn = ((num_points - 1 - i) * (-1.0) + i * 1.0) / (num_points - 1)
+    for which in range(1, dim):
+        d = dim - which
+        c = cumulative(xn, lambda x: np.maximum(1.0 - x * x, 0.0) ** (0.5 * d) * V(d) / V(d + 1))
+        stencils[which * num_points:(which + 1) * num_points] = c / c[-1]
+    out = {"num_points": num_points, "dim": dim, "r1": r1, "r2": r2, "dx1_ball1": float(x1[1] - x1[0]),
+           "stencils": [float(v) for v in stencils]}
+    _INVCDF[key] = out
+    return out
 
 
 def _system_image(cfg, doc, length):
@@ -69,8 +148,19 @@ def _system_image(cfg, doc, length):
         n = body["N"]
         img[:n * n] = body["S"]
         img[n * n] = body["E"]
-    elif tag == "Fake":
+    elif tag in ("Fake", "FakeErfinv"):
         img[:len(body["position"])] = body["position"]
+    elif tag in ("Wca", "Sw"):
+        pos = body["cell"]["positions"]
+        n = len(pos)
+        for i, p in enumerate(pos):
+            img[3 * i:3 * i + 3] = (p["x"], p["y"], p["z"])
+        img[3 * n] = body["E"]
+        img[3 * n + 1] = body.get("error", 0.0)
+    elif tag == "TwoWells":
+        n = len(body["position"])
+        img[:n] = body["position"]
+        img[n] = body["d_squared"]
     else:
         raise NotImplementedError("cannot restore system variant %r" % tag)
     return img
@@ -162,8 +252,8 @@ def restore_walker(engine, w, doc):
               "have_visited": [1 if x else 0 for x in doc["have_visited_since_maxentropy"]], "wl_hist": wl_hist}
     for label, bc in bins.get("extra", {}).items():
         arrays["extra_total"], arrays["extra_count"] = bc["total"], bc["count"]
-    if tag == "Fake":
-        # Fake keeps no cached energy: System::energy evaluates the function (fake.rs:96-99) -- on the device, so
+    if tag in ("Fake", "FakeErfinv", "TwoWells"):
+        # these keep no cached energy: System::energy evaluates the function (fake.rs:96-99) -- on the device, so
         # that the restored value is the one the kernels would compute
         st.energy = engine.compute_energy(w)
     engine.set_walker_bins(w, st, arrays)
@@ -321,6 +411,69 @@ def load(path):
     ext = os.path.splitext(str(path))[1].lstrip(".")
     with open(path, "rb") as f:
         return loads(f.read(), ext)
+
+
+def config_from_document(doc, n_walkers=1, **overrides):
+    """The sadmc_config a checkpoint document implies -- what `--resume-from` needs (mc/mod.rs:92-106 deserialises the
+    whole EnergyMC; here the engine is re-created from the parameters the document carries and the walker restored)."""
+    tag, body = next(iter(doc["system"].items()))
+    kw = {}
+    if tag == "Lj":
+        system, kw = "lj", dict(N=len(body["positions"]), lj_radius=body["max_radius"])
+    elif tag == "Ising":
+        system, kw = "ising", dict(N=body["N"])
+    elif tag == "Fake":
+        system, fn = "fake", body["function"]
+        if fn == "Linear":
+            kw = dict(fake_function=_abi.FAKE_LINEAR, N=1)
+        else:
+            ftag, f = next(iter(fn.items()))
+            if ftag == "Quadratic":
+                kw = dict(fake_function=_abi.FAKE_QUADRATIC, N=f["dimensions"])
+            elif ftag == "Pieces":
+                kw = dict(fake_function=_abi.FAKE_PIECES, N=3, fake_a=f["a"], fake_b=f["b"], fake_e1=f["e1"], fake_e2=f["e2"])
+            else:
+                kw = dict(fake_function=_abi.FAKE_GAUSSIAN, N=3, fake_sigma=f["sigma"])
+    elif tag in ("Wca", "Sw"):
+        system = "wca" if tag == "Wca" else "sw"
+        b = body["cell"]["box_diagonal"]
+        kw = dict(N=len(body["cell"]["positions"]), cell_width=(b["x"], b["y"], b["z"]))
+        if tag == "Sw":
+            kw["sw_well_width"] = body["cell"]["r_cutoff"]
+    elif tag == "TwoWells":
+        p = body["parameters"]
+        system, kw = "two-wells", dict(N=p["N"], tw_h2_to_h1=p["h2_to_h1"], tw_barrier_over_h1=p["barrier_over_h1"], tw_r2=p["r2"])
+    elif tag == "FakeErfinv":
+        system, kw = "fake-erfinv", dict(N=len(body["position"]), erfinv_mean_energy=body["parameters"]["mean_energy"])
+    else:
+        raise NotImplementedError("system variant %r has no device kernel" % tag)
+    mtag, m = next(iter(doc["method"].items()))
+    if mtag == "Sad":
+        method, mk = "sad", dict(sad_min_T=m["min_T"])
+    elif mtag == "Samc":
+        method, mk = "samc", dict(samc_t0=m["t0"])
+    elif mtag == "WL":
+        method = "inv-t-wl" if m["inv_t"] else "wl"
+        mk = {} if m.get("min_gamma") is None else dict(wl_min_gamma=m["min_gamma"])
+    else:
+        method, mk = "canonical", dict(canonical_T=m["temperature"])
+    kw.update(mk)
+    for k in ("min_allowed_energy", "max_allowed_energy"):
+        if doc.get(k) is not None:
+            kw[k] = doc[k]
+    plan, value = next(iter(doc["move_plan"].items()))
+    kw["move_plan"] = _abi.MOVE_TRANSLATION_SCALE if plan == "TranslationScale" else _abi.MOVE_ACCEPTANCE_RATE
+    kw["move_value"] = value
+    bins = doc["bins"]
+    kw["energy_bin"] = bins["width"]
+    if kw.get("min_allowed_energy") is None or kw.get("max_allowed_energy") is None:
+        # no bounds to derive the device's bin window from: keep room for as many new bins as exist, on both sides
+        n = len(bins["lnw"])
+        span = max(n, 64) * bins["width"]
+        kw["bin_window_lo"] = bins["min"] - span
+        kw["bin_window_hi"] = bins["min"] + n * bins["width"] + span
+    kw.update(overrides)
+    return _abi.make_config(system, method, n_walkers=n_walkers, init_mode=_abi.INIT_EXTERNAL, **kw)
 
 
 def resume(cfg, save_as):

@@ -154,6 +154,13 @@ class Movie(Plugin):
         p = "Never" if self.period == NEVER else {"TotalMoves": self.period[1]}
         return {"movie_time": self.movie_time, "which_frame": self.which_frame, "period": p}
 
+    def restore(self, doc):
+        """`movies` of a checkpoint: all three fields are serialised (plugin.rs:403-408), a resumed run keeps its schedule."""
+        self.movie_time = doc.get("movie_time")
+        self.which_frame = int(doc.get("which_frame", 0))
+        p = doc.get("period", "Never")
+        self.period = NEVER if p == "Never" else total_moves(p["TotalMoves"])
+
     def shall_i_save(self, moves):  # 446-463
         if self.movie_time is not None and self.period == total_moves(moves):
             which = self.which_frame + 1

@@ -32,15 +32,29 @@ def same(a, b, ctx):
 
 
 @pytest.mark.parametrize("ext", ["yaml", "json", "cbor"])
-@pytest.mark.parametrize("case", ["lj31", "ising_wl", "fake"])
+@pytest.mark.parametrize("case", ["lj31", "ising_wl", "fake", "sw", "wca", "two_wells", "erfinv"])
 def test_checkpoint_file_resume_equals_continuous(ext, case, tmp_path):
     if case == "lj31":
         cfg = lj_cfg()
     elif case == "ising_wl":
         cfg = make_config("ising", "inv-t-wl", N=8, min_allowed_energy=-128.0, max_allowed_energy=50.0, n_walkers=3, seed=2)
+    elif case == "sw":  # tests/resume-sad.rs
+        cfg = make_config("sw", "sad", N=64, filling_fraction=0.25, sad_min_T=0.5, n_walkers=3, seed=1,
+                          move_plan=_abi.MOVE_ACCEPTANCE_RATE, move_value=0.5)
+    elif case == "wca":  # the N*N-attempt start, relaxed below max_allowed_energy by from_params; `pressure` extras
+        cfg = make_config("wca", "samc", N=20, reduced_density=0.4, energy_bin=1.0, n_walkers=3, seed=9, samc_t0=1e3,
+                          max_allowed_energy=200.0)
+    elif case == "two_wells":
+        cfg = make_config("two-wells", "sad", N=12, tw_h2_to_h1=1.1, tw_barrier_over_h1=0.1, tw_r2=0.5, sad_min_T=0.001,
+                          energy_bin=1e-3, move_value=1e-2, n_walkers=3, seed=1)
+    elif case == "erfinv":
+        cfg = make_config("fake-erfinv", "samc", N=3, erfinv_mean_energy=0.0, samc_t0=1e3, energy_bin=0.05, n_walkers=3, seed=5,
+                          bin_window_lo=-30.0, bin_window_hi=30.0)
     else:
         cfg = make_config("fake", "sad", fake_function=_abi.FAKE_QUADRATIC, N=3, sad_min_T=0.001, energy_bin=0.01,
                           n_walkers=4, seed=3, bin_window_lo=-2.5, bin_window_hi=4.0)
+    if ext != "yaml" and case in ("sw", "wca", "two_wells", "erfinv"):
+        pytest.skip("the three codecs are covered by the first three systems")
     full = WalkerEngine(cfg)
     full.run(15000)
     full.run(15000)
@@ -53,6 +67,43 @@ def test_checkpoint_file_resume_equals_continuous(ext, case, tmp_path):
     second = checkpoint.resume(cfg, save_as)
     second.run(15000)
     same(full, second, "%s %s" % (case, ext))
+    # --resume-from: the engine configuration is rebuilt from the document alone
+    doc = checkpoint.load(paths[0])
+    tag = next(iter(doc["system"]))
+    assert tag == checkpoint.SYSTEM_TAGS[cfg.system]
+    over = {}
+    if not _abi.isnan(cfg.bin_window_lo):
+        over = dict(bin_window_lo=cfg.bin_window_lo, bin_window_hi=cfg.bin_window_hi)
+    if cfg.system == _abi.SYS_LJ:
+        over["lanes_per_walker"] = cfg.lanes_per_walker
+    cfg2 = checkpoint.config_from_document(doc, n_walkers=cfg.n_walkers, **over)
+    third = checkpoint.resume(cfg2, save_as)
+    third.run(15000)
+    same(full, third, "%s %s from the document" % (case, ext))
+
+
+def test_system_documents_have_the_reference_field_names():
+    # wca.rs:23-33 + optcell.rs:27-40 (subcells are #[serde(skip)]), optsquare.rs:24-31, two_wells.rs:219-232, erfinv.rs:29-38
+    e = WalkerEngine(make_config("wca", "samc", N=20, reduced_density=0.4, samc_t0=1e3, max_allowed_energy=200.0, seed=9))
+    d = checkpoint.walker_document(e, 0)["system"]["Wca"]
+    assert set(d) == {"E", "error", "cell", "possible_change"} and d["possible_change"] == "None"
+    assert set(d["cell"]) == {"box_diagonal", "r_cutoff", "positions"} and len(d["cell"]["positions"]) == 20
+    assert d["cell"]["r_cutoff"] == 2.0 ** (1.0 / 6.0) and abs(d["cell"]["box_diagonal"]["x"] ** 3 - 50.0) < 1e-9
+    e = WalkerEngine(make_config("sw", "sad", N=50, filling_fraction=0.3, sad_min_T=0.5))
+    d = checkpoint.walker_document(e, 0)["system"]["Sw"]
+    assert set(d) == {"E", "cell", "possible_change"} and d["cell"]["r_cutoff"] == 1.3
+    e = WalkerEngine(make_config("two-wells", "sad", N=12, tw_h2_to_h1=1.1, tw_barrier_over_h1=0.1, tw_r2=0.5, sad_min_T=0.001,
+                                 energy_bin=1e-3, move_value=1e-2))
+    d = checkpoint.walker_document(e, 0)["system"]["TwoWells"]
+    assert set(d) == {"position", "d_squared", "parameters", "change", "well_position", "invcdf"}
+    assert set(d["invcdf"]) == {"num_points", "dim", "r1", "r2", "dx1_ball1", "stencils"} and len(d["invcdf"]["stencils"]) == 120000
+    st = np.array(d["invcdf"]["stencils"]).reshape(12, 10000)
+    assert (st[:, 0] == 0).all() and np.allclose(st[:, -1], 1.0) and (np.diff(st, axis=1) >= 0).all()
+    assert abs(st[5, 5000] - 0.5) < 1e-3  # the symmetric sphere coordinates: half the weight below 0
+    e = WalkerEngine(make_config("fake-erfinv", "samc", N=3, erfinv_mean_energy=0.0, samc_t0=1e3, energy_bin=0.05,
+                                 bin_window_lo=-30.0, bin_window_hi=30.0))
+    d = checkpoint.walker_document(e, 0)["system"]["FakeErfinv"]
+    assert set(d) == {"position", "parameters", "possible_change"} and d["parameters"] == {"mean_energy": 0.0}
 
 
 def test_document_has_the_reference_schema_and_feeds_the_reference_post_processing(tmp_path):
