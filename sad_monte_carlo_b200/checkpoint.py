@@ -466,12 +466,15 @@ def config_from_document(doc, n_walkers=1, **overrides):
     kw["move_value"] = value
     bins = doc["bins"]
     kw["energy_bin"] = bins["width"]
-    if kw.get("min_allowed_energy") is None or kw.get("max_allowed_energy") is None:
-        # no bounds to derive the device's bin window from: keep room for as many new bins as exist, on both sides
-        n = len(bins["lnw"])
-        span = max(n, 64) * bins["width"]
-        kw["bin_window_lo"] = bins["min"] - span
+    # The device keeps a fixed bin window.  The engine derives it from min/max_allowed_energy or from the system's own
+    # bounds (Ising, square well, fake, two wells); where a side has neither (LJ and WCA above, erfinv on both sides)
+    # leave room for as many new bins as the document holds.
+    n = len(bins["lnw"])
+    span = max(n, 64) * bins["width"]
+    if system in ("lj", "wca", "fake-erfinv") and kw.get("max_allowed_energy") is None:
         kw["bin_window_hi"] = bins["min"] + n * bins["width"] + span
+    if system == "fake-erfinv" and kw.get("min_allowed_energy") is None:
+        kw["bin_window_lo"] = bins["min"] - span
     kw.update(overrides)
     return _abi.make_config(system, method, n_walkers=n_walkers, init_mode=_abi.INIT_EXTERNAL, **kw)
 

@@ -60,7 +60,7 @@ def test_resume_from_continues_the_checkpoint_as_it_is(tmp_path):
 
 def test_many_walkers_one_file_each_and_walker_w_is_seed_plus_w(tmp_path):
     base = ["--lj-N", "13", "--lj-radius", "2", "--max-allowed-energy=0", "--sad-min-T", "0.05", "--energy-bin", "0.05",
-            "--translation-scale", "0.05", "--max-iter", "2e4", "--quiet"]
+            "--translation-scale", "0.05", "--max-iter", "2e4", "--quiet", "--lanes-per-walker", "1"]
     run(base + ["--seed", "3", "--num-walkers", "4", "--checkpoint-walkers", "3", "--save-as", "many.cbor"], tmp_path)
     assert sorted(os.listdir(tmp_path)) == ["many-w%06d.cbor" % w for w in range(3)]
     run(base + ["--seed", "5", "--save-as", "one.cbor"], tmp_path)
