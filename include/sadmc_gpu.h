@@ -250,6 +250,10 @@ int sadmc_resume(sadmc_engine* e, uint64_t moves);
 /* ---- window geometry ---------------------------------------------------- */
 /* Device window: bin j of every walker covers [lo + j*width, lo + (j+1)*width). */
 int sadmc_window(sadmc_engine* e, double* lo, double* width, uint32_t* nbins);
+/* `Cell::box_diagonal` and `Cell::r_cutoff` (optcell.rs:27-33) of the periodic fluids, as the engine derived them
+ * from CellWidth / CellVolume / ReducedDensity / FillingFraction (wca.rs:396-401, optsquare.rs:360-368, optcell.rs:44-50):
+ * what a checkpoint's `cell` records.  SADMC_ERR_INVALID for the other systems. */
+int sadmc_cell_box(sadmc_engine* e, double box_diagonal[3], double* r_cutoff);
 
 /* ---- merge for reporting ------------------------------------------------ */
 /* Fold the local walkers' bins into window-aligned sums, written to DEVICE

@@ -38,6 +38,7 @@ PROTOTYPES = {
     "sadmc_set_walker_bins": (C.c_int, [vp, C.c_uint32, C.POINTER(WalkerState), u64p, u64p, f64p, f64p, f64p, u64p, u8p, u64p, f64p, u64p]),
     "sadmc_resume": (C.c_int, [vp, C.c_uint64]),
     "sadmc_window": (C.c_int, [vp, f64p, f64p, C.POINTER(C.c_uint32)]),
+    "sadmc_cell_box": (C.c_int, [vp, f64p, f64p]),
     "sadmc_fold_select": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_int]),
     "sadmc_fold_device": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "sadmc_fold": (C.c_int, [vp, u64p, f64p, f64p, f64p, f64p, u64p]),

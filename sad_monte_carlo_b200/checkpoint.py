@@ -32,7 +32,7 @@ def _opt(x):
     return None if (isinstance(x, float) and math.isnan(x)) else x
 
 
-def _system_document(cfg, image):
+def _system_document(cfg, image, cell=None):
     """`system` field: the `Any` variant of this walker (positions etc.) from the ABI's f64 image."""
     if cfg.system == _abi.SYS_LJ:  # lj.rs:32-45
         n = cfg.N
@@ -57,10 +57,9 @@ def _system_document(cfg, image):
     if cfg.system in (_abi.SYS_WCA, _abi.SYS_SW):  # wca.rs:23-33, optsquare.rs:24-31 around optcell.rs:27-40
         n = cfg.N
         pos = np.asarray(image[:3 * n]).reshape(n, 3)
-        box = box_diagonal(cfg)
+        box, r_cutoff = cell  # from the engine (sadmc_cell_box): a cube root taken twice need not round the same way
         sw = cfg.system == _abi.SYS_SW
-        cell = {"box_diagonal": {"x": box[0], "y": box[1], "z": box[2]},
-                "r_cutoff": cfg.sw_well_width * 1.0 if sw else 2.0 ** (1.0 / 6.0),
+        cell = {"box_diagonal": {"x": box[0], "y": box[1], "z": box[2]}, "r_cutoff": r_cutoff,
                 "positions": [{"x": float(p[0]), "y": float(p[1]), "z": float(p[2])} for p in pos]}  # subcells: #[serde(skip)]
         if sw:
             return {"Sw": {"E": float(image[3 * n]), "cell": cell, "possible_change": "None"}}
@@ -76,18 +75,6 @@ def _system_document(cfg, image):
         return {"FakeErfinv": {"position": [float(x) for x in image[:cfg.N]], "parameters": {"mean_energy": cfg.erfinv_mean_energy},
                                "possible_change": []}}
     raise NotImplementedError("no checkpoint document for system kind %d" % cfg.system)
-
-
-def box_diagonal(cfg):
-    """Cell::new (optcell.rs:44-61) behind CellDimensionsGivenNumber (wca.rs:396-401, optsquare.rs:360-368)."""
-    if cfg.cell_width[0] > 0:
-        return [abs(cfg.cell_width[k]) for k in range(3)]
-    if cfg.system == _abi.SYS_SW:
-        vol = cfg.N * (math.pi * 1.0 * 1.0 * 1.0 / 6.0) / cfg.filling_fraction
-    else:
-        vol = cfg.N / cfg.reduced_density
-    w = float(np.cbrt(vol))
-    return [w, w, w]
 
 
 _INVCDF = {}
@@ -195,7 +182,7 @@ def walker_document(engine, w, save_as="resume.yaml", report=None, movies=None, 
     move_plan = ({"TranslationScale": cfg.move_value} if cfg.move_plan == _abi.MOVE_TRANSLATION_SCALE
                  else {"AcceptanceRate": cfg.move_value})
     return {
-        "system": _system_document(cfg, engine.system(w)),
+        "system": _system_document(cfg, engine.system(w), engine.cell_box() if cfg.system in (_abi.SYS_WCA, _abi.SYS_SW) else None),
         "method": _method_document(cfg, st, b),
         "moves": int(st.moves), "time_L": 0, "accepted_moves": int(st.accepted_moves),
         "min_allowed_energy": _opt(cfg.min_allowed_energy), "max_allowed_energy": _opt(cfg.max_allowed_energy),

@@ -951,6 +951,15 @@ int sadmc_window(sadmc_engine* e, double* lo, double* width, uint32_t* nbins) {
   return 0;
 }
 
+int sadmc_cell_box(sadmc_engine* e, double box_diagonal[3], double* r_cutoff) {
+  if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  if (e->cfg.system != SADMC_SYS_WCA && e->cfg.system != SADMC_SYS_SW) return fail(SADMC_ERR_INVALID, "system %d has no periodic cell", e->cfg.system);
+  if (box_diagonal)
+    for (int k = 0; k < 3; k++) box_diagonal[k] = e->P.box[k];
+  if (r_cutoff) *r_cutoff = e->cfg.system == SADMC_SYS_SW ? e->cfg.sw_well_width * 1.0 : std::pow(2.0, 1.0 / 6.0);
+  return 0;
+}
+
 // ---- merge for reporting -------------------------------------------------------
 int sadmc_fold_select(sadmc_engine* e, uint32_t first_walker, uint32_t walker_stride, int sad_range_only) {
   if (!e) return fail(SADMC_ERR_INVALID, "null engine");

@@ -173,6 +173,12 @@ class WalkerEngine:
         self._check(self.L.sadmc_window(self.h, C.byref(lo), C.byref(width), C.byref(n)))
         return lo.value, width.value, n.value
 
+    def cell_box(self):
+        """(box_diagonal[3], r_cutoff) of a periodic fluid: `Cell` of optcell.rs:27-33 as the engine derived it."""
+        box, rc = (C.c_double * 3)(), C.c_double()
+        self._check(self.L.sadmc_cell_box(self.h, box, C.byref(rc)))
+        return [box[0], box[1], box[2]], rc.value
+
     def fold_select(self, first_walker=0, walker_stride=1, sad_range_only=False):
         """Which walkers the following folds merge (interleaved groups: ensemble error bars) and whether SAD
         walkers contribute ln w only inside their own [too_lo, too_hi]."""
