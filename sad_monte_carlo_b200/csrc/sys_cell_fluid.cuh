@@ -31,7 +31,10 @@ struct CellFluidSys {
   static constexpr int G = 32;
   static constexpr bool FAST_BOOK = false;
   static constexpr int BLOCK = 128;
-  static constexpr int MIN_BLOCKS = 4;
+#ifndef SADMC_FLUID_MIN_BLOCKS
+#define SADMC_FLUID_MIN_BLOCKS 4
+#endif
+  static constexpr int MIN_BLOCKS = SADMC_FLUID_MIN_BLOCKS;
   static constexpr bool COOP = false;
   __device__ __forceinline__ void set_cooperative(bool) {}
   __device__ __forceinline__ void finish_move() {}
@@ -249,22 +252,59 @@ struct CellFluidSys {
     }
   }
 
-  __device__ double compute_energy() const { // wca.rs:222-230 / optsquare.rs:176-186
-    double acc = 0.0;
-    int cnt = 0;
-    for (int i = 0; i < N; i++) {
-      if (SW) {
-        const double w2 = wsqr;
-        for_neighbours(px[i], py[i], pz[i], i, [&](double d2) {
-          if (d2 < w2) cnt -= 1;
-        });
-      } else {
-        for_neighbours(px[i], py[i], pz[i], i, [&](double d2) { acc += wca_potential(d2); });
+  // Sum over ATOMS in parallel: lane l takes atoms l, l + 32, ... and visits, for each, the 27 neighbouring cells
+  // one after the other (same candidate set and imaged coordinates as for_neighbours).  The per-move lookups
+  // spread one atom's 27 cells over the lanes; a whole-system sum done that way runs N serial rounds per warp
+  // (subcell index with three f64 divides per round), and `set_energy` asks for one every ~10 accepted moves
+  // (wca.rs:164-177) -- it was most of the WCA kernel's time.
+  template <class F>
+  __device__ __forceinline__ void for_all_pairs(int natoms, F&& f) const {
+    for (int i = lane; i < natoms; i += 32) {
+      const double rx = px[i], ry = py[i], rz = pz[i];
+      int cx, cy, cz;
+      subcell(rx, ry, rz, cx, cy, cz);
+      for (int dx = -1; dx <= 1; dx++) {
+        int qx = cx + dx;
+        double ox = 0.0;
+        if (qx < 0) {
+          qx += ncx;
+          ox = 1.0;
+        } else if (qx >= ncx) {
+          qx -= ncx;
+          ox = -1.0;
+        }
+        for (int dy = -1; dy <= 1; dy++) {
+          int qy = cy + dy;
+          double oy = 0.0;
+          if (qy < 0) {
+            qy += ncy;
+            oy = 1.0;
+          } else if (qy >= ncy) {
+            qy -= ncy;
+            oy = -1.0;
+          }
+          for (int dz = -1; dz <= 1; dz++) {
+            int qz = cz + dz;
+            double oz = 0.0;
+            if (qz < 0) {
+              qz += ncz;
+              oz = 1.0;
+            } else if (qz >= ncz) {
+              qz -= ncz;
+              oz = -1.0;
+            }
+            for (int j = head[flat(qx, qy, qz)]; j >= 0; j = next[j]) {
+              if (j == i) continue;
+              const double ix = px[j] - ox * Lx, iy = py[j] - oy * Ly, iz = pz[j] - oz * Lz;
+              const double ex = ix - rx, ey = iy - ry, ez = iz - rz;
+              f(ex * ex + ey * ey + ez * ez);
+            }
+          }
+        }
       }
     }
-    if (SW) return (double)warp_sum_int(cnt) * 0.5;
-    return warp_sum(acc) * 0.5;
   }
+  __device__ double compute_energy() const { return compute_energy_first(N); } // wca.rs:222-230 / optsquare.rs:176-186
   // optsquare.rs:108-152: all pairs, all 27 images, no cell list (SquareWell::verify_energy)
   __device__ double compute_energy_slowly() const {
     int cnt = 0;
@@ -379,9 +419,18 @@ struct CellFluidSys {
     E = compute_energy();
     return E;
   }
+  // the same sum over the first `natoms` atoms (randomize adds them one by one)
   __device__ double compute_energy_first(int natoms) const {
     double acc = 0.0;
-    for (int i = 0; i < natoms; i++) for_neighbours(px[i], py[i], pz[i], i, [&](double d2) { acc += wca_potential(d2); });
+    int cnt = 0;
+    if (SW) {
+      const double w2 = wsqr;
+      for_all_pairs(natoms, [&](double d2) {
+        if (d2 < w2) cnt -= 1;
+      });
+      return (double)warp_sum_int(cnt) * 0.5;
+    }
+    for_all_pairs(natoms, [&](double d2) { acc += wca_potential(d2); });
     return warp_sum(acc) * 0.5;
   }
   __device__ bool verify_energy() const {
@@ -395,7 +444,7 @@ struct CellFluidSys {
     if (SW) return false;
     if (moves % ((unsigned long long)N * (unsigned long long)N) != 0) return false;
     double p = 0.0;
-    for (int i = 0; i < N; i++) for_neighbours(px[i], py[i], pz[i], i, [&](double d2) { p += wca_pressure(d2); });
+    for_all_pairs(N, [&](double d2) { p += wca_pressure(d2); });
     p = warp_sum(p);
     v = p / (3.0 * (Lx * Ly * Lz));
     return true;
