@@ -32,7 +32,7 @@ struct CellFluidSys {
   static constexpr bool FAST_BOOK = false;
   static constexpr int BLOCK = 128;
 #ifndef SADMC_FLUID_MIN_BLOCKS
-#define SADMC_FLUID_MIN_BLOCKS 4
+#define SADMC_FLUID_MIN_BLOCKS 5
 #endif
   static constexpr int MIN_BLOCKS = SADMC_FLUID_MIN_BLOCKS;
   static constexpr bool COOP = false;
