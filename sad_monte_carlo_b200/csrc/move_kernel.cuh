@@ -14,6 +14,16 @@ namespace sadmc {
 
 constexpr int ZIG_SMEM_BYTES = 4128; // 2 * 257 doubles, padded to 32 B
 
+// Systems that let the move loop evaluate the next proposal's draws one move ahead declare PREDRAW (rng.cuh).
+template <class S, class = void>
+struct HasPredraw {
+  static constexpr bool value = false;
+};
+template <class S>
+struct HasPredraw<S, decltype((void)S::PREDRAW)> {
+  static constexpr bool value = S::PREDRAW;
+};
+
 template <int G>
 __device__ __forceinline__ unsigned group_mask() {
   if (G >= 32) return 0xffffffffu;
@@ -161,6 +171,9 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
   // sqrt(1 / moves) of the NEXT move is evaluated one move ahead, in the shadow of the bin-record load
   // (it depends on nothing but the move counter); same IEEE operations, so the value is unchanged.
   double recent_next = sqrt(1.0 / (double)(moves0 + 1)); // energy.rs:913
+  constexpr bool PREDRAW = HasPredraw<Sys>::value;
+  PreDraw pre; // the draws of the coming proposal when pre.ok, evaluated during the previous move
+  pre.ok = false;
 #pragma unroll 1
   for (unsigned long long m = 0; m < n_moves; m++) {
     moves += 1; // energy.rs:905
@@ -172,8 +185,11 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
     int i2 = i1;
     BinLo r2;
     BinHi h2;
-    r2.lnw = 0.0;
-    r2.hist = 0;
+    // ln w and histogram of the bin the proposal lands in: the current bin's cached values unless the load below
+    // replaces them (no select on the loaded registers afterwards: a copy right behind the load would stall the warp
+    // there for the whole DRAM latency instead of at the accept test)
+    r2.lnw = bk.c_lnw;
+    r2.hist = bk.c_hist;
     r2.etot = 0.0;
     r2.e2tot = 0.0;
     h2.t_found = 0;
@@ -182,7 +198,19 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
     h2.wl_hist = 0;
     if (!halted) {
       bk.acc_rate *= 1.0 - recent_scale;
-      if (sys.plan_move(rng, bk.tscale, zx, zf, e2)) { // energy.rs:915
+      bool some;
+      if constexpr (PREDRAW) {
+        if (pre.ok) {
+          rng.s0 = pre.s0;
+          rng.s1 = pre.s1;
+          some = sys.plan_move_drawn((int)pre.which, pre.v0, pre.v1, pre.v2, bk.tscale, e2);
+        } else {
+          some = sys.plan_move(rng, bk.tscale, zx, zf, e2);
+        }
+      } else {
+        some = sys.plan_move(rng, bk.tscale, zx, zf, e2);
+      }
+      if (some) { // energy.rs:915
         bool out_of_bounds = false;
         if (P.has_max) out_of_bounds = e2 > P.max_allowed && e2 > e1;
         if (P.has_min) out_of_bounds = out_of_bounds || (e2 < P.min_allowed && e2 < e1);
@@ -210,9 +238,21 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
     // first-visit hook changes its inputs).
     recent_next = sqrt(1.0 / (double)(moves + 1));
     double gamma_now = bk.gamma(moves);
+    // ... and the next proposal's random numbers, for both places the stream can be at after the accept test
+    PreDraw pre_b;
+    unsigned long long rs0 = 0, rs1 = 0;
+    if constexpr (PREDRAW) {
+      pre.ok = false;
+      pre_b.ok = false;
+      if (!halted) {
+        predraw_both(rng, sys.predraw_n(), sys.predraw_zone(), zx, zf, pre, pre_b);
+        rs0 = rng.s0;
+        rs1 = rng.s1;
+      }
+    }
     if (proposing) {
-      const double lnw2 = other_bin ? r2.lnw : bk.c_lnw;
-      const unsigned long long hist2 = other_bin ? r2.hist : bk.c_hist;
+      const double lnw2 = r2.lnw;
+      const unsigned long long hist2 = r2.hist;
       const unsigned long long tL_before = bk.tL;
       if (!bk.reject_move(e1, e2, i2, lnw2, hist2, moves, rng)) { // energy.rs:927-931
         accepted = true;
@@ -221,6 +261,9 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
         sys.confirm();
       }
       if (METHOD == SADMC_METHOD_SAD && bk.tL != tL_before) gamma_now = bk.gamma(moves); // energy.rs:466-483 fired
+    }
+    if constexpr (PREDRAW) {
+      if (rng.s0 != rs0 || rng.s1 != rs1) pre = pre_b; // the accept test drew its uniform: the proposal starts one word later
     }
     if (Sys::COOP) sys.finish_move(); // converged point: warp-cooperative energy recomputation
     if (accepted) {

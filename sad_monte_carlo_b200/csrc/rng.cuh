@@ -188,6 +188,80 @@ struct Rng {
   }
 };
 
+// ---- the NEXT proposal's draws, evaluated one move ahead (move_kernel.cuh, Sys::PREDRAW) -----------------------
+// A proposal of the cluster systems is `Uniform::new(0, N)` + three StandardNormals (lj.rs:368-369): words
+// W, Z0, Z1, Z2 of the stream, Z3 / Z4 when one ziggurat draw leaves the fast path (normal3 above).  Which word
+// the proposal starts at is only known once the current move's accept test has or has not drawn its uniform
+// (energy.rs:465) -- and that test waits ~1 600 cycles for the bin record.  So both candidates (start at word 0,
+// start at word 1) are evaluated in the shadow of that load from the seven words the two of them can touch, and the
+// move loop picks one afterwards.  `ok == false` (integer rejection zone, ziggurat tail layer, two irregular draws
+// in one call: ~0.1 % of proposals) means "not evaluated": the caller then draws the proposal the ordinary way from
+// the unchanged generator state, so the stream is the reference's in every case.
+struct PreDraw {
+  double v0, v1, v2;
+  uint64_t s0, s1; // generator state after the proposal's draws
+  uint32_t which;
+  bool ok;
+};
+// One candidate: ww = the integer word, z0..z4 = the following five words, (e2s0,e2s1) / (e3s0,e3s1) / (e4s0,e4s1) =
+// generator state after z2 / z3 / z4.
+__device__ __forceinline__ PreDraw predraw_one(uint64_t ww, uint64_t z0, uint64_t z1, uint64_t z2, uint64_t z3, uint64_t z4, uint64_t e2s0,
+                                               uint64_t e2s1, uint64_t e3s0, uint64_t e3s1, uint64_t e4s0, uint64_t e4s1, uint32_t n, uint64_t zone,
+                                               const double* zx, const double* zf) {
+  PreDraw r;
+  r.which = (uint32_t)SADMC_UMUL64HI(ww, (uint64_t)n);
+  const bool which_ok = ww * (uint64_t)n <= zone; // Rng::below's acceptance
+#define SADMC_ZIG_FAST(k)                                                                 \
+  const uint32_t i##k = (uint32_t)(z##k & 0xff);                                           \
+  const double n##k = (sadmc_bits_f64((z##k >> 12) | 0x4000000000000000ull) - 3.0) * zx[i##k]; \
+  const bool ok##k = fabs(n##k) < zx[i##k + 1];
+  SADMC_ZIG_FAST(0)
+  SADMC_ZIG_FAST(1)
+  SADMC_ZIG_FAST(2)
+  if (ok0 && ok1 && ok2) {
+    r.v0 = n0;
+    r.v1 = n1;
+    r.v2 = n2;
+    r.s0 = e2s0;
+    r.s1 = e2s1;
+    r.ok = which_ok;
+    return r;
+  }
+  SADMC_ZIG_FAST(3)
+  SADMC_ZIG_FAST(4)
+#undef SADMC_ZIG_FAST
+  // exactly Rng::normal3's single-irregular-draw case
+  const int f = !ok0 ? 0 : (!ok1 ? 1 : 2);
+  const uint32_t fi = f == 0 ? i0 : (f == 1 ? i1 : i2);
+  const double fx = f == 0 ? n0 : (f == 1 ? n1 : n2);
+  const uint64_t fu = f == 0 ? z1 : (f == 1 ? z2 : z3);
+  const double u01 = (double)(fu >> 11) * (1.0 / 9007199254740992.0);
+  const bool acc = exp_cmp(zf[fi + 1] + (zf[fi] - zf[fi + 1]) * u01, -fx * fx / 2.0) < 0;
+  const bool need_ok = f == 0 ? (acc ? (ok2 && ok3) : (ok2 && ok3 && ok4)) : (f == 1 ? (acc ? ok3 : (ok3 && ok4)) : (acc ? true : ok4));
+  r.v0 = f == 0 ? (acc ? n0 : n2) : n0;
+  r.v1 = f == 0 ? (acc ? n2 : n3) : (f == 1 ? (acc ? n1 : n3) : n1);
+  r.v2 = f == 2 ? (acc ? n2 : n4) : (acc ? n3 : n4);
+  r.s0 = acc ? e3s0 : e4s0;
+  r.s1 = acc ? e3s1 : e4s1;
+  r.ok = which_ok && fi != 0 && need_ok;
+  return r;
+}
+// Both candidates from generator state `g` (taken by value: the caller's generator is not advanced).
+__device__ __forceinline__ void predraw_both(Rng g, uint32_t n, uint64_t zone, const double* zx, const double* zf, PreDraw& a, PreDraw& b) {
+  const uint64_t w0 = g.next();
+  const uint64_t w1 = g.next();
+  const uint64_t w2 = g.next();
+  const uint64_t w3 = g.next();
+  const uint64_t t3s0 = g.s0, t3s1 = g.s1; // after w3
+  const uint64_t w4 = g.next();
+  const uint64_t t4s0 = g.s0, t4s1 = g.s1;
+  const uint64_t w5 = g.next();
+  const uint64_t t5s0 = g.s0, t5s1 = g.s1;
+  const uint64_t w6 = g.next();
+  a = predraw_one(w0, w1, w2, w3, w4, w5, t3s0, t3s1, t4s0, t4s1, t5s0, t5s1, n, zone, zx, zf);
+  b = predraw_one(w1, w2, w3, w4, w5, w6, t4s0, t4s1, t5s0, t5s1, g.s0, g.s1, n, zone, zx, zf);
+}
+
 // zone of UniformInt::sample_single (conservative power-of-two approximation)
 __host__ __device__ inline uint64_t zone_single(uint64_t n) {
   int lz = 0;
