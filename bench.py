@@ -162,6 +162,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = load_library()
+    if args.exact and args.lanes != 1:
+        args.lanes = 1  # the reference's sequential pair sum cannot be split across lanes
+    if args.walkers == 0:
+        # whole waves of resident CTAs: 148 SMs x 3 CTAs x 64 walkers x 3 waves (two lanes) / 148 x 2 x 128 x 2 (one lane)
+        args.walkers = 85248 if args.lanes == 2 else 75776
     W = args.walkers
     cfg = lj31_config(W, walker_offset=rank * W, device=local, lanes=args.lanes,
                       flags=(1 if args.no_round_trips else 0) | (0 if args.exact else 4))
@@ -268,7 +273,7 @@ def run_ours(args):
                          "traffic": None, "per_unit": "900 FP64 flop per move (30 per pair x 30 pairs), divide = 1 flop; "
                                                       "`achieved` = 900 x moves per launch / average launch duration",
                          "peak_source": "DFMA microkernel in this library, measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                         "kernel": "move_kernel<LjThreadSys<fast, 31, 1>, SAD>", "ms_per_launch": ms_max / args.steps},
+                         "kernel": "move_kernel<LjThreadSys<%s, 31, %d>, SAD>" % ("exact" if args.exact else "fast", args.lanes), "ms_per_launch": ms_max / args.steps},
             "roofline_hbm": {"bound": "hbm", "achieved": per_gpu_moves_s * BYTES_PER_MOVE / 1e9, "peak": peaks.get("hbm_gbs"),
                              "unit": "GB/s", "frac": per_gpu_moves_s * BYTES_PER_MOVE / 1e9 / peaks.get("hbm_gbs"),
                              "traffic": NCU_DRAM_BYTES_PER_MOVE * W * args.moves_per_step,
@@ -297,7 +302,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--walkers", type=int, default=int(os.environ.get("SADMC_BENCH_WALKERS", 75776)), help="walkers per GPU")
+    ap.add_argument("--walkers", type=int, default=int(os.environ.get("SADMC_BENCH_WALKERS", 0)),
+                    help="walkers per GPU (default: whole waves of resident CTAs: 75 776 = two waves at one lane per walker, 85 248 = three at two)")
     ap.add_argument("--moves-per-step", type=int, default=int(os.environ.get("SADMC_BENCH_MOVES", 20000)))
     ap.add_argument("--burn-in", type=int, default=int(os.environ.get("SADMC_BENCH_BURN_IN", 200000)))
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("SADMC_BENCH_LANES", 1)))

@@ -90,8 +90,9 @@ static int pick_kernels(sadmc_engine* e) {
     case SADMC_SYS_FAKE_ERFINV: e->ks = kernels_erfinv(P); return 0;
     case SADMC_SYS_LJ: {
       int G = c.lanes_per_walker;
-      if (G == 0) G = c.n_walkers >= 16384 ? 1 : (c.n_walkers >= 4096 ? 8 : 32);
       const bool fast = (c.flags & SADMC_FLAG_FAST_MATH) != 0;
+      // many walkers: one thread per walker, cluster in shared memory (the fastest measured); few: a warp or part of one
+      if (G == 0) G = c.n_walkers >= 16384 ? 1 : (c.n_walkers >= 4096 ? 8 : 32);
       if (G == 1 || (fast && (G == 2 || G == 4))) { // configuration in shared memory (sys_lj_thread.cuh)
         if (c.N > 64) return fail(SADMC_ERR_UNSUPPORTED, "lj: shared-memory kernels hold N <= 64 atoms (N=%u)", c.N);
         const bool ok = !fast ? kernels_lj_thread_exact((int)c.N, P, &e->ks)

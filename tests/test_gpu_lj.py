@@ -165,8 +165,9 @@ def test_lj_thread_per_walker_exact_other_methods(method, kw):
         assert_walker_equal(eng, w, o, exact=True, context=method)
 
 
-def test_lj_thread_per_walker_fast_math_per_move_energy_within_1e12():
-    cfg = lj_cfg(n_walkers=4, lanes=1, flags=_abi.FLAG_FAST_MATH)
+@pytest.mark.parametrize("lanes", [1, 2, 4])
+def test_lj_thread_per_walker_fast_math_per_move_energy_within_1e12(lanes):
+    cfg = lj_cfg(n_walkers=4, lanes=lanes, flags=_abi.FLAG_FAST_MATH)
     eng = WalkerEngine(cfg)
     o = OracleMC(lj_cfg(n_walkers=4, lanes=1), walker=1)
     worst = 0.0
@@ -191,8 +192,9 @@ def test_lj_thread_per_walker_fast_math_per_move_energy_within_1e12():
     print("fast-math worst relative per-move energy error: %.3g" % worst)
 
 
-def test_lj_thread_per_walker_fast_math_tracks_reference_trajectory():
-    cfg = lj_cfg(n_walkers=100, lanes=1, flags=_abi.FLAG_FAST_MATH)
+@pytest.mark.parametrize("lanes", [1, 2, 4])
+def test_lj_thread_per_walker_fast_math_tracks_reference_trajectory(lanes):
+    cfg = lj_cfg(n_walkers=100, lanes=lanes, flags=_abi.FLAG_FAST_MATH)
     eng = WalkerEngine(cfg)
     oracles = {w: OracleMC(lj_cfg(n_walkers=100, lanes=1), walker=w) for w in (0, 50, 99)}
     eng.run(60000)  # long enough for several warp-cooperative energy recomputations per walker
@@ -209,7 +211,8 @@ def test_lj_thread_per_walker_fast_math_tracks_reference_trajectory():
 # ---- converged physics: heat capacity of LJ31 against the literature curves the reference ships -------------------
 
 @pytest.mark.timeout(600)
-def test_lj31_heat_capacity_short_run_approaches_the_reference_curve():
+@pytest.mark.parametrize("lanes", [1, 2])  # 1: the kernel bench.py times
+def test_lj31_heat_capacity_short_run_approaches_the_reference_curve(lanes):
     """A 15-second version of tools/lj31_cv_run.py (the full 1e8-move run is pinned on the CPU side by
     tests/test_analysis.py from its committed folds): 37 888 SAD walkers x 3e6 moves, min_T 0.15, energy bin 0.1.
     Stated tolerance for this SHORT run: within 12 % of tRem_Ref.csv (the curve of the reference's own error metric,
@@ -218,7 +221,7 @@ def test_lj31_heat_capacity_short_run_approaches_the_reference_curve():
     from sad_monte_carlo_b200 import analysis
     W, G = 37888, 8
     cfg = make_config("lj", "sad", N=31, lj_radius=2.5, max_allowed_energy=0.0, sad_min_T=0.15, energy_bin=0.1,
-                      move_value=0.05, n_walkers=W, init_mode=_abi.INIT_RANDOMIZE, lanes_per_walker=1, seed=0,
+                      move_value=0.05, n_walkers=W, init_mode=_abi.INIT_RANDOMIZE, lanes_per_walker=lanes, seed=0,
                       flags=_abi.FLAG_FAST_MATH, bin_window_lo=-133.7, bin_window_hi=0.2)
     eng = WalkerEngine(cfg)
     for _ in range(3):
