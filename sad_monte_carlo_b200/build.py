@@ -50,7 +50,25 @@ def needs_build():
     return _stale(OUT, units() + headers())
 
 
+HOST_SRC = os.path.join(ROOT, "host")
+HOST_BIN = os.path.join(HERE, "bin", "histogram")
+
+
+def build_host(force=False, verbose=False):
+    """The compiled host: host/histogram.cpp -> sad_monte_carlo_b200/bin/histogram (dlopens libsadmc_gpu.so)."""
+    srcs = [os.path.join(HOST_SRC, f) for f in os.listdir(HOST_SRC)] + [os.path.join(ROOT, "include", "sadmc_gpu.h")]
+    if not force and not _stale(HOST_BIN, srcs):
+        return HOST_BIN
+    os.makedirs(os.path.dirname(HOST_BIN), exist_ok=True)
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-o", HOST_BIN, os.path.join(HOST_SRC, "histogram.cpp"), "-ldl"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd, cwd=ROOT)
+    return HOST_BIN
+
+
 def build(force=False, verbose=False, extra=()):
+    build_host(force=force, verbose=verbose)
     if not force and not needs_build():
         return OUT
     extra = list(extra) + os.environ.get("SADMC_NVCC_EXTRA", "").split()

@@ -1,0 +1,153 @@
+"""The compiled host (host/*.hpp, host/histogram.cpp -> sad_monte_carlo_b200/bin/histogram): the same command line,
+the same documents and the same three codecs as the Python host, checked against it on the CPU (`--dry-run` and
+`--convert` need no GPU)."""
+import json
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from sad_monte_carlo_b200 import build, checkpoint, histogram
+
+BIN = build.build_host()
+
+COMMAND_LINES = [
+    "--lj-N 31 --max-allowed-energy=0 --sad-min-T 0.01 --translation-scale 0.05 --energy-bin 0.01 --save-as lj-sad-31-bin001.yaml "
+    "--movie-time 10^(1/8) --save-time 0.5 --lj-radius 2.5 --seed=3",                                    # run-lj-clusters.sh:53
+    "--sw-N=100 --sw-filling-fraction=0.3 --sw-well-width=1.3 --sad-min-T=0.5 --acceptance-rate=0.5 --max-iter=1000 --save-as=big-guy.yaml",
+    "--ising-N 32 --wl --wl-min-gamma=1e-4 --min-allowed-energy=-2048 --max-allowed-energy=50",
+    "--lj-N 31 --lj-radius 2.5 --Inv-t-WL --min-allowed-energy=-133.53 --max-allowed-energy=-110 --energy-bin 0.001",
+    "--lj-N 38 --lj-radius 3 --inv-t-wl --max-iter 1e9 --quiet",
+    "--lj-N 31 --lj-radius 2.5 --samc-t0 1e5 --max-independent-samples 12",
+    "--wca-reduced-density 0.8 --wca-N 256 --samc-t0 1e7 --max-allowed-energy 2560",
+    "--wca-cell-volume 1000 --wca-N 256 --sad-min-T 1",
+    "--wca-cell-width=5,6,7 --wca-N 20 --sad-min-T 1",
+    "--sw-cell-width 6 7 8 --sw-N 10 --sw-well-width 1.5 --sad-min-T 1",
+    "--fake-linear --sad-min-T 0.001 --energy-bin 0.01",
+    "--fake-quadratic-dimensions 3 --sad-min-T 0.001",
+    "--fake-pieces-a 0.1 --fake-pieces-b 0.2 --fake-pieces-e1 1.0 --fake-pieces-e2 0.5 --sad-min-T 0.1",
+    "--fake-gaussian-sigma 0.3 --sad-min-T 0.1",
+    "--fake-erfinv-mean-energy 0 --fake-erfinv-N 3 --sad-min-T 0.1",
+    "--two-wells-N 12 --two-wells-h2-to-h1 1.1 --two-wells-barrier-over-h1 0.1 --two-wells-r2 1/2 --sad-min-T 0.001 --seed 7",
+    "--ising-N 16 --T 2.5",
+    "--ising-N 16 --sad-min-T sqrt(2)*pi --num-walkers 4096 --gpu-device 3 --bin-window-lo -600 --bin-window-hi 600 --fast-math --lanes-per-walker 1",
+]
+
+
+def run(argv, check=True, cwd=None):
+    r = subprocess.run([BIN] + argv, capture_output=True, text=True, cwd=cwd)
+    if check:
+        assert r.returncode == 0, r.stderr
+    return r
+
+
+def same(a, b):
+    if isinstance(a, float) and isinstance(b, float):
+        return a == b or (math.isnan(a) and math.isnan(b))
+    if isinstance(a, dict) and isinstance(b, dict):
+        return list(a) == list(b) and all(same(a[k], b[k]) for k in a)
+    if isinstance(a, list) and isinstance(b, list):
+        return len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+    return type(a) is type(b) and a == b
+
+
+@pytest.mark.parametrize("line", COMMAND_LINES)
+def test_dry_run_is_what_the_python_host_parses(line):
+    argv = line.split()
+    got = json.loads(run(argv + ["--dry-run"]).stdout)
+    out = []
+    histogram.main(argv + ["--dry-run"], out=out.append)
+    want = json.loads(out[-1])
+    assert same(got, want), (got, want)
+
+
+@pytest.mark.parametrize("argv,msg", [
+    ("--lj-N 31 --lj-radius 2.5", "no method"), ("--sad-min-T 1", "no system"),
+    ("--lj-N 31 --lj-radius 2.5 --ising-N 4 --sad-min-T 1", "more than one system"),
+    ("--lj-N 31 --sad-min-T 1", "--lj-radius is required"), ("--lj-N 3.5 --lj-radius 2 --sad-min-T 1", "integer"),
+    ("--lj-N 31 --lj-radius 2.5 --sad-min-T 1 --frobnicate", "unknown flag"), ("--lj-N 31 --lj-radius 2.5 --sad-min-T", "needs 1 value"),
+    ("--lj-N 31 --lj-radius 1/0 --sad-min-T 1", "division by zero"), ("--water-N 10 --sad-min-T 1", "no device kernel"),
+    ("--ising-N 8 --sad-min-T 1 --save-as run.txt", "I don't know how to create file"),
+])
+def test_usage_errors_exit_2(argv, msg):
+    r = run(argv.split() + ["--dry-run"], check=False)
+    assert r.returncode == 2 and msg in r.stderr
+
+
+def test_engine_errors_are_messages_not_crashes(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = run(["--ising-N", "8", "--sad-min-T", "1", "--max-iter", "10", "--save-as", str(tmp_path / "x.json")], check=False)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr and not (tmp_path / "x.json").exists()
+
+
+DOC = {
+    "system": {"Wca": {"E": 3.25, "error": 1e-300, "possible_change": "None",
+                       "cell": {"box_diagonal": {"x": 5.0, "y": 5.5, "z": 6.0}, "r_cutoff": 2 ** (1 / 6),
+                                "positions": [{"x": 0.1, "y": -1e-7, "z": 1.0}, {"x": 3.0000000000000004, "y": 3.0, "z": 1e21}]}}},
+    "method": {"WL": {"gamma": 0.5, "lowest_hist": 0, "highest_hist": 3, "total_hist": 9, "num_states": 4.0, "hist": [1, 2, 0],
+                      "min_energy": -1.0, "inv_t": True, "min_gamma": None}},
+    "moves": 12345678901234, "rng": {"s0": 18446744073709551615, "s1": 9223372036854775808}, "which_frame": -3,
+    "move_plan": {"AcceptanceRate": 0.4}, "save_as": "dir with space/x: y.yaml", "odd strings": ["", "null", "1.5", "true", "a, b", "- x", "#c", "é"],
+    "report": {"max_iter": "Never", "max_independent_samples": None, "quiet": False}, "manager": {}, "empty": [],
+    "bins": {"lnw": [0.0, -0.0, 1.0 / 3.0, 1e100, float("inf")] + [0.1 * k for k in range(60)], "histogram": list(range(70))},
+    "nested": [[1, 2], [3, [4, {"k": [5.5]}]], {"a": {"b": {"c": [1, 2, 3]}}}],
+}
+
+
+@pytest.mark.parametrize("src", ["yaml", "json", "cbor"])
+@pytest.mark.parametrize("dst", ["yaml", "json", "cbor"])
+def test_codecs_agree_with_the_python_host(src, dst, tmp_path):
+    a, b = tmp_path / ("in." + src), tmp_path / ("out." + dst)
+    checkpoint.write_atomic(str(a), checkpoint.dumps(DOC, src))       # written by Python (PyYAML flow style, wrapped lines)
+    run(["--convert", str(a), "--convert-to", str(b)])                  # read and re-written by the compiled host
+    got = checkpoint.load(str(b))                                      # read by Python
+    assert same(got, DOC), (src, dst)
+
+
+def test_block_style_yaml_as_serde_writes_it(tmp_path):
+    # serde_yaml emits block sequences and never flow collections
+    text = """---
+system:
+  Ising:
+    E: -4.0
+    N: 2
+    S:
+      - 1
+      - -1
+      - 1
+      - -1
+    possible_change: ~
+method:
+  Sad:
+    min_T: 1.0
+    too_lo: -8.0
+moves: 7
+bins:
+  extra: {}
+  lnw:
+    - 0.0
+    - 1.5e-3
+positions:
+  - x: 1.0
+    y: 2.0
+  - x: 3.0
+    y: 4.0
+save_as: "a b.yaml"
+"""
+    a, b = tmp_path / "in.yaml", tmp_path / "out.json"
+    a.write_text(text)
+    run(["--convert", str(a), "--convert-to", str(b)])
+    import yaml
+    assert same(json.loads(b.read_text()), yaml.safe_load(text))
+
+
+def test_two_wells_invcdf_tables_match_the_python_host():
+    # derived data of the TwoWells document (two_wells.rs:46-137); the compiled host sums sequentially like the reference
+    src = os.path.join(os.path.dirname(BIN), "..", "..", "host", "checkpoint.hpp")
+    assert "two_wells_invcdf" in open(src).read()
+    st = np.array(checkpoint.two_wells_invcdf(12, 0.5)["stencils"]).reshape(12, 10000)
+    assert (st[:, 0] == 0).all() and np.allclose(st[:, -1], 1.0)
