@@ -132,7 +132,10 @@ def run_reference(args):
         "impl": "reference", "metric": "LJ31 SAD MC moves/sec", "value": value, "unit": "moves/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(0, per_step),
+        # our arm's config; what this arm actually ran on the CPU is the bounded sample described in cpu_baseline.sample
+        "config": workload_config(args.walkers, args.moves_per_step, lanes_per_walker=args.lanes,
+                                  arithmetic="exact (reference operation order)" if args.exact else "fast-math (<= 1e-12 rel. per move)",
+                                  burn_in_moves=args.burn_in, round_trip_diagnostics=not args.no_round_trips),
         "cpu_baseline": {"value": value, "unit": "moves/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -162,11 +165,6 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = load_library()
-    if args.exact and args.lanes != 1:
-        args.lanes = 1  # the reference's sequential pair sum cannot be split across lanes
-    if args.walkers == 0:
-        # whole waves of resident CTAs: 148 SMs x 3 CTAs x 64 walkers x 3 waves (two lanes) / 148 x 2 x 128 x 2 (one lane)
-        args.walkers = 85248 if args.lanes == 2 else 75776
     W = args.walkers
     cfg = lj31_config(W, walker_offset=rank * W, device=local, lanes=args.lanes,
                       flags=(1 if args.no_round_trips else 0) | (0 if args.exact else 4))
@@ -315,6 +313,11 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.exact and args.lanes != 1:
+        args.lanes = 1  # the reference's sequential pair sum cannot be split across lanes
+    if args.walkers == 0:
+        # whole waves of resident CTAs: 148 SMs x 2 CTAs x 128 walkers x 2 waves (one lane per walker) / 148 x 3 x 64 x 3 (two lanes)
+        args.walkers = 85248 if args.lanes == 2 else 75776
     if args.impl == "reference":
         run_reference(args)
     else:
