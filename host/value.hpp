@@ -517,19 +517,21 @@ inline Value from_cbor(const std::string& bytes) {
 }
 
 // ---- yaml ---------------------------------------------------------------------------------------
+// A string may be written plain only if no yaml resolver (1.1 as PyYAML, 1.2 core as serde_yaml) could read it as
+// anything but the same string: a word or path of [A-Za-z0-9_./-] starting with a letter or '/', not one of the
+// boolean / null words of yaml 1.1.  Everything else is double-quoted.
 inline bool yaml_plain_ok(const std::string& s) {
   if (s.empty()) return false;
-  if (scalar_from_text(s, true).kind != Value::String) return false; // would read back as something else
-  const std::string bad_first = "-?:,[]{}#&*!|>'\"%@` ";
-  if (bad_first.find(s[0]) != std::string::npos) return false;
-  if (s.back() == ' ') return false;
-  for (size_t k = 0; k < s.size(); k++) {
-    const unsigned char c = (unsigned char)s[k];
-    if (c < 0x20 || c == ',' || c == '[' || c == ']' || c == '{' || c == '}') return false;
-    if (c == ':' && (k + 1 == s.size() || s[k + 1] == ' ')) return false;
-    if (c == '#' && k > 0 && s[k - 1] == ' ') return false;
-  }
-  return true;
+  const unsigned char c0 = (unsigned char)s[0];
+  if (!(isalpha(c0) || c0 == '/' || c0 == '_')) return false;
+  for (unsigned char c : s)
+    if (!(isalnum(c) || c == '_' || c == '.' || c == '/' || c == '-')) return false;
+  std::string low;
+  for (unsigned char c : s) low += (char)tolower(c);
+  static const char* words[] = {"y", "n", "yes", "no", "on", "off", "true", "false", "null", "nan", "inf", "infinity"};
+  for (const char* w : words)
+    if (low == w) return false;
+  return scalar_from_text(s, true).kind == Value::String;
 }
 inline void yaml_scalar(const Value& v, std::string& out) {
   switch (v.kind) {
@@ -629,6 +631,26 @@ inline std::string to_yaml(const Value& v) {
   return out;
 }
 
+// index just past the quoted scalar that starts at s[p] (' with '' escapes, " with backslash escapes); npos if unterminated
+inline size_t skip_quoted(const std::string& s, size_t p) {
+  const char q = s[p++];
+  while (p < s.size()) {
+    if (q == '"' && s[p] == '\\') {
+      p += 2;
+      continue;
+    }
+    if (s[p] == q) {
+      if (q == '\'' && p + 1 < s.size() && s[p + 1] == '\'') {
+        p += 2;
+        continue;
+      }
+      return p + 1;
+    }
+    p++;
+  }
+  return std::string::npos;
+}
+
 // Reader: lines -> (indent, text); block structure by indentation, flow collections by a json-like scanner that
 // may continue over the following lines.
 struct YamlReader {
@@ -655,16 +677,23 @@ struct YamlReader {
     }
   }
   static std::string strip_comment(const std::string& t) {
-    bool sq = false, dq = false;
     size_t end = t.size();
-    for (size_t k = 0; k < t.size(); k++) {
+    for (size_t k = 0; k < t.size();) {
       const char c = t[k];
-      if (c == '"' && !sq && (k == 0 || t[k - 1] != '\\')) dq = !dq;
-      if (c == '\'' && !dq) sq = !sq;
-      if (c == '#' && !sq && !dq && (k == 0 || t[k - 1] == ' ')) {
+      size_t b = k;
+      while (b > 0 && t[b - 1] == ' ') b--;
+      const bool token_start = b == 0 || t[b - 1] == '[' || t[b - 1] == '{' || t[b - 1] == ',' || (b < k && (t[b - 1] == ':' || t[b - 1] == '-'));
+      if ((c == '"' || c == '\'') && token_start) {
+        const size_t e = skip_quoted(t, k);
+        if (e == std::string::npos) break;
+        k = e;
+        continue;
+      }
+      if (c == '#' && (k == 0 || t[k - 1] == ' ')) {
         end = k;
         break;
       }
+      k++;
     }
     while (end > 0 && (t[end - 1] == ' ' || t[end - 1] == '\t')) end--;
     return t.substr(0, end);
@@ -674,13 +703,14 @@ struct YamlReader {
   // position of the ": " / trailing ':' that ends a block-map key, or npos
   static size_t key_colon(const std::string& t) {
     if (t.empty() || t[0] == '[' || t[0] == '{') return std::string::npos;
-    bool sq = false, dq = false;
-    for (size_t k = 0; k < t.size(); k++) {
-      const char c = t[k];
-      if (c == '"' && !sq && (k == 0 || t[k - 1] != '\\')) dq = !dq;
-      if (c == '\'' && !dq) sq = !sq;
-      if (c == ':' && !sq && !dq && (k + 1 == t.size() || t[k + 1] == ' ')) return k;
+    size_t k = 0;
+    if (t[0] == '"' || t[0] == '\'') { // a quoted key
+      k = skip_quoted(t, 0);
+      if (k == std::string::npos) return std::string::npos;
+      return (k < t.size() && t[k] == ':' && (k + 1 == t.size() || t[k + 1] == ' ')) ? k : std::string::npos;
     }
+    for (; k < t.size(); k++)
+      if (t[k] == ':' && (k + 1 == t.size() || t[k + 1] == ' ')) return k;
     return std::string::npos;
   }
   static std::string unquote(const std::string& t) {
@@ -707,14 +737,20 @@ struct YamlReader {
   Value flow(std::string text) {
     auto balanced = [](const std::string& s) {
       int depth = 0;
-      bool sq = false, dq = false;
-      for (size_t k = 0; k < s.size(); k++) {
+      for (size_t k = 0; k < s.size();) {
         const char c = s[k];
-        if (c == '"' && !sq && (k == 0 || s[k - 1] != '\\')) dq = !dq;
-        if (c == '\'' && !dq) sq = !sq;
-        if (sq || dq) continue;
+        size_t b = k; // a quote opens a quoted scalar only at the start of a token
+        while (b > 0 && s[b - 1] == ' ') b--;
+        const bool token_start = b == 0 || s[b - 1] == '[' || s[b - 1] == '{' || s[b - 1] == ',' || (s[b - 1] == ':' && b < k);
+        if ((c == '"' || c == '\'') && token_start) {
+          const size_t e = skip_quoted(s, k);
+          if (e == std::string::npos) return false; // the scalar continues on the next line
+          k = e;
+          continue;
+        }
         if (c == '[' || c == '{') depth++;
         if (c == ']' || c == '}') depth--;
+        k++;
       }
       return depth == 0;
     };
@@ -772,10 +808,9 @@ struct YamlReader {
     fws(s, p);
     const size_t b = p;
     if (p < s.size() && (s[p] == '"' || s[p] == '\'')) {
-      const char q = s[p++];
-      while (p < s.size() && !(s[p] == q && s[p - 1] != '\\')) p++;
-      if (p >= s.size()) fail("unterminated quoted scalar");
-      p++;
+      const size_t e = skip_quoted(s, p);
+      if (e == std::string::npos) fail("unterminated quoted scalar");
+      p = e;
       return s.substr(b, p - b);
     }
     while (p < s.size() && s[p] != ',' && s[p] != ']' && s[p] != '}' && !(s[p] == ':' && (key || p + 1 == s.size() || s[p + 1] == ' '))) p++;
@@ -788,7 +823,21 @@ struct YamlReader {
   Value after(const std::string& rest, int parent_indent, bool in_seq_item) {
     if (!rest.empty()) {
       if (rest[0] == '[' || rest[0] == '{') return flow(rest);
-      return scalar(rest);
+      if (rest[0] == '"' || rest[0] == '\'') { // a quoted scalar folded over several lines
+        std::string t = rest;
+        while (skip_quoted(t, 0) == std::string::npos && cur < lines.size()) {
+          t += ' ';
+          t += lines[cur++].text;
+        }
+        return scalar(t);
+      }
+      // a plain scalar folded over several lines: after `key: text` deeper lines can only continue the text
+      std::string t = rest;
+      while (cur < lines.size() && lines[cur].indent > parent_indent) {
+        t += ' ';
+        t += lines[cur++].text;
+      }
+      return scalar(t);
     }
     if (cur >= lines.size()) return Value::null();
     const Line& nx = lines[cur];

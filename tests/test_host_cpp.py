@@ -151,3 +151,32 @@ def test_two_wells_invcdf_tables_match_the_python_host():
     assert "two_wells_invcdf" in open(src).read()
     st = np.array(checkpoint.two_wells_invcdf(12, 0.5)["stencils"]).reshape(12, 10000)
     assert (st[:, 0] == 0).all() and np.allclose(st[:, -1], 1.0)
+
+
+def test_codecs_fuzz_against_the_python_host(tmp_path):
+    """Random documents (nested maps / lists, awkward strings and numbers) written by Python in one format, re-encoded by
+    the compiled host into another, read back by Python."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    import re
+    # the one class of plain scalars the yaml generations disagree on: `1e5` is a float for serde_yaml (1.2 core schema,
+    # what the reference writes) and a string for PyYAML (1.1); the compiled host reads it as the reference means it
+    numberish = re.compile(r"[-+]?(\d[\d_]*\.?[\d_]*|\.\d+)([eE][-+]?\d+)?")
+    ok = lambda s: s == s.strip() and not numberish.fullmatch(s)
+    keys = st.text(alphabet="abcXYZ_ -:#'\"09", min_size=1, max_size=8).filter(ok)
+    scalars = st.one_of(st.none(), st.booleans(), st.integers(min_value=-2 ** 63, max_value=2 ** 64 - 1),
+                        st.floats(allow_nan=False), st.text(alphabet="ab -:,#[]{}'\"\\~!&*|>%@`09.eE+\t", max_size=10).filter(ok),
+                        st.sampled_from(["null", "~", "true", "No", "0x1f", ".inf", "-", "? x", "1_000", "a: b", "- a", "a #b", "x" * 100 + " y" * 40]))
+    docs = st.recursive(scalars, lambda c: st.one_of(st.lists(c, max_size=5), st.dictionaries(keys, c, max_size=5)), max_leaves=30)
+    n = [0]
+
+    @settings(max_examples=80, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.dictionaries(keys, docs, min_size=1, max_size=6), st.sampled_from(["yaml", "json", "cbor"]), st.sampled_from(["yaml", "json", "cbor"]))
+    def check(doc, src, dst):
+        n[0] += 1
+        a, b = tmp_path / ("f%d.%s" % (n[0], src)), tmp_path / ("g%d.%s" % (n[0], dst))
+        checkpoint.write_atomic(str(a), checkpoint.dumps(doc, src))
+        run(["--convert", str(a), "--convert-to", str(b)])
+        got = checkpoint.load(str(b))
+        assert same(got, doc), (src, dst, doc, got)
+
+    check()
