@@ -96,6 +96,9 @@ typedef enum {
  * warp-cooperative energy recomputation instead of the reference's exact operation order.
  * Per-move energies then agree with the reference to <= 1e-12 relative instead of bit for bit. */
 #define SADMC_FLAG_FAST_MATH 4u
+/* EXPERIMENT, with SADMC_FLAG_FAST_MATH and lanes_per_walker = 1, LJ31 / LJ38 only: a helper warp per bookkeeping warp
+ * sums half of the pair loop (csrc/sys_lj_paired.cuh).  Same tolerance tier as SADMC_FLAG_FAST_MATH. */
+#define SADMC_FLAG_HELPER_WARPS 8u
 
 typedef struct sadmc_config {
   uint32_t abi_version; /* = SADMC_ABI_VERSION */

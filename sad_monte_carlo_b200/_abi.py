@@ -23,6 +23,7 @@ INIT_REFERENCE, INIT_RANDOMIZE, INIT_EXTERNAL = 0, 1, 2
 FLAG_NO_ROUND_TRIPS = 1
 FLAG_SUM_TREE = 2
 FLAG_FAST_MATH = 4
+FLAG_HELPER_WARPS = 8  # experiment: helper warps for the LJ pair loop (with FLAG_FAST_MATH, lanes_per_walker = 1)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WINDOW, ERR_UNSUPPORTED, ERR_VERIFY = 0, -1, -2, -3, -4, -5
 

@@ -95,6 +95,10 @@ static int pick_kernels(sadmc_engine* e) {
       if (G == 0) G = c.n_walkers >= 16384 ? 1 : (c.n_walkers >= 4096 ? 8 : 32);
       if (G == 1 || (fast && (G == 2 || G == 4))) { // configuration in shared memory (sys_lj_thread.cuh)
         if (c.N > 64) return fail(SADMC_ERR_UNSUPPORTED, "lj: shared-memory kernels hold N <= 64 atoms (N=%u)", c.N);
+        if (fast && G == 1 && (c.flags & SADMC_FLAG_HELPER_WARPS)) { // experiment: helper warps for the pair loop
+          if (kernels_lj_thread_paired((int)c.N, P, &e->ks)) return 0;
+          return fail(SADMC_ERR_UNSUPPORTED, "lj: helper-warp kernels exist for N = 31 and 38 only (N=%u)", c.N);
+        }
         const bool ok = !fast ? kernels_lj_thread_exact((int)c.N, P, &e->ks)
                               : (G == 1 ? kernels_lj_thread_fast((int)c.N, G, P, &e->ks) : kernels_lj_thread_fast_multi((int)c.N, G, P, &e->ks));
         if (ok) return 0;
@@ -517,9 +521,11 @@ int sadmc_create(const sadmc_config* cfg, sadmc_engine** out) {
     CKB(cudaStreamSynchronize(e->stream));
   }
   P.zig = e->d_zig;
-  if (e->ks.smem > 48 * 1024) {
+  if (e->ks.smem > 48 * 1024 || e->ks.move_smem > 48 * 1024) {
     for (int m = 1; m <= 5; m++)
-      if (e->ks.move[m]) CKB(cudaFuncSetAttribute((const void*)e->ks.move[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ks.smem));
+      if (e->ks.move[m])
+        CKB(cudaFuncSetAttribute((const void*)e->ks.move[m], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(e->ks.move_smem ? e->ks.move_smem : e->ks.smem)));
     CKB(cudaFuncSetAttribute((const void*)e->ks.init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ks.smem));
     CKB(cudaFuncSetAttribute((const void*)e->ks.shim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ks.smem));
   }
@@ -564,9 +570,17 @@ int sadmc_run_async(sadmc_engine* e, uint64_t n_moves) {
   CK(cudaSetDevice(e->cfg.device));
   int grid;
   launch_cfg(e, &grid);
+  int block = e->ks.block;
+  size_t smem = e->ks.smem;
+  if (e->ks.move_block) { // move kernels with their own launch shape (helper warps)
+    block = e->ks.move_block;
+    smem = e->ks.move_smem;
+    const long long threads = (long long)e->cfg.n_walkers * e->ks.move_threads_per_walker;
+    grid = (int)((threads + block - 1) / block);
+  }
   move_fn f = e->ks.move[e->cfg.method];
   CK(cudaEventRecord(e->ev0, e->stream));
-  f<<<grid, e->ks.block, e->ks.smem, e->stream>>>(e->P, e->moves, n_moves);
+  f<<<grid, block, smem, e->stream>>>(e->P, e->moves, n_moves);
   CK(cudaGetLastError());
   CK(cudaEventRecord(e->ev1, e->stream));
   e->launches++;

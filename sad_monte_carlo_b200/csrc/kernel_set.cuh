@@ -28,6 +28,9 @@ struct KernelSet {
   shim_fn shim;
   int G, block;
   size_t smem;
+  // when the move kernels are launched differently from init / shim (helper warps): 0 = as above
+  int move_block, move_threads_per_walker;
+  size_t move_smem;
 };
 
 // factories, one per translation unit; the bool ones return false when no instance was built
@@ -38,6 +41,7 @@ KernelSet kernels_erfinv(const DevParams& P);
 KernelSet kernels_cell_fluid(bool square_well, const DevParams& P);
 bool kernels_lj_thread_exact(int N, const DevParams& P, KernelSet* out);
 bool kernels_lj_thread_fast(int N, int G, const DevParams& P, KernelSet* out);
+bool kernels_lj_thread_paired(int N, const DevParams& P, KernelSet* out);
 bool kernels_lj_thread_fast_multi(int N, int G, const DevParams& P, KernelSet* out);
 bool kernels_lj_warp(int G, int A, const DevParams& P, KernelSet* out);
 bool kernels_lj_warp_small(int G, int A, const DevParams& P, KernelSet* out);

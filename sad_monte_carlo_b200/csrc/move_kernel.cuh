@@ -24,6 +24,16 @@ struct HasPredraw<S, decltype((void)S::PREDRAW)> {
   static constexpr bool value = S::PREDRAW;
 };
 
+// Systems with helper warps for the pair loop (sys_lj_paired.cuh) declare HELPERS.
+template <class S, class = void>
+struct HasHelpers {
+  static constexpr bool value = false;
+};
+template <class S>
+struct HasHelpers<S, decltype((void)S::HELPERS)> {
+  static constexpr bool value = S::HELPERS;
+};
+
 template <int G>
 __device__ __forceinline__ unsigned group_mask() {
   if (G >= 32) return 0xffffffffu;
@@ -144,7 +154,18 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
   const double* zx = stage_zig(P, smem);
   const double* zf = zx + SADMC_ZIG_TABLE_LEN;
   constexpr int G = Sys::G;
-  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr bool HELPERS = HasHelpers<Sys>::value;
+  unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if constexpr (HELPERS) {
+    // the upper half of the CTA only ever runs the pair loop for the walkers of the lower half
+    if (threadIdx.x >= Sys::WALKERS_PER_BLOCK) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Sys::HELPER_REGS));
+      Sys::helper_loop(P, smem + ZIG_SMEM_BYTES, n_moves);
+      return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Sys::MAIN_REGS));
+    tid = blockIdx.x * Sys::WALKERS_PER_BLOCK + threadIdx.x;
+  }
   const uint32_t w_raw = tid / G;
   const int lane = (int)(tid % G);
   // Systems whose rare paths are warp-cooperative (Sys::COOP) keep every thread of the
@@ -196,10 +217,14 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
     h2.rt_stamp = 0;
     h2.round_trips = 0;
     h2.wl_hist = 0;
+    bool some_paired = false;
+    if constexpr (HELPERS) some_paired = sys.plan_move_paired(!halted, rng, bk.tscale, zx, zf, e2); // every thread: barriers inside
     if (!halted) {
       bk.acc_rate *= 1.0 - recent_scale;
       bool some;
-      if constexpr (PREDRAW) {
+      if constexpr (HELPERS) {
+        some = some_paired;
+      } else if constexpr (PREDRAW) {
         if (pre.ok) {
           rng.s0 = pre.s0;
           rng.s1 = pre.s1;
