@@ -29,8 +29,19 @@ struct LjPairedSys : LjThreadSys<true, NT, 1> {
   static constexpr int BLOCK = 256;     // threads per CTA at launch: 128 bookkeeping + 128 helpers
   static constexpr int MIN_BLOCKS = 2;
   static constexpr int WALKERS_PER_BLOCK = 128;
-  static constexpr int HALF = (NT + 1) / 2; // rows [0, HALF) stay with the bookkeeping thread
-  static constexpr int MAIN_REGS = 200, HELPER_REGS = 56;
+#ifndef SADMC_PAIR_HALF
+#define SADMC_PAIR_HALF ((NT + 1) / 2)
+#endif
+#ifndef SADMC_PAIR_MAIN_REGS
+#define SADMC_PAIR_MAIN_REGS 200
+#define SADMC_PAIR_HELPER_REGS 56
+#endif
+#ifndef SADMC_PAIR_UNROLL
+#define SADMC_PAIR_UNROLL 2
+#endif
+  static constexpr int HALF = SADMC_PAIR_HALF; // rows [0, HALF) stay with the bookkeeping thread
+  static constexpr int MAIN_REGS = SADMC_PAIR_MAIN_REGS, HELPER_REGS = SADMC_PAIR_HELPER_REGS;
+  static constexpr int PAIR_UNROLL = SADMC_PAIR_UNROLL; // two-atom bodies in flight
   static constexpr int EX_SLOTS = 7;        // ox, oy, oz, tx, ty, tz, partial
 
   double* ex; // this walker's exchange column
@@ -47,7 +58,7 @@ struct LjPairedSys : LjThreadSys<true, NT, 1> {
   static __device__ __forceinline__ double half_sum(const double* col, double ox, double oy, double oz, double tx, double ty, double tz) {
     constexpr int S = WALKERS_PER_BLOCK;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 2
+#pragma unroll(PAIR_UNROLL)
     for (int k = K0; k + 1 < K1; k += 2) {
       const double xa = col[(0 * NT + k) * S], ya = col[(1 * NT + k) * S], za = col[(2 * NT + k) * S];
       const double xb = col[(0 * NT + k + 1) * S], yb = col[(1 * NT + k + 1) * S], zb = col[(2 * NT + k + 1) * S];
