@@ -180,3 +180,60 @@ def test_codecs_fuzz_against_the_python_host(tmp_path):
         assert same(got, doc), (src, dst, doc, got)
 
     check()
+
+
+def _doc(system, method, **top):
+    d = {"system": system, "method": method, "moves": 1000, "time_L": 0, "accepted_moves": 500, "min_allowed_energy": None,
+         "max_allowed_energy": None, "move_plan": {"TranslationScale": 0.05}, "translation_scale": 0.05, "acceptance_rate": 0.5,
+         "rng": {"s0": 1, "s1": 2}, "save_as": "x.json", "report": {"max_iter": {"TotalMoves": 5000}, "max_independent_samples": 77, "quiet": False},
+         "movies": {"movie_time": 2.0, "which_frame": 9, "period": {"TotalMoves": 1024}}, "save": {"save_time_seconds": 900.0}, "manager": {},
+         "bins": {"min": -2.5, "width": 0.5, "histogram": [1, 2, 3], "t_found": [0, 1, 2], "lnw": [0.0, 1.0, 2.0], "energy_total": [1.0, 2.0, 3.0],
+                  "energy_squared_total": [1.0, 4.0, 9.0], "extra": {}},
+         "have_visited_since_maxentropy": [False, True, True], "round_trips": [1, 1, 1], "max_S": 0.0, "max_S_index": 0}
+    d.update(top)
+    return d
+
+
+P3 = [{"x": 0.1, "y": 0.2, "z": 0.3}, {"x": 1.0, "y": 1.1, "z": 1.2}, {"x": -1.0, "y": 0.0, "z": 0.5}]
+SAD = {"Sad": {"min_T": 0.01, "too_lo": -2.0, "too_hi": -1.0, "tL": 10, "tF": 20, "num_states": 3, "highest_hist": 3, "version": "Sad",
+               "latest_parameter": 100.0}}
+WLM = {"WL": {"gamma": 0.25, "lowest_hist": 1, "highest_hist": 3, "total_hist": 6, "num_states": 3.0, "hist": [1, 2, 3], "min_energy": -2.0,
+              "inv_t": False, "min_gamma": 1e-4}}
+RESUME_DOCS = {
+    "lj": _doc({"Lj": {"E": -2.0, "error": 0.0, "possible_change": "None", "positions": P3, "max_radius_squared": 6.25, "max_radius": 2.5}}, SAD,
+               max_allowed_energy=0.0),
+    "lj_open": _doc({"Lj": {"E": -2.0, "error": 0.0, "possible_change": "None", "positions": P3, "max_radius_squared": 6.25, "max_radius": 2.5}},
+                    {"Samc": {"t0": 1e5}}),
+    "ising": _doc({"Ising": {"E": -4.0, "N": 2, "S": [1, -1, 1, -1], "possible_change": None}}, WLM, min_allowed_energy=-8.0, max_allowed_energy=2.0,
+                  move_plan={"AcceptanceRate": 0.3}),
+    "fake_linear": _doc({"Fake": {"position": [0.5], "function": "Linear", "possible_change": [0.0]}}, SAD),
+    "fake_quadratic": _doc({"Fake": {"position": [0.1, 0.2, 0.3, 0.4], "function": {"Quadratic": {"dimensions": 4}}, "possible_change": [0.0] * 4}}, SAD),
+    "fake_pieces": _doc({"Fake": {"position": [0.1, 0.2, 0.3], "function": {"Pieces": {"a": 0.1, "b": 0.2, "e1": 1.0, "e2": 0.5}},
+                                  "possible_change": [0.0] * 3}}, {"Canonical": {"temperature": 1.5}}),
+    "fake_gaussian": _doc({"Fake": {"position": [0.1, 0.2, 0.3], "function": {"Gaussian": {"sigma": 0.3}}, "possible_change": [0.0] * 3}}, SAD),
+    "erfinv": _doc({"FakeErfinv": {"position": [0.5, 0.5, 0.5], "parameters": {"mean_energy": 0.25}, "possible_change": []}}, {"Samc": {"t0": 10.0}}),
+    "wca": _doc({"Wca": {"E": 3.0, "error": 1e-9, "possible_change": "None",
+                         "cell": {"box_diagonal": {"x": 5.0, "y": 5.5, "z": 6.0}, "r_cutoff": 2 ** (1 / 6), "positions": P3}}},
+                {"WL": dict(WLM["WL"], inv_t=True, min_gamma=None)}),
+    "sw": _doc({"Sw": {"E": -3.0, "possible_change": "None",
+                       "cell": {"box_diagonal": {"x": 5.0, "y": 5.0, "z": 5.0}, "r_cutoff": 1.3, "positions": P3}}}, SAD),
+    "two_wells": _doc({"TwoWells": {"position": [-0.99] + [0.0] * 5, "d_squared": 0.9801, "parameters": {"N": 6, "h2_to_h1": 1.1, "barrier_over_h1": 0.1,
+                                                                                                    "r2": 0.5},
+                                    "change": {"index": 0, "values": {"x": 0.0, "y": 0.0, "z": 0.0}}, "well_position": 0.66, "invcdf": {}}}, SAD),
+}
+
+
+@pytest.mark.parametrize("name", sorted(RESUME_DOCS))
+@pytest.mark.parametrize("ext", ["json", "yaml", "cbor"])
+def test_resume_from_configuration_is_what_the_python_host_derives(name, ext, tmp_path):
+    # --resume-from reads nothing but the file (mc/mod.rs:92-106): system, method, bounds, move plan, bin width and the
+    # plugin parameters all come out of the document -- the same way in both hosts
+    p = tmp_path / ("ck." + ext)
+    checkpoint.write_atomic(str(p), checkpoint.dumps(RESUME_DOCS[name], ext))
+    argv = ["--resume-from", str(p), "--num-walkers", "1", "--dry-run"]
+    got = json.loads(run(argv).stdout)
+    out = []
+    histogram.main(argv, out=out.append)
+    want = json.loads(out[-1])
+    assert same(got, want), (got, want)
+    assert got["config"]["init_mode"] == 2 and got["plugins"]["max_iter"] == 5000 and got["plugins"]["save_time"] == 0.25
