@@ -237,3 +237,71 @@ def test_resume_from_configuration_is_what_the_python_host_derives(name, ext, tm
     want = json.loads(out[-1])
     assert same(got, want), (got, want)
     assert got["config"]["init_mode"] == 2 and got["plugins"]["max_iter"] == 5000 and got["plugins"]["save_time"] == 0.25
+
+
+@pytest.fixture(scope="module")
+def selftest_exe(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("selftest") / "selftest_plugins")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(root, "host", "selftest_plugins.cpp")])
+    return exe
+
+
+def _python_schedule(max_iter, movie_time, doubling, accept_every, max_samples=None):
+    """The same scripted Monte Carlo through the Python host's plugins (held against a literal per-move restatement of
+    plugin.rs in tests/test_host_plugins.py)."""
+    from sad_monte_carlo_b200 import plugins
+    lines = []
+
+    class MC:
+        moves = 0
+
+        def num_moves(self):
+            return self.moves
+
+        def num_accepted_moves(self):
+            return self.moves // accept_every
+
+        def independent_samples(self):
+            return self.num_accepted_moves()
+
+        def verify_energy(self):
+            lines.append("verify %d" % self.moves)
+
+        def checkpoint(self):
+            lines.append("checkpoint %d" % self.moves)
+
+        def save_movie_frame(self, m):
+            lines.append("frame %d" % m)
+
+    mc = MC()
+    report = plugins.Report(max_iter=max_iter or None, max_independent_samples=max_samples, quiet=True)
+    save = plugins.Save(save_time_hours=None if doubling else 1e-12 / 3600.0)
+    movies = plugins.Movie(movie_time=movie_time)
+    manager = plugins.PluginManager()
+    for _ in range(100000):
+        n = manager.moves_until_next_action()
+        mc.moves += n
+        a = manager.run(mc, [report, save, movies], moves_made=n)
+        lines.append("tick %d action %d period %d frame %d" % (mc.moves, int(a), manager.period, movies.which_frame))
+        if a == plugins.Action.EXIT:
+            return lines
+    raise AssertionError("the scripted run never ended")
+
+
+@pytest.mark.parametrize("max_iter,movie_time,doubling,accept_every,max_samples", [
+    (1000, 2.0, 1, 3, None), (12345, 10 ** 0.125, 1, 2, None), (5000, None, 1, 5, None), (3000, 1.5, 0, 2, None),
+    (0, 3.0, 1, 4, 777), (10 ** 7, 10.0, 1, 3, None), (1, 2.0, 1, 1, None),
+])
+def test_plugin_schedule_equals_the_python_host(max_iter, movie_time, doubling, accept_every, max_samples, selftest_exe):
+    exe = selftest_exe
+    argv = [exe, str(max_iter), "none" if movie_time is None else repr(movie_time), str(doubling), str(accept_every)]
+    if max_samples is not None:
+        argv.append(str(max_samples))
+    got = subprocess.run(argv, capture_output=True, text=True, check=True).stdout.splitlines()
+    want = _python_schedule(max_iter, movie_time, doubling, accept_every, max_samples)
+    if not doubling:
+        # with a save_time the next checkpoint depends on the measured time per move: only the stop and the frames are comparable
+        keep = lambda ls: [l for l in ls if l.startswith("frame")] + ls[-1:]
+        got, want = [l.split(" period")[0] for l in keep(got)], [l.split(" period")[0] for l in keep(want)]
+    assert got == want
