@@ -338,7 +338,8 @@ def _cbor_decode(b, i=0):
 def dumps(doc, ext):
     if ext == "yaml":
         import yaml
-        return yaml.safe_dump(doc, default_flow_style=None, sort_keys=False).encode()
+        dumper = getattr(yaml, "CSafeDumper", yaml.SafeDumper)  # libyaml when present: same text, several times faster
+        return yaml.dump(doc, Dumper=dumper, default_flow_style=None, sort_keys=False).encode()
     if ext == "json":
         return json.dumps(doc).encode()
     if ext == "cbor":
@@ -351,7 +352,7 @@ def dumps(doc, ext):
 def loads(data, ext):
     if ext == "yaml":
         import yaml
-        return yaml.safe_load(data)
+        return yaml.load(data, Loader=getattr(yaml, "CSafeLoader", yaml.SafeLoader))
     if ext == "json":
         return json.loads(data)
     if ext == "cbor":
