@@ -11,6 +11,7 @@
 #include <cmath>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sadmc_gpu.h"
@@ -300,14 +301,6 @@ struct WcaScratch {
     }
   }
 };
-
-} // namespace hostctor
-} // namespace sadmc
-
-#include <thread>
-
-namespace sadmc {
-namespace hostctor {
 
 inline std::vector<double> wca_image(uint32_t n, const double box[3], uint64_t attempts, unsigned n_threads = 0) {
   const double r_cut = std::pow(2.0, 1.0 / 6.0); // wca.rs:61-63
