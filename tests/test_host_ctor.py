@@ -63,3 +63,33 @@ def test_box_smaller_than_the_cutoff_is_an_error_code(gpu_lib):
     cfg = make_config("wca", N=1, reduced_density=2.0, seed=1)  # L = 0.79 < 2^(1/6): wca.rs:186-191 panics
     assert gpu_lib.sadmc_reference_system(C.byref(cfg), None, 0, None) == _abi.ERR_INVALID
     assert b"not large enough" in gpu_lib.sadmc_last_error()
+
+
+def test_analytic_systems_start_where_the_reference_puts_them(gpu_lib):
+    # fake.rs:85-93 (the origin), erfinv.rs:50-58 (0.5 everywhere), two_wells.rs:248-250 (x0 = -0.99, d^2 cached)
+    img = _image(gpu_lib, make_config("fake", fake_function=_abi.FAKE_QUADRATIC, N=4, seed=1))
+    assert img.tolist() == [0.0] * 4
+    img = _image(gpu_lib, make_config("fake-erfinv", N=3, erfinv_mean_energy=0.0, seed=1))
+    assert img.tolist() == [0.5] * 3
+    cfg = make_config("two-wells", N=12, tw_h2_to_h1=1.1, tw_barrier_over_h1=0.1, tw_r2=0.5, seed=1)
+    img = _image(gpu_lib, cfg)
+    assert img[0] == -0.99 and not img[1:12].any() and img[12] == (-0.99) ** 2
+    assert np.array_equal(img, OracleMC(cfg).system())
+
+
+@pytest.mark.parametrize("system,kw,msg", [
+    ("two-wells", dict(N=10, tw_h2_to_h1=1.1, tw_barrier_over_h1=0.1, tw_r2=0.5), b"not divisible by three"),   # two_wells.rs:240-245
+    ("ising", dict(N=1), b"N must be > 1"),                                                                         # ising.rs:39
+    ("lj", dict(N=31, lj_radius=0.0), b"radius must be > 0"),
+])
+def test_constructor_panics_become_error_codes(gpu_lib, system, kw, msg):
+    cfg = make_config(system, seed=1, **kw)
+    assert gpu_lib.sadmc_reference_system(C.byref(cfg), None, 0, None) == _abi.ERR_INVALID
+    assert msg in gpu_lib.sadmc_last_error()
+
+
+def test_buffer_too_small_is_reported_not_overrun(gpu_lib):
+    cfg = make_config("ising", N=8, seed=1)
+    buf = np.full(10, 7.0)
+    assert gpu_lib.sadmc_reference_system(C.byref(cfg), buf.ctypes.data_as(f64p), buf.size, None) == _abi.ERR_INVALID
+    assert (buf == 7.0).all() and b"needs 65 doubles" in gpu_lib.sadmc_last_error()
