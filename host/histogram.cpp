@@ -80,7 +80,32 @@ static int real_main(int argc, char** argv) {
     return 0;
   }
   PluginParams pp = plugin_params(flags);
-  const uint32_t n_walkers = has(flags, "num-walkers") ? (uint32_t)flags.at("num-walkers").u : 1;
+  // One process per GPU (mpirun / torchrun export WORLD_SIZE, RANK, LOCAL_RANK): --num-walkers is the total, rank r runs
+  // global walkers [r W/G, (r+1) W/G) on device LOCAL_RANK -- walker w is still the reference run with --seed seed+w,
+  // whatever G is -- and writes its own files `name.rankRofG[-wNNNNNN].ext`.  No traffic between ranks.
+  auto env_int = [](const char* name, long fallback) {
+    const char* v = getenv(name);
+    return v && *v ? strtol(v, nullptr, 10) : fallback;
+  };
+  const long world = env_int("WORLD_SIZE", 1), rank = env_int("RANK", 0), local_rank = env_int("LOCAL_RANK", rank);
+  const uint32_t total_walkers = has(flags, "num-walkers") ? (uint32_t)flags.at("num-walkers").u : 1;
+  if (world < 1 || total_walkers % (uint32_t)world) throw UsageError("--num-walkers " + std::to_string(total_walkers) + " does not divide over " + std::to_string(world) + " processes");
+  const uint32_t n_walkers = total_walkers / (uint32_t)world;
+  auto rank_path = [&](const std::string& path) {
+    if (world == 1) return path;
+    const size_t slash = path.find_last_of('/');
+    const size_t dot = path.find_last_of('.');
+    const bool has_ext = dot != std::string::npos && (slash == std::string::npos || dot > slash);
+    const std::string tag = ".rank" + std::to_string(rank) + "of" + std::to_string(world);
+    return has_ext ? path.substr(0, dot) + tag + path.substr(dot) : path + tag;
+  };
+  auto place = [&](sadmc_config& c) {
+    if (world > 1) {
+      c.n_walkers = n_walkers;
+      c.walker_offset = (uint32_t)rank * n_walkers;
+      if (!has(flags, "gpu-device")) c.device = (int32_t)local_rank;
+    }
+  };
   const std::string lib_hint = self_dir(argv[0]) + "/../libsadmc_gpu.so";
   auto known_ext = [](const std::string& p) {
     const std::string e = extension_of(p);
@@ -94,13 +119,14 @@ static int real_main(int argc, char** argv) {
   bool restore_movies = false;
   Value movie_state;
   if (has(flags, "resume-from")) { // Params::ResumeFrom, mc/mod.rs:92-106: nothing else is read from the command line
-    const std::string path = flags.at("resume-from").path;
+    const std::string path = rank_path(flags.at("resume-from").path);
     if (!known_ext(path)) throw UsageError("I don't know how to read file \"" + path + "\"");
     const Value doc0 = load(walker_path(path, 0, n_walkers));
     cfg = config_from_document(doc0, n_walkers);
     if (has(flags, "bin-window-lo")) cfg.bin_window_lo = num(flags, "bin-window-lo");
     if (has(flags, "bin-window-hi")) cfg.bin_window_hi = num(flags, "bin-window-hi");
     if (has(flags, "gpu-device")) cfg.device = (int32_t)flags.at("gpu-device").u;
+    place(cfg);
     const Value* sa = doc0.find("save_as");
     save_as = (n_walkers == 1 && sa && sa->kind == Value::String) ? sa->s : path;
     Report r;
@@ -130,7 +156,8 @@ static int real_main(int argc, char** argv) {
     printf("Resuming from file \"%s\"\n", path.c_str());
   } else {
     cfg = config_from_flags(flags);
-    save_as = has(flags, "save-as") ? flags.at("save-as").path : "resume.yaml"; // mc/mod.rs:88
+    place(cfg);
+    save_as = rank_path(has(flags, "save-as") ? flags.at("save-as").path : "resume.yaml"); // mc/mod.rs:88
     if (!known_ext(save_as)) throw UsageError("I don't know how to create file \"" + save_as + "\""); // mc/mod.rs:118
     const std::string first = walker_path(save_as, 0, n_walkers);
     const bool resuming = has(flags, "save-as") && file_exists(first);

@@ -369,6 +369,21 @@ HELP = __doc__ + "\nFlags:\n" + "\n".join(
     for n, k in ALL_FLAGS.items())
 
 
+def shard_env():
+    """(world, rank, local rank) of a one-process-per-GPU launch (torchrun / mpirun export these); (1, 0, 0) otherwise."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    return world, rank, int(os.environ.get("LOCAL_RANK", rank))
+
+
+def rank_path(path, rank, world):
+    """`name.ext` -> `name.rank3of8.ext` when the walkers are sharded over several processes."""
+    if world == 1:
+        return path
+    stem, ext = os.path.splitext(path)
+    return "%s.rank%dof%d%s" % (stem, rank, world, ext)
+
+
 def main(argv=None, out=print):
     argv = list(sys.argv[1:] if argv is None else argv)
     flags = parse_flags(argv)
@@ -378,14 +393,29 @@ def main(argv=None, out=print):
     pp = plugin_params(flags)
     from . import checkpoint, plugins
     n_walkers = flags.get("num-walkers", 1)
+    # One process per GPU (torchrun --nproc-per-node G -m sad_monte_carlo_b200.histogram ...): --num-walkers is the total,
+    # rank r runs global walkers [r W/G, (r+1) W/G) on device LOCAL_RANK -- walker w is still the reference run with
+    # --seed seed+w, whatever G is -- and writes its own files `name.rankRofG[-wNNNNNN].ext`.  No traffic between ranks.
+    world, rank, local_rank = shard_env()
+    if n_walkers % world:
+        raise UsageError("--num-walkers %d does not divide over %d processes" % (n_walkers, world))
+    n_walkers //= world
+
+    def place(cfg):
+        if world > 1:
+            cfg.n_walkers = n_walkers
+            cfg.walker_offset = rank * n_walkers
+            if "gpu-device" not in flags:
+                cfg.device = local_rank
+        return cfg
 
     if "resume-from" in flags:  # Params::ResumeFrom, mc/mod.rs:92-106: nothing else is read from the command line
-        path = flags["resume-from"]
+        path = rank_path(flags["resume-from"], rank, world)
         if os.path.splitext(path)[1].lstrip(".") not in ("yaml", "json", "cbor"):
             raise UsageError("I don't know how to read file %r" % path)
         doc0 = checkpoint.load(checkpoint.walker_path(path, 0, n_walkers))
         over = {k: flags[f] for f, k in (("bin-window-lo", "bin_window_lo"), ("bin-window-hi", "bin_window_hi"), ("gpu-device", "device")) if f in flags}
-        cfg = checkpoint.config_from_document(doc0, n_walkers=n_walkers, **over)
+        cfg = place(checkpoint.config_from_document(doc0, n_walkers=n_walkers, **over))
         save_as = doc0.get("save_as", path) if n_walkers == 1 else path
         rep = doc0.get("report", {})
         mi = rep.get("max_iter", "Never")
@@ -399,8 +429,8 @@ def main(argv=None, out=print):
         out("Resuming from file %r" % path)
         movie_state = doc0.get("movies")
     else:
-        cfg = config_from_flags(flags)
-        save_as = flags.get("save-as", "resume.yaml")  # mc/mod.rs:88
+        cfg = place(config_from_flags(flags))
+        save_as = rank_path(flags.get("save-as", "resume.yaml"), rank, world)  # mc/mod.rs:88
         if os.path.splitext(save_as)[1].lstrip(".") not in ("yaml", "json", "cbor"):
             raise UsageError("I don't know how to create file %r" % save_as)  # mc/mod.rs:118
         first = checkpoint.walker_path(save_as, 0, n_walkers)

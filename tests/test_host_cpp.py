@@ -305,3 +305,30 @@ def test_plugin_schedule_equals_the_python_host(max_iter, movie_time, doubling, 
         keep = lambda ls: [l for l in ls if l.startswith("frame")] + ls[-1:]
         got, want = [l.split(" period")[0] for l in keep(got)], [l.split(" period")[0] for l in keep(want)]
     assert got == want
+
+
+@pytest.mark.parametrize("rank,world,local", [(0, 2, 0), (3, 4, 3), (9, 16, 1)])
+def test_one_process_per_gpu_sharding_is_the_same_in_both_hosts(rank, world, local, monkeypatch):
+    # torchrun / mpirun export WORLD_SIZE, RANK, LOCAL_RANK: --num-walkers is the total, every rank gets a contiguous block
+    # of global walkers (walker w == the reference run with --seed seed+w, whatever the GPU count), its own device and files
+    argv = "--lj-N 31 --lj-radius 2.5 --sad-min-T 0.01 --max-allowed-energy 0 --num-walkers 8192 --seed 5 --save-as out/run.cbor --dry-run".split()
+    env = dict(os.environ, WORLD_SIZE=str(world), RANK=str(rank), LOCAL_RANK=str(local))
+    r = subprocess.run([BIN] + argv, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    got = json.loads(r.stdout)
+    for k, v in (("WORLD_SIZE", world), ("RANK", rank), ("LOCAL_RANK", local)):
+        monkeypatch.setenv(k, str(v))
+    out = []
+    histogram.main(argv, out=out.append)
+    want = json.loads(out[-1])
+    assert same(got, want)
+    c = got["config"]
+    assert (c["n_walkers"], c["walker_offset"], c["device"], c["seed"]) == (8192 // world, rank * (8192 // world), local, 5)
+    assert got["save_as"] == "out/run.rank%dof%d.cbor" % (rank, world)
+    # an explicit device wins; a walker count that does not divide is an error
+    r = subprocess.run([BIN] + argv + ["--gpu-device", "0"], capture_output=True, text=True, env=env)
+    assert json.loads(r.stdout)["config"]["device"] == 0
+    r = subprocess.run([BIN] + [a if a != "8192" else "8191" for a in argv], capture_output=True, text=True, env=env)
+    assert r.returncode == 2 and "does not divide" in r.stderr
+    with pytest.raises(SystemExit):
+        histogram.main([a if a != "8192" else "8191" for a in argv], out=out.append)
