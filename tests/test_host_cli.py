@@ -128,3 +128,45 @@ def test_resume_from_rebuilds_the_configuration_from_the_document(tmp_path):
         assert (c["move_plan"], c["move_value"], c["energy_bin"], c["init_mode"]) == (_abi.MOVE_ACCEPTANCE_RATE, 0.4, 1.0, _abi.INIT_EXTERNAL)
         assert (c["min_allowed_energy"], c["max_allowed_energy"]) == (0.0, 20.0)
         assert d["plugins"]["max_iter"] == 5000 and d["plugins"]["save_time"] == 0.5
+
+
+def test_main_glue_runs_with_a_stand_in_engine(monkeypatch, tmp_path):
+    """The part of main() behind --dry-run (engine creation, plugins, the run loop, shard placement) with a stand-in
+    engine: no GPU here, the real path is tests/test_gpu_cli.py."""
+    from sad_monte_carlo_b200 import engine as engine_mod, plugins
+    made = []
+
+    class Engine:
+        def __init__(self, cfg):
+            self.cfg, self.n_walkers, self.moves = cfg, cfg.n_walkers, 0
+            made.append(self)
+
+        def run(self, n):
+            self.moves += n
+
+        def num_moves(self):
+            return self.moves
+
+        def num_accepted_moves(self):
+            return self.moves // 2
+
+        def verify_energy(self, w=0):
+            return True
+
+        def close(self):
+            self.closed = True
+
+    saved = []
+    monkeypatch.setattr(engine_mod, "WalkerEngine", Engine)
+    monkeypatch.setattr(plugins.EngineMC, "checkpoint", lambda self: saved.append((self.save_as, self.engine.moves)))
+    monkeypatch.chdir(tmp_path)
+    lines = []
+    assert histogram.main("--ising-N 16 --sad-min-T 1 --max-iter 1000 --num-walkers 8 --save-as a.json".split(), out=lines.append) == 0
+    e = made[-1]
+    assert (e.moves, e.cfg.n_walkers, e.cfg.walker_offset, e.closed) == (1000, 8, 0, True)
+    assert saved[-1] == ("a.json", 1000) and "1000 moves per walker, 8 walkers" in lines[-1]
+    for k, v in (("WORLD_SIZE", "4"), ("RANK", "2"), ("LOCAL_RANK", "2")):
+        monkeypatch.setenv(k, v)
+    assert histogram.main("--ising-N 16 --sad-min-T 1 --max-iter 50 --num-walkers 8 --save-as a.json --quiet".split(), out=lines.append) == 0
+    e = made[-1]
+    assert (e.moves, e.cfg.n_walkers, e.cfg.walker_offset, e.cfg.device) == (50, 2, 4, 2) and saved[-1] == ("a.rank2of4.json", 50)
