@@ -663,6 +663,7 @@ struct YamlReader {
 
   explicit YamlReader(const std::string& src) {
     size_t p = 0;
+    Scan st; // carried from line to line: an open quoted scalar, the depth of an open flow collection
     while (p <= src.size()) {
       size_t e = src.find('\n', p);
       if (e == std::string::npos) e = src.size();
@@ -671,29 +672,109 @@ struct YamlReader {
       if (!l.empty() && l.back() == '\r') l.pop_back();
       int ind = 0;
       while ((size_t)ind < l.size() && l[(size_t)ind] == ' ') ind++;
-      std::string t = strip_comment(l.substr((size_t)ind));
-      if (t.empty() || t == "---" || t == "...") continue;
+      const bool continuation = st.open_quote != 0 || st.depth > 0;
+      std::string t = strip_comment(l.substr((size_t)ind), st);
+      if (!continuation && (t.empty() || t == "---" || t == "...")) continue;
+      if (continuation && t.empty()) continue;
       lines.push_back({ind, t});
     }
   }
-  static std::string strip_comment(const std::string& t) {
-    size_t end = t.size();
-    for (size_t k = 0; k < t.size();) {
+  struct Scan {
+    char open_quote = 0;
+    int depth = 0;
+  };
+  // Cut a trailing comment.  A '#' is a comment only outside quoted scalars; a quote opens a scalar only where a
+  // scalar can begin (start of a block value or key, or a token inside a flow collection); '[' / '{' open a flow
+  // collection only where a block value begins.  Both can stay open over line ends.
+  static std::string strip_comment(const std::string& t, Scan& st) {
+    const size_t n = t.size();
+    size_t end = n, k = 0;
+    if (st.open_quote) { // find the end of the scalar that began on an earlier line
+      const char q = st.open_quote;
+      bool closed = false;
+      while (k < n) {
+        if (q == '"' && t[k] == '\\') {
+          k += 2;
+          continue;
+        }
+        if (t[k] == q) {
+          if (q == '\'' && k + 1 < n && t[k + 1] == '\'') {
+            k += 2;
+            continue;
+          }
+          k++;
+          closed = true;
+          break;
+        }
+        k++;
+      }
+      if (!closed) return t;
+      st.open_quote = 0;
+    }
+    bool value_start = st.depth == 0 && k == 0; // a key, a "- " entry or a scalar may begin here
+    bool seen_key_colon = false;
+    while (k < n) {
       const char c = t[k];
-      size_t b = k;
-      while (b > 0 && t[b - 1] == ' ') b--;
-      const bool token_start = b == 0 || t[b - 1] == '[' || t[b - 1] == '{' || t[b - 1] == ',' || (b < k && (t[b - 1] == ':' || t[b - 1] == '-'));
-      if ((c == '"' || c == '\'') && token_start) {
-        const size_t e = skip_quoted(t, k);
-        if (e == std::string::npos) break;
-        k = e;
-        continue;
+      if (st.depth == 0) {
+        if (value_start) {
+          if (c == ' ') {
+            k++;
+            continue;
+          }
+          if (c == '-' && (k + 1 == n || t[k + 1] == ' ')) { // block sequence entry
+            k += 2;
+            continue;
+          }
+          if (c == '"' || c == '\'') {
+            const size_t e = skip_quoted(t, k);
+            if (e == std::string::npos) {
+              st.open_quote = c;
+              return t;
+            }
+            k = e;
+            value_start = false;
+            continue;
+          }
+          if (c == '[' || c == '{') {
+            st.depth = 1;
+            k++;
+            value_start = false;
+            continue;
+          }
+          value_start = false; // a plain scalar or key begins: quotes and brackets inside it are text
+        }
+        if (c == ':' && (k + 1 == n || t[k + 1] == ' ') && !seen_key_colon) {
+          seen_key_colon = true;
+          value_start = true;
+          k++;
+          continue;
+        }
+        if (c == '#' && (k == 0 || t[k - 1] == ' ')) {
+          end = k;
+          break;
+        }
+        k++;
+      } else { // inside a flow collection
+        size_t b = k;
+        while (b > 0 && t[b - 1] == ' ') b--;
+        const bool token_start = b == 0 || t[b - 1] == '[' || t[b - 1] == '{' || t[b - 1] == ',' || (b < k && t[b - 1] == ':');
+        if ((c == '"' || c == '\'') && token_start) {
+          const size_t e = skip_quoted(t, k);
+          if (e == std::string::npos) {
+            st.open_quote = c;
+            return t;
+          }
+          k = e;
+          continue;
+        }
+        if (c == '[' || c == '{') st.depth++;
+        if (c == ']' || c == '}') st.depth--;
+        if (c == '#' && (k == 0 || t[k - 1] == ' ')) {
+          end = k;
+          break;
+        }
+        k++;
       }
-      if (c == '#' && (k == 0 || t[k - 1] == ' ')) {
-        end = k;
-        break;
-      }
-      k++;
     }
     while (end > 0 && (t[end - 1] == ' ' || t[end - 1] == '\t')) end--;
     return t.substr(0, end);

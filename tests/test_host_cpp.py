@@ -169,7 +169,7 @@ def test_codecs_fuzz_against_the_python_host(tmp_path):
     docs = st.recursive(scalars, lambda c: st.one_of(st.lists(c, max_size=5), st.dictionaries(keys, c, max_size=5)), max_leaves=30)
     n = [0]
 
-    @settings(max_examples=80, deadline=None, suppress_health_check=list(HealthCheck))
+    @settings(max_examples=300, derandomize=True, deadline=None, suppress_health_check=list(HealthCheck))
     @given(st.dictionaries(keys, docs, min_size=1, max_size=6), st.sampled_from(["yaml", "json", "cbor"]), st.sampled_from(["yaml", "json", "cbor"]))
     def check(doc, src, dst):
         n[0] += 1
