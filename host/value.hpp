@@ -675,7 +675,13 @@ struct YamlReader {
       const bool continuation = st.open_quote != 0 || st.depth > 0;
       std::string t = strip_comment(l.substr((size_t)ind), st);
       if (!continuation && (t.empty() || t == "---" || t == "...")) continue;
-      if (continuation && t.empty()) continue;
+      if (continuation) { // the rest of a flow collection or quoted scalar: folded into the line it began on (a line break is a space)
+        if (!t.empty() && !lines.empty()) {
+          lines.back().text += ' ';
+          lines.back().text += t;
+        }
+        continue;
+      }
       lines.push_back({ind, t});
     }
   }
