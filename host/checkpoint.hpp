@@ -474,13 +474,81 @@ inline std::string walker_path(const std::string& save_as, uint32_t w, uint32_t 
 }
 inline Value load(const std::string& path) { return loads(read_file(path), extension_of(path)); }
 
-// MonteCarlo::checkpoint (mc/mod.rs:110-120) for walkers [0, n_save)
+inline std::string partial_marker(const std::string& save_as) {
+  const size_t slash = save_as.find_last_of('/');
+  const size_t dot = save_as.find_last_of('.');
+  const bool has_ext = dot != std::string::npos && (slash == std::string::npos || dot > slash);
+  return (has_ext ? save_as.substr(0, dot) : save_as) + ".partial";
+}
+
+// MonteCarlo::checkpoint (mc/mod.rs:110-120) for walkers [0, n_save).  The set of per-walker files is written all or
+// nothing: halted walkers stop the save before any file is touched, every document goes to a temporary file beside its
+// target, and only then are the temporaries renamed into place.  A partial set (n_save < n_walkers) is marked by
+// `name.partial` so that a later resume refuses it with a clear message.
 inline void save(const GpuEnergyMC& mc, const std::string& save_as, uint32_t n_save, const Value& report, const Value& movies, const Value& save_doc) {
   const std::string ext = extension_of(save_as);
-  for (uint32_t w = 0; w < n_save && w < mc.n_walkers(); w++) {
-    const std::string p = walker_path(save_as, w, mc.n_walkers());
-    write_atomic(p, dumps(walker_document(mc, w, p, report, movies, save_doc), ext));
+  uint64_t left = 0, failed = 0;
+  mc.num_halted(&left, &failed);
+  if (left || failed)
+    throw std::runtime_error("no checkpoint written: " + std::to_string(left) + " walker(s) left the bin window and " + std::to_string(failed) +
+                             " failed verify_energy");
+  const uint32_t n = n_save < mc.n_walkers() ? n_save : mc.n_walkers();
+  std::vector<std::pair<std::string, std::string>> staged; // (temporary, target)
+  try {
+    for (uint32_t w = 0; w < n; w++) {
+      const std::string p = walker_path(save_as, w, mc.n_walkers());
+      const std::string tmp = p + ".tmp." + std::to_string((long)getpid());
+      const size_t slash = p.find_last_of('/');
+      if (slash != std::string::npos) make_dirs(p.substr(0, slash));
+      const std::string data = dumps(walker_document(mc, w, p, report, movies, save_doc), ext);
+      std::ofstream f(tmp, std::ios::binary | std::ios::trunc);
+      if (!f) throw std::runtime_error("error creating file \"" + p + "\"");
+      staged.emplace_back(tmp, p);
+      f.write(data.data(), (std::streamsize)data.size());
+      f.flush();
+      if (!f) throw std::runtime_error("error writing checkpoint \"" + p + "\"");
+    }
+    for (auto& tp : staged)
+      if (rename(tp.first.c_str(), tp.second.c_str()) != 0) throw std::runtime_error("error renaming checkpoint \"" + tp.second + "\"");
+  } catch (...) {
+    for (auto& tp : staged) unlink(tp.first.c_str());
+    throw;
   }
+  const std::string marker = partial_marker(save_as);
+  if (n < mc.n_walkers())
+    write_atomic(marker, std::to_string(n) + " of " + std::to_string(mc.n_walkers()) + " walkers\n");
+  else if (file_exists(marker))
+    unlink(marker.c_str());
+}
+
+// Before any engine is created: the checkpoint set must be complete and (cfg != nullptr) must describe the configuration
+// the command line asks for.  Throws std::runtime_error saying what is wrong.
+inline sadmc_config config_from_document(const Value& doc, uint32_t n_walkers);
+inline void check_resumable(const sadmc_config* cfg, const std::string& save_as, uint32_t n_walkers) {
+  const std::string marker = partial_marker(save_as);
+  if (file_exists(marker)) {
+    std::string what = read_file(marker);
+    while (!what.empty() && (what.back() == '\n' || what.back() == ' ')) what.pop_back();
+    throw std::runtime_error(save_as + " holds only " + what + " (written with --checkpoint-walkers): it cannot be resumed");
+  }
+  uint32_t missing = 0;
+  std::string first_missing;
+  for (uint32_t w = 0; w < n_walkers; w++)
+    if (!file_exists(walker_path(save_as, w, n_walkers))) {
+      if (!missing) first_missing = walker_path(save_as, w, n_walkers);
+      missing++;
+    }
+  if (missing)
+    throw std::runtime_error("checkpoint set " + save_as + " is incomplete: " + std::to_string(missing) + " of " + std::to_string(n_walkers) +
+                             " walker files are missing (first: " + first_missing + ")");
+  if (!cfg) return;
+  const sadmc_config want = config_from_document(load(walker_path(save_as, 0, n_walkers)), n_walkers);
+  if (cfg->system != want.system) throw std::runtime_error("checkpoint " + save_as + " was written for another system");
+  if (cfg->N != want.N) throw std::runtime_error("checkpoint " + save_as + " was written for another system size");
+  if (cfg->energy_bin == cfg->energy_bin && cfg->energy_bin != want.energy_bin)
+    throw std::runtime_error("checkpoint " + save_as + " was written with another bin width");
+  const bool same = cfg->method == want.method || (cfg->method == SADMC_METHOD_INV_T_WL && want.method == SADMC_METHOD_SAMC);
+  if (!same) throw std::runtime_error("checkpoint " + save_as + " was written by another method");
 }
 
 // `--save-as` on an existing file (mc/mod.rs:70-84): restore every walker of a fresh INIT_EXTERNAL engine
@@ -491,7 +559,8 @@ inline void resume_into(GpuEnergyMC& mc, const std::string& save_as) {
     const Value doc = load(walker_path(save_as, w, mc.n_walkers()));
     restore_walker(mc, w, doc);
     const uint64_t m = doc.at("moves").as_u64();
-    if (have && m != moves) throw std::runtime_error("walker checkpoints disagree on `moves`");
+    if (have && m != moves)
+      throw std::runtime_error("walker checkpoints disagree on `moves`: the set " + save_as + " was interrupted while it was being replaced");
     moves = m;
     have = true;
   }

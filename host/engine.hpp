@@ -35,6 +35,8 @@ struct Api {
   SADMC_FN(sadmc_run)
   SADMC_FN(sadmc_num_moves)
   SADMC_FN(sadmc_num_accepted_moves)
+  SADMC_FN(sadmc_accepted_moves_range)
+  SADMC_FN(sadmc_num_halted)
   SADMC_FN(sadmc_get_walker)
   SADMC_FN(sadmc_get_bins)
   SADMC_FN(sadmc_system_len)
@@ -78,6 +80,8 @@ struct Api {
     SADMC_FN(sadmc_run)
     SADMC_FN(sadmc_num_moves)
     SADMC_FN(sadmc_num_accepted_moves)
+    SADMC_FN(sadmc_accepted_moves_range)
+    SADMC_FN(sadmc_num_halted)
     SADMC_FN(sadmc_get_walker)
     SADMC_FN(sadmc_get_bins)
     SADMC_FN(sadmc_system_len)
@@ -153,6 +157,12 @@ class GpuEnergyMC {
     check(api.sadmc_num_accepted_moves(h, &a));
     return a;
   }
+  uint64_t min_accepted_moves() const { // the slowest walker's count: every walker is one reference run
+    uint64_t lo = 0, hi = 0;
+    check(api.sadmc_accepted_moves_range(h, &lo, &hi));
+    return lo;
+  }
+  void num_halted(uint64_t* left_window, uint64_t* failed_verify) const { check(api.sadmc_num_halted(h, left_window, failed_verify)); }
   uint64_t launch_count() const {
     uint64_t n = 0;
     check(api.sadmc_launch_count(h, &n));

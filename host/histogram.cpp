@@ -91,14 +91,15 @@ static int real_main(int argc, char** argv) {
   const uint32_t total_walkers = has(flags, "num-walkers") ? (uint32_t)flags.at("num-walkers").u : 1;
   if (world < 1 || total_walkers % (uint32_t)world) throw UsageError("--num-walkers " + std::to_string(total_walkers) + " does not divide over " + std::to_string(world) + " processes");
   const uint32_t n_walkers = total_walkers / (uint32_t)world;
-  auto rank_path = [&](const std::string& path) {
+  auto rank_path_of = [&](const std::string& path, long r) {
     if (world == 1) return path;
     const size_t slash = path.find_last_of('/');
     const size_t dot = path.find_last_of('.');
     const bool has_ext = dot != std::string::npos && (slash == std::string::npos || dot > slash);
-    const std::string tag = ".rank" + std::to_string(rank) + "of" + std::to_string(world);
+    const std::string tag = ".rank" + std::to_string(r) + "of" + std::to_string(world);
     return has_ext ? path.substr(0, dot) + tag + path.substr(dot) : path + tag;
   };
+  auto rank_path = [&](const std::string& path) { return rank_path_of(path, rank); };
   auto place = [&](sadmc_config& c) {
     if (world > 1) {
       c.n_walkers = n_walkers;
@@ -116,7 +117,7 @@ static int real_main(int argc, char** argv) {
   std::string save_as;
   std::unique_ptr<GpuEnergyMC> mc;
   Movie movies;
-  bool restore_movies = false;
+  bool restore_movies = false, resumed = false;
   Value movie_state;
   if (has(flags, "resume-from")) { // Params::ResumeFrom, mc/mod.rs:92-106: nothing else is read from the command line
     const std::string path = rank_path(flags.at("resume-from").path);
@@ -151,21 +152,35 @@ static int real_main(int argc, char** argv) {
       print_json(Value::map().set("resume_from", Value::string(path)).set("config", config_summary(cfg)).set("plugins", plugin_summary(pp)));
       return 0;
     }
+    check_resumable(nullptr, path, n_walkers);
     mc.reset(new GpuEnergyMC(cfg, lib_hint));
     resume_into(*mc, path);
     printf("Resuming from file \"%s\"\n", path.c_str());
+    resumed = true;
   } else {
     cfg = config_from_flags(flags);
     place(cfg);
     save_as = rank_path(has(flags, "save-as") ? flags.at("save-as").path : "resume.yaml"); // mc/mod.rs:88
     if (!known_ext(save_as)) throw UsageError("I don't know how to create file \"" + save_as + "\""); // mc/mod.rs:118
     const std::string first = walker_path(save_as, 0, n_walkers);
-    const bool resuming = has(flags, "save-as") && file_exists(first);
+    // every rank takes the same decision from the files of ALL ranks (one node, one file system): a run resumes when
+    // some rank has a checkpoint, and then every rank's set must be complete and written for this command line
+    bool resuming = false;
+    std::vector<std::string> all_sets;
+    for (long r = 0; r < world; r++) all_sets.push_back(rank_path_of(has(flags, "save-as") ? flags.at("save-as").path : "resume.yaml", r));
+    if (has(flags, "save-as"))
+      for (auto& p : all_sets) resuming = resuming || file_exists(walker_path(p, 0, n_walkers)) || file_exists(partial_marker(p));
+    if (resuming) {
+      if (has(flags, "checkpoint-walkers") && flags.at("checkpoint-walkers").u < n_walkers)
+        throw UsageError("--checkpoint-walkers writes a partial set that cannot be resumed; " + first + " exists: remove it or drop --checkpoint-walkers");
+      for (auto& p : all_sets) check_resumable(&cfg, p, n_walkers);
+    }
     if (has(flags, "dry-run")) {
       print_json(Value::map().set("config", config_summary(cfg)).set("plugins", plugin_summary(pp)).set("save_as", Value::string(save_as))
                      .set("resuming", Value::boolean(resuming)));
       return 0;
     }
+    resumed = resuming;
     if (resuming) { // mc/mod.rs:70-84, then update_from_params (energy.rs:899-902): report + save come from the flags
       cfg.init_mode = SADMC_INIT_EXTERNAL;
       mc.reset(new GpuEnergyMC(cfg, lib_hint));
@@ -189,13 +204,18 @@ static int real_main(int argc, char** argv) {
   Save save;
   save.has_save_time = pp.has_save_time;
   save.save_time_seconds = 3600.0 * pp.save_time;
+  if (resumed) {
+    report.set_resumed();
+    save.set_resumed();
+  }
   if (pp.has_movie_time) movies.set_movie_time(pp.movie_time);
   if (restore_movies) movies.restore(movie_state);
   const uint32_t n_save = has(flags, "checkpoint-walkers") ? (uint32_t)flags.at("checkpoint-walkers").u : mc->n_walkers();
 
   McView view;
   view.num_moves = [&] { return mc->num_moves(); };
-  view.num_accepted_moves = [&] { return mc->num_accepted_moves(); };
+  view.num_accepted_moves = [&] { return mc->num_accepted_moves() / (mc->n_walkers() ? mc->n_walkers() : 1); }; // mean per walker
+  view.min_accepted_moves = [&] { return mc->min_accepted_moves(); };
   view.verify_energy = [&] { // PluginManager::run calls sys.verify_energy() before logging (plugin.rs:102-103)
     if (!mc->verify_energy(0)) throw EngineError(SADMC_ERR_VERIFY, "verify_energy failed for walker 0");
   };

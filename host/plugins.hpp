@@ -46,11 +46,13 @@ struct TimeToRun { // plugin.rs:43-51
 };
 
 // what the plugins call on `MonteCarlo` (mc/mod.rs:37-143)
+// With many walkers the per-run quantities are per-walker quantities (every walker is one reference run):
+// num_accepted_moves = mean per walker (progress line), independent_samples = the slowest walker's accepted moves.
 struct McView {
-  std::function<uint64_t()> num_moves, num_accepted_moves;
+  std::function<uint64_t()> num_moves, num_accepted_moves, min_accepted_moves;
   std::function<void()> checkpoint, verify_energy;
   std::function<void(uint64_t)> save_movie_frame;
-  uint64_t independent_samples() const { return num_accepted_moves(); } // mc/mod.rs:134-136
+  uint64_t independent_samples() const { return min_accepted_moves ? min_accepted_moves() : num_accepted_moves(); } // mc/mod.rs:134-136
 };
 
 struct Plugin {
@@ -61,18 +63,28 @@ struct Plugin {
   virtual void save(McView&) {}
 };
 
-inline double now_seconds() {
+inline double steady_seconds() {
   using namespace std::chrono;
   return duration<double>(steady_clock::now().time_since_epoch()).count();
 }
+// the clock the plugins read; tests replace it (host/selftest_plugins.cpp)
+inline std::function<double()>& plugin_clock() {
+  static std::function<double()> c = steady_seconds;
+  return c;
+}
+inline double now_seconds() { return plugin_clock()(); }
 
 struct Report : Plugin { // plugin.rs:149-310
   TimeToRun max_iter;
   bool has_max_samples = false;
   uint64_t max_independent_samples = 0;
   bool quiet = false;
+  // `start` is #[serde(skip, default)] (plugin.rs:153-155): a resumed Report has None and takes (now, moves) at its
+  // first log instead of printing (262-264) -- set_resumed()
+  bool has_start = true;
   double start_time = now_seconds();
   uint64_t start_moves = 0;
+  void set_resumed() { has_start = false; }
 
   Value document() const {
     Value v = Value::map();
@@ -98,6 +110,12 @@ struct Report : Plugin { // plugin.rs:149-310
   void print(McView& mc) { // Report::print 206-269 (wording kept, durations in seconds)
     if (quiet) return;
     const uint64_t moves = mc.num_moves();
+    if (!has_start) { // plugin.rs:262-264
+      has_start = true;
+      start_time = now_seconds();
+      start_moves = moves;
+      return;
+    }
     const double dt = now_seconds() - start_time;
     const double per_move = dt / (double)(moves > start_moves ? moves - start_moves : 1);
     if (max_iter.kind == TimeToRun::TotalMoves) {
@@ -120,8 +138,15 @@ struct Save : Plugin { // plugin.rs:313-400
   uint64_t next_output = 1;
   bool has_save_time = true;
   double save_time_seconds = 3600.0;
+  // next_output and start are #[serde(skip, default)] (plugin.rs:315-320): a resumed run saves at its first tick
+  // (next_output = 0), takes (now, moves) as its start there and saves next 2^20 moves later (373-376)
+  bool has_start = true;
   double start_time = now_seconds();
   uint64_t start_moves = 0;
+  void set_resumed() {
+    has_start = false;
+    next_output = 0;
+  }
 
   Value document() const {
     Value v = Value::map();
@@ -131,6 +156,13 @@ struct Save : Plugin { // plugin.rs:313-400
   bool shall_i_save(uint64_t moves) { // 353-383
     if (moves < next_output) return false;
     if (has_save_time) {
+      if (!has_start) { // plugin.rs:373-376
+        has_start = true;
+        start_time = now_seconds();
+        start_moves = moves;
+        next_output = moves + (1ull << 20);
+        return true;
+      }
       double per_move = (now_seconds() - start_time) / (double)(moves > start_moves ? moves - start_moves : 1);
       if (per_move < 1e-30) per_move = 1e-30;
       const double mpp = 1.0 + std::floor(save_time_seconds / per_move);

@@ -2,6 +2,8 @@
 // GPU): prints one line per manager tick so that tests/test_host_cpp.py can hold the schedule against the Python host's
 // (which is itself held against a literal per-move restatement of src/mc/plugin.rs:93-144).
 //   selftest_plugins MAX_ITER MOVIE_TIME|none SAVE_DOUBLING(0|1) ACCEPT_EVERY [MAX_SAMPLES]
+//   selftest_plugins resumed RESUMED_AT MOVES_PER_SECOND SAVE_TIME_SECONDS N_SAVES
+//       a run resumed at RESUMED_AT moves under a scripted clock: prints the moves of the first N_SAVES checkpoints
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -10,7 +12,42 @@
 
 using namespace sadmc_host;
 
+static int resumed_schedule(char** argv) {
+  uint64_t moves = strtoull(argv[2], nullptr, 10);
+  const double rate = atof(argv[3]);
+  double t = 0.0;
+  plugin_clock() = [&] { return t; };
+  Report report;
+  report.quiet = true;
+  report.max_iter = TimeToRun::never();
+  report.set_resumed();
+  Save save;
+  save.save_time_seconds = atof(argv[4]);
+  save.set_resumed();
+  int saves = 0;
+  const int want = atoi(argv[5]);
+  McView mc;
+  mc.num_moves = [&] { return moves; };
+  mc.num_accepted_moves = [&] { return moves / 2; };
+  mc.verify_energy = [] {};
+  mc.checkpoint = [&] {
+    printf("checkpoint %llu\n", (unsigned long long)moves);
+    saves++;
+  };
+  mc.save_movie_frame = [](uint64_t) {};
+  std::vector<Plugin*> plugins = {&report, &save};
+  PluginManager manager;
+  for (int guard = 0; guard < 1000 && saves < want; guard++) {
+    const uint64_t n = manager.moves_until_next_action();
+    moves += n;
+    t += (double)n / rate;
+    manager.run(mc, plugins, n);
+  }
+  return saves == want ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
+  if (argc == 6 && strcmp(argv[1], "resumed") == 0) return resumed_schedule(argv);
   if (argc < 5) return 2;
   const uint64_t max_iter = strtoull(argv[1], nullptr, 10);
   uint64_t moves = 0;

@@ -203,11 +203,19 @@ int sadmc_set_stream(sadmc_engine* e, void* cuda_stream);
 void* sadmc_get_stream(sadmc_engine* e);
 
 /* ---- the hot path ------------------------------------------------------ */
-/* n_moves x `move_once` (energy.rs:904-974) for every walker.  Blocking. */
+/* n_moves x `move_once` (energy.rs:904-974) for every walker.  Blocking.
+ * Returns SADMC_ERR_WINDOW when walkers left the device bin window during this call (the reference would have grown
+ * its vectors, energy.rs:400-434; here such a walker freezes with its status set and the caller is told at once),
+ * SADMC_ERR_VERIFY when the in-loop `verify_energy` of energy.rs:907-911 failed for a walker (the reference
+ * panics: lj.rs:259, wca.rs:248, optsquare.rs:200).  Each halted walker is reported by one call only; the other
+ * walkers have completed their n_moves and the engine stays usable. */
 int sadmc_run(sadmc_engine* e, uint64_t n_moves);
 /* Same, but only enqueues on the engine's stream. */
 int sadmc_run_async(sadmc_engine* e, uint64_t n_moves);
+/* Waits for the stream; reports newly halted walkers like sadmc_run. */
 int sadmc_sync(sadmc_engine* e);
+/* Walkers halted since creation: left the bin window / failed verify_energy.  Either pointer may be NULL. */
+int sadmc_num_halted(sadmc_engine* e, uint64_t* left_window, uint64_t* failed_verify);
 /* Device time of the move kernel(s) of the last sadmc_run, CUDA events. */
 int sadmc_last_run_ms(sadmc_engine* e, float* ms);
 /* How many kernels of this library have been launched by this engine. */
@@ -216,6 +224,8 @@ int sadmc_launch_count(sadmc_engine* e, uint64_t* n);
 /* ---- state out (what Report/Save/Movie and the parity tests read) ------ */
 int sadmc_num_moves(sadmc_engine* e, uint64_t* moves);                  /* MonteCarlo::num_moves, energy.rs:981 */
 int sadmc_num_accepted_moves(sadmc_engine* e, uint64_t* accepted_sum);  /* energy.rs:984, summed over walkers */
+/* Smallest and largest per-walker accepted-move count (what one reference process would report lies in between). */
+int sadmc_accepted_moves_range(sadmc_engine* e, uint64_t* min_accepted, uint64_t* max_accepted);
 int sadmc_get_walker(sadmc_engine* e, uint32_t w, sadmc_walker_state* out);
 int sadmc_get_energies(sadmc_engine* e, double* energies /* [n_walkers] */);
 /* `Bins` (energy.rs:146-163) + round-trip vectors (203-205) of walker w, in
@@ -270,8 +280,18 @@ int sadmc_cell_box(sadmc_engine* e, double box_diagonal[3], double* r_cutoff);
  * ln w only for bins inside its own [too_lo, too_hi], the range in which SAD defines ln w
  * (plotting/parse-binning.py:150-164 reconstructs the rest from the histogram). */
 int sadmc_fold_select(sadmc_engine* e, uint32_t first_walker, uint32_t walker_stride, int sad_range_only);
+/* Same with at most `walker_count` walkers (0 = to the end): with stride 1 a contiguous block, i.e. the shard a rank of
+ * a multi-GPU run would hold.  sad_range_only = 2 counts only the bins STRICTLY inside (too_lo, too_hi): the two end
+ * bins are centred on too_lo / too_hi and `update_weights` reverts the increment for the half of their visits that
+ * lies outside the range (energy.rs:535-538), so their ln w is not an estimate of the entropy. */
+int sadmc_fold_select_ex(sadmc_engine* e, uint32_t first_walker, uint32_t walker_stride, uint32_t walker_count,
+                         int sad_range_only);
 int sadmc_fold_device(sadmc_engine* e, void* d_histogram, void* d_energy_total, void* d_energy_squared_total,
                       void* d_lnw_sum, void* d_lnw_sq_sum, void* d_lnw_count);
+/* The same fold as ONE device buffer of 7 x nbins doubles, for a single collective: histogram >> 32,
+ * histogram & 0xffffffff (both exact in f64, also after summing over ranks), lnw_count, energy_total,
+ * energy_squared_total, lnw_sum, lnw_sq_sum. */
+int sadmc_fold_packed_device(sadmc_engine* e, void* d_packed);
 /* Same into HOST buffers (single-GPU convenience). */
 int sadmc_fold(sadmc_engine* e, uint64_t* histogram, double* energy_total, double* energy_squared_total,
                double* lnw_sum, double* lnw_sq_sum, uint64_t* lnw_count);
@@ -284,6 +304,8 @@ int sadmc_sys_compute_energy(sadmc_engine* e, uint32_t w, double* energy);    /*
 /* MovableSystem::plan_move: draws from walker w's RNG; *some = 0 is `None`. */
 int sadmc_sys_plan_move(sadmc_engine* e, uint32_t w, double mean_distance, int* some, double* e_new);
 int sadmc_sys_confirm(sadmc_engine* e, uint32_t w);                           /* ConfirmSystem::confirm  */
+/* System::randomize (system/mod.rs:59; lj.rs:262-279, wca.rs:252-270, fake.rs:102-111): draws from walker w's RNG. */
+int sadmc_sys_randomize(sadmc_engine* e, uint32_t w, double* energy);
 int sadmc_sys_verify_energy(sadmc_engine* e, uint32_t w);                     /* System::verify_energy   */
 
 /* ---- measurement utility (bench.py) --------------------------------------- */

@@ -301,6 +301,17 @@ int oracle_sys_plan_move(oracle_mc* o, double mean_distance, int* some, double* 
   return 0;
 }
 void oracle_sys_confirm(oracle_mc* o) { o->mc->system->confirm(); }
+// System::randomize (system/mod.rs:59) driven by the walker's own generator; returns 0 and the new energy, or
+// SADMC_ERR_UNSUPPORTED where the reference is todo!() / not restated (optsquare.rs:202-204, two-wells)
+int oracle_sys_randomize(oracle_mc* o, double* energy) {
+  try {
+    *energy = o->mc->system->randomize(o->mc->rng);
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return SADMC_ERR_UNSUPPORTED;
+  }
+}
 int oracle_sys_verify_energy(oracle_mc* o) { return o->mc->system->verify_energy() ? 0 : SADMC_ERR_VERIFY; }
 // SquareWell only: the reference's slow all-image recount (optsquare.rs:108-152)
 double oracle_sw_compute_energy_slowly(oracle_mc* o) {

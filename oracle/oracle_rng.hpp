@@ -124,7 +124,10 @@ struct Rng {
       const double v12 = float_with_exponent(next_u64() >> 12, 0);
       const double res = (v12 - 1.0) * scale + low;
       if (res < high) return res;
-      scale = bits_to_f64(sadmc_f64_bits(scale) - 1);
+      // rand 0.7.3 uniform.rs, UniformFloat::sample_single: `let mask = !scale.finite_mask(); if mask.any() { scale =
+      // scale.decrease_masked(mask) }` -- the scale only shrinks when high - low overflowed; a finite scale whose
+      // rounding produced res >= high simply draws again.
+      if (!std::isfinite(scale)) scale = bits_to_f64(sadmc_f64_bits(scale) - 1);
     }
   }
   // rand 0.7 Open01 for f64: (0,1)

@@ -25,6 +25,8 @@ PROTOTYPES = {
     "sadmc_launch_count": (C.c_int, [vp, u64p]),
     "sadmc_num_moves": (C.c_int, [vp, u64p]),
     "sadmc_num_accepted_moves": (C.c_int, [vp, u64p]),
+    "sadmc_num_halted": (C.c_int, [vp, u64p, u64p]),
+    "sadmc_accepted_moves_range": (C.c_int, [vp, u64p, u64p]),
     "sadmc_get_walker": (C.c_int, [vp, C.c_uint32, C.POINTER(WalkerState)]),
     "sadmc_get_energies": (C.c_int, [vp, f64p]),
     "sadmc_get_bins": (C.c_int, [vp, C.c_uint32, C.c_uint32, u64p, u64p, f64p, f64p, f64p, u64p, u8p, u64p, f64p, u64p]),
@@ -40,12 +42,15 @@ PROTOTYPES = {
     "sadmc_window": (C.c_int, [vp, f64p, f64p, C.POINTER(C.c_uint32)]),
     "sadmc_cell_box": (C.c_int, [vp, f64p, f64p]),
     "sadmc_fold_select": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_int]),
+    "sadmc_fold_select_ex": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
     "sadmc_fold_device": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    "sadmc_fold_packed_device": (C.c_int, [vp, vp]),
     "sadmc_fold": (C.c_int, [vp, u64p, f64p, f64p, f64p, f64p, u64p]),
     "sadmc_sys_energy": (C.c_int, [vp, C.c_uint32, f64p]),
     "sadmc_sys_compute_energy": (C.c_int, [vp, C.c_uint32, f64p]),
     "sadmc_sys_plan_move": (C.c_int, [vp, C.c_uint32, C.c_double, C.POINTER(C.c_int), f64p]),
     "sadmc_sys_confirm": (C.c_int, [vp, C.c_uint32]),
+    "sadmc_sys_randomize": (C.c_int, [vp, C.c_uint32, f64p]),
     "sadmc_sys_verify_energy": (C.c_int, [vp, C.c_uint32]),
     "sadmc_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, f64p]),
     "sadmc_selftest_exp_cmp": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, u64p, u64p]),

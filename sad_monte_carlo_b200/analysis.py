@@ -143,3 +143,124 @@ def cv_error_vs_reference(folds, ref_csv, T_min, T_max=np.inf):
     m = (Tr >= T_min) & (Tr <= T_max)
     mean, sem, _ = cv_from_grouped_folds(folds, Tr[m])
     return Tr[m], mean, sem, Cr[m], (mean - Cr[m]) / Cr[m]
+
+
+# ---- exact bin weights of the analytic systems: what ln w of a converged flat-histogram run estimates ---------------
+# A walker's ln w[i] converges to ln of the density of states INTEGRATED over bin i (plus a constant), so the gate
+# compares with the integral over the bin, not with D at the bin centre (they differ in the half bins at E = 0 and
+# E = 1 and wherever D varies across a bin, e.g. sqrt(E) near 0).
+
+def fake_bin_weights(function, window_lo, width, n, dimensions=3):
+    """Integral of the exact DOS of `--fake-linear` / `--fake-quadratic-dimensions d` over each window bin.
+
+    Same densities as plotting/analyze-boundaries.py:22-25 (linear: 1 on [0, 1]; quadratic: (d/2) E^(d/2-1), the
+    reference lists d = 3, 1.5 sqrt(E)), via their cumulative forms N(E) = E and N(E) = E^(d/2) on [0, 1]."""
+    edges = np.clip(window_lo + np.arange(n + 1) * width, 0.0, 1.0)
+    if function == "linear":
+        cum = edges
+    elif function == "quadratic":
+        cum = edges ** (0.5 * dimensions)
+    else:
+        raise ValueError(function)
+    return np.diff(cum)
+
+
+def two_wells_energy(x1, rho2, h2_to_h1, r2, barrier_over_h1):
+    """`TwoWells::find_energy` (src/system/two_wells.rs:266-315) on arrays: energy, and NaN where the move is forbidden."""
+    r1 = 1.0
+    rw = np.sqrt(barrier_over_h1) * 1.0 + r2 * np.sqrt(1.0 + barrier_over_h1 - 1.0 / h2_to_h1)
+    x2 = x1 - r1 - r2
+    xw = x1 - rw
+    xi = x2 + rw
+    d1, d2, dw, di = rho2 + x1 * x1, rho2 + x2 * x2, rho2 + xw * xw, rho2 + xi * xi
+    e_1 = d1 / (r1 * r1) - 1.0
+    e_2 = h2_to_h1 * (d2 / (r2 * r2) - 1.0)
+    e_w = h2_to_h1 * (dw / (r2 * r2) - 1.0)
+    e_i = di / (r1 * r1) - 1.0
+    big = d1 <= r1 * r1
+    small = ~big & (d2 <= r2 * r2)
+    cyl = ~big & ~small & (rho2 <= r2 * r2) & (x1 > 0.0) & (x1 <= r1 + r2)
+    e = np.full(np.broadcast(x1, rho2).shape, np.nan)
+    e = np.where(big, np.minimum(e_1, e_w), e)
+    e = np.where(small, np.where((e_i > e_2) & (e_i < 0.0), e_i, e_2), e)
+    e = np.where(cyl, 0.0, e)
+    return e
+
+
+def two_wells_bin_weights(window_lo, width, n, N, h2_to_h1, r2):
+    """Exact volume of configuration space per energy bin (E < 0) of the two-wells system, any barrier height.
+
+    two-wells/system.py:86-90 writes D(e) as the sum of two hypersphere wells.  That sum is exact for the geometry of
+    two_wells.rs:266-315, not an approximation: inside the big sphere the states below E are the UNION of the ball of
+    radius sqrt(1 + E) about the origin and the ball of radius r2 sqrt(1 + E/h2) about `well_position`; inside the small
+    sphere they are the INTERSECTION of the mirror-image pair (same radii, same separation), so the two lens volumes
+    cancel and the cumulative volume is (1 + E)^(N/2) + r2^N (1 + E/h2)^(N/2) (times the unit N-ball's volume).  The
+    zero-energy cylinder only adds weight to the bin that holds E = 0.  tests/test_analysis.py checks this against the
+    direct quadrature below for barriers 0, 0.1, 0.2."""
+    edges = np.minimum(window_lo + np.arange(n + 1) * width, 0.0)
+    cum = np.clip(1.0 + edges, 0.0, None) ** (0.5 * N) + r2 ** N * np.clip(1.0 + edges / h2_to_h1, 0.0, None) ** (0.5 * N)
+    w = np.diff(cum)
+    w[window_lo + (np.arange(n) + 1) * width > 0.0] = 0.0  # the bin holding E = 0 also holds the cylinder: not gated
+    return w
+
+
+def two_wells_bin_weights_quadrature(window_lo, width, n, N, h2_to_h1, r2, barrier_over_h1, grid=6000):
+    """The same volumes by direct quadrature of `find_energy` (for coarse bins: the midpoint rule aliases fine ones).
+
+    The energy depends on x1 and rho^2 = sum of the other N - 1 squared coordinates only, so the N-dimensional
+    volume element is rho^(N-2) d rho d x1 (constant factors drop out of an entropy).  Midpoint rule on a
+    grid x grid mesh, binned exactly as `Bins::state_to_index` (energy.rs:371-373) bins energies."""
+    x = -1.0 + (np.arange(grid) + 0.5) * ((2.0 + 2.0 * r2 + 1e-9) / grid)
+    rho = (np.arange(grid) + 0.5) * (1.0 / grid)
+    w = np.zeros(n)
+    wt_rho = rho ** (N - 2)
+    for i0 in range(0, grid, 500):
+        xs = x[i0:i0 + 500, None]
+        e = two_wells_energy(xs, (rho * rho)[None, :], h2_to_h1, r2, barrier_over_h1)
+        ok = np.isfinite(e)
+        idx = np.floor((e[ok] - window_lo) / width).astype(np.int64)
+        wt = np.broadcast_to(wt_rho[None, :], e.shape)[ok]
+        good = (idx >= 0) & (idx < n)
+        w += np.bincount(idx[good], weights=wt[good], minlength=n)
+    return w
+
+
+def grouped_entropy(folds, groups, per_group, min_fraction=0.9):
+    """Per-group walker-mean entropies from SAD-range-only folds: list of (S, mask) for g in range(groups).
+
+    folds[g] is one `sadmc_fold` result for the interleaved group g (`sadmc_fold_select(g, groups, 1)`)."""
+    out = []
+    for g in range(groups):
+        cnt = np.asarray(folds[g]["lnw_count"], dtype=np.float64)
+        ok = cnt >= min_fraction * per_group
+        S = np.zeros_like(cnt)
+        S[ok] = np.asarray(folds[g]["lnw_sum"], dtype=np.float64)[ok] / cnt[ok]
+        out.append((S, ok))
+    return out
+
+
+def dos_gate(folds, groups, per_group, weights, min_fraction=0.9, min_weight=0.0):
+    """RMS of S - ln(exact bin weight) after removing the additive constant, per interleaved walker group.
+
+    Returns dict(rms_mean, rms_sem, rms_all, n_bins, worst): `rms_mean`/`rms_sem` are the mean and the standard
+    error over the groups' own RMS values (ensemble error bar); `rms_all` is the RMS of the all-walker mean entropy."""
+    lnD = np.full(len(weights), -np.inf)
+    pos = weights > min_weight
+    lnD[pos] = np.log(weights[pos])
+    per = grouped_entropy(folds, groups, per_group, min_fraction)
+    common = np.isfinite(lnD)
+    for _, ok in per:
+        common &= ok
+    rms = []
+    Sall = np.zeros(len(weights))
+    for S, _ in per:
+        d = S[common] - lnD[common]
+        d = d - d.mean()
+        rms.append(float(np.sqrt(np.mean(d * d))))
+        Sall[common] += S[common] / groups
+    d = Sall[common] - lnD[common]
+    d = d - d.mean()
+    rms = np.array(rms)
+    return {"rms_mean": float(rms.mean()), "rms_sem": float(rms.std(ddof=1) / np.sqrt(groups)) if groups > 1 else 0.0,
+            "rms_all": float(np.sqrt(np.mean(d * d))), "n_bins": int(common.sum()),
+            "worst": float(np.abs(d).max()) if common.any() else float("nan"), "residual": d, "mask": common}

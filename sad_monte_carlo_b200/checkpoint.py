@@ -375,6 +375,16 @@ def write_atomic(path, data):
         raise
 
 
+def stage(path, data):
+    """First half of write_atomic: the complete temporary file beside `path`; os.replace(tmp, path) publishes it."""
+    d = os.path.dirname(os.path.abspath(path))
+    os.makedirs(d, exist_ok=True)
+    fd, tmp = tempfile.mkstemp(dir=d, prefix="." + os.path.basename(path) + ".")
+    with os.fdopen(fd, "wb") as f:
+        f.write(data)
+    return tmp
+
+
 def walker_path(save_as, w, n_walkers):
     """One file per walker: `name.ext` for a single walker (as the reference), `name-w000017.ext` otherwise."""
     if n_walkers == 1:
@@ -384,15 +394,67 @@ def walker_path(save_as, w, n_walkers):
 
 
 def save(engine, save_as, walkers=None, **plugin_docs):
-    """MonteCarlo::checkpoint (mc/mod.rs:110-120) for the chosen walkers (default: all)."""
+    """MonteCarlo::checkpoint (mc/mod.rs:110-120) for the chosen walkers (default: all).
+
+    The set of per-walker files is written all or nothing: every walker is checked first (a halted walker stops the
+    save before any file is touched), every document is written to a temporary file beside its target, and only
+    then are the temporaries renamed into place; a partial set (`walkers` shorter than the engine) is marked by
+    `name.partial` so that a later resume refuses it with a clear message instead of failing on a missing file."""
     ext = os.path.splitext(str(save_as))[1].lstrip(".")
-    walkers = range(engine.n_walkers) if walkers is None else walkers
-    paths = []
-    for w in walkers:
-        p = walker_path(save_as, w, engine.n_walkers)
-        write_atomic(p, dumps(walker_document(engine, w, save_as=p, **plugin_docs), ext))
-        paths.append(p)
-    return paths
+    partial = walkers is not None and len(list(walkers)) < engine.n_walkers
+    walkers = list(range(engine.n_walkers) if walkers is None else walkers)
+    left, failed = engine.num_halted()
+    if left or failed:
+        bad = [w for w in range(engine.n_walkers) if engine.walker(w).status != 0][:8]
+        raise RuntimeError("no checkpoint written: %d walker(s) left the bin window and %d failed verify_energy (first: %s)"
+                           % (left, failed, bad))
+    staged = []
+    try:
+        for w in walkers:
+            p = walker_path(save_as, w, engine.n_walkers)
+            staged.append((stage(p, dumps(walker_document(engine, w, save_as=p, **plugin_docs), ext)), p))
+        for tmp, p in staged:
+            os.replace(tmp, p)
+    except BaseException:
+        for tmp, _ in staged:
+            if os.path.exists(tmp):
+                os.unlink(tmp)
+        raise
+    marker = os.path.splitext(str(save_as))[0] + ".partial"
+    if partial:
+        write_atomic(marker, ("%d of %d walkers\n" % (len(walkers), engine.n_walkers)).encode())
+    elif os.path.exists(marker):
+        os.unlink(marker)
+    return [p for _, p in staged]
+
+
+def check_resumable(cfg, save_as, n_walkers):
+    """Before any engine is created: the checkpoint set must be complete and must describe the configuration `cfg`.
+
+    Returns the document of walker 0.  Raises ValueError with what is wrong otherwise (missing files, a set written
+    with --checkpoint-walkers, a different system / size / method / bin width)."""
+    marker = os.path.splitext(str(save_as))[0] + ".partial"
+    if os.path.exists(marker):
+        raise ValueError("%s holds only %s (written with --checkpoint-walkers): it cannot be resumed"
+                         % (save_as, open(marker).read().strip()))
+    missing = [w for w in range(n_walkers) if not os.path.exists(walker_path(save_as, w, n_walkers))]
+    if missing:
+        raise ValueError("checkpoint set %s is incomplete: %d of %d walker files are missing (first: %s)"
+                         % (save_as, len(missing), n_walkers, walker_path(save_as, missing[0], n_walkers)))
+    doc0 = load(walker_path(save_as, 0, n_walkers))
+    if cfg is not None:
+        want = config_from_document(doc0, n_walkers=n_walkers)
+        for field, what in (("system", "system"), ("N", "system size"), ("energy_bin", "bin width")):
+            a, b = getattr(cfg, field), getattr(want, field)
+            if field == "energy_bin" and _abi.isnan(a):
+                continue  # no --energy-bin given: the system's own (what the document holds)
+            if a != b:
+                raise ValueError("checkpoint %s was written for another %s (%r, the command line says %r)" % (save_as, what, b, a))
+        m_doc, m_cfg = want.method, cfg.method
+        same = m_doc == m_cfg or (m_cfg == _abi.METHOD_INV_T_WL and m_doc == _abi.METHOD_SAMC)  # 1/t-WL after its switch
+        if not same:
+            raise ValueError("checkpoint %s was written by another method (%d, the command line says %d)" % (save_as, m_doc, m_cfg))
+    return doc0
 
 
 def load(path):
@@ -474,13 +536,15 @@ def resume(cfg, save_as):
     local = _abi.Config()
     C.memmove(C.byref(local), C.byref(cfg), C.sizeof(cfg))
     local.init_mode = _abi.INIT_EXTERNAL
+    check_resumable(None, save_as, local.n_walkers)
     eng = WalkerEngine(local)
     moves = None
     for w in range(eng.n_walkers):
         doc = load(walker_path(save_as, w, eng.n_walkers))
         restore_walker(eng, w, doc)
         if moves is not None and doc["moves"] != moves:
-            raise ValueError("walker checkpoints disagree on `moves` (%d vs %d)" % (doc["moves"], moves))
+            raise ValueError("walker checkpoints disagree on `moves` (%d vs %d): the set %s was interrupted while it was "
+                             "being replaced" % (doc["moves"], moves, save_as))
         moves = doc["moves"]
     eng.resume(moves)
     return eng

@@ -110,6 +110,7 @@ struct DevParams {
   double* sys;         // [n_walkers][sys_stride] f64 system image (LJ/WCA/SW/fake/two-wells)
   uint32_t* sys_words; // Ising: [n_walkers][ising_words] packed spins
   const double* zig;   // X[257] then F[257]
+  unsigned int* halted; // [0] walkers that left the bin window, [1] walkers whose verify_energy failed (since creation)
   uint32_t n_walkers, cap, sys_stride, ising_words;
   double width;
   int has_min, has_max;
@@ -596,8 +597,16 @@ struct Book {
 
   // ---- round trips (energy.rs:950-965) ------------------------------------
   __device__ __forceinline__ void round_trips(int i1_ref, unsigned long long moves) {
-    if (P.flags & SADMC_FLAG_NO_ROUND_TRIPS) return;
     const int i_ref = ci - lo;
+    if (P.flags & SADMC_FLAG_NO_ROUND_TRIPS) {
+      // max_S / max_S_index are still kept: the largest ln w of the walker is what the merge for reporting aligns
+      // walkers by (fold_kernels.cuh), and it costs two instructions here instead of a pass over the window there
+      if (c_lnw > max_S) {
+        max_S = c_lnw;
+        max_S_index = i_ref;
+      }
+      return;
+    }
     if (c_lnw > max_S) {
       max_S = c_lnw;
       max_S_index = i_ref;

@@ -62,7 +62,9 @@ struct sadmc_engine {
   double* d_fold_part = nullptr; // per-chunk partial sums of the two-stage fold
   size_t fold_part_bytes = 0;
   float last_ms = 0.f;
-  FoldSel fold_sel = {0u, 1u, 0};
+  FoldSel fold_sel = {0u, 1u, 0u, 0};
+  unsigned int* h_halted = nullptr;     // pinned copy of P.halted, refreshed behind every launch
+  unsigned int halted_seen[2] = {0, 0}; // what sadmc_sync has reported already
   std::vector<void*> allocs;
 };
 
@@ -444,6 +446,7 @@ void sadmc_destroy(sadmc_engine* e) {
   cudaSetDevice(e->cfg.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (void* p : e->allocs) cudaFree(p);
+  if (e->h_halted) cudaFreeHost(e->h_halted);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -513,6 +516,9 @@ int sadmc_create(const sadmc_config* cfg, sadmc_engine** out) {
   BAIL(dev_alloc(e, (void**)&e->d_zig, 2 * SADMC_ZIG_TABLE_LEN * 8, false));
   BAIL(dev_alloc(e, (void**)&e->d_shim, sizeof(ShimOut), true));
   BAIL(dev_alloc(e, (void**)&e->d_pending, 8 * 8, true));
+  BAIL(dev_alloc(e, (void**)&P.halted, 2 * sizeof(unsigned int), true));
+  CKB(cudaMallocHost((void**)&e->h_halted, 2 * sizeof(unsigned int)));
+  e->h_halted[0] = e->h_halted[1] = 0;
   {
     double z[2 * SADMC_ZIG_TABLE_LEN];
     memcpy(z, hostctor::H_ZX, sizeof hostctor::H_ZX);
@@ -547,6 +553,7 @@ int sadmc_start(sadmc_engine* e) {
                                                          e->cfg.method, e->cfg.samc_t0, 100000000ull);
   e->launches++;
   CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(e->h_halted, e->P.halted, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   e->started = true;
   e->moves = 0;
@@ -583,13 +590,34 @@ int sadmc_run_async(sadmc_engine* e, uint64_t n_moves) {
   f<<<grid, block, smem, e->stream>>>(e->P, e->moves, n_moves);
   CK(cudaGetLastError());
   CK(cudaEventRecord(e->ev1, e->stream));
+  CK(cudaMemcpyAsync(e->h_halted, e->P.halted, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, e->stream));
   e->launches++;
   e->moves += n_moves;
   return 0;
 }
+// A walker that leaves its bin window (or fails verify_energy, where the reference panics) freezes with its status
+// set; the run reports it at the next synchronisation instead of carrying on silently.  Each halted walker is
+// reported once; sadmc_num_halted gives the totals at any time.
 int sadmc_sync(sadmc_engine* e) {
   if (!e) return fail(SADMC_ERR_INVALID, "null engine");
   CK(cudaStreamSynchronize(e->stream));
+  if (e->h_halted) {
+    const unsigned int win = e->h_halted[0], ver = e->h_halted[1];
+    const unsigned int new_win = win - e->halted_seen[0], new_ver = ver - e->halted_seen[1];
+    e->halted_seen[0] = win;
+    e->halted_seen[1] = ver;
+    if (new_ver) return fail(SADMC_ERR_VERIFY, "verify_energy failed for %u walker(s) (%u in total); they are halted (sadmc_get_walker(...).status)", new_ver, ver);
+    if (new_win)
+      return fail(SADMC_ERR_WINDOW, "%u walker(s) left the device bin window [bin_window_lo, bin_window_hi) and are halted (%u in total): widen the window",
+                  new_win, win);
+  }
+  return 0;
+}
+int sadmc_num_halted(sadmc_engine* e, uint64_t* left_window, uint64_t* failed_verify) {
+  if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  CK(cudaStreamSynchronize(e->stream));
+  if (left_window) *left_window = e->h_halted ? e->h_halted[0] : 0;
+  if (failed_verify) *failed_verify = e->h_halted ? e->h_halted[1] : 0;
   return 0;
 }
 int sadmc_run(sadmc_engine* e, uint64_t n_moves) {
@@ -637,6 +665,21 @@ int sadmc_num_accepted_moves(sadmc_engine* e, uint64_t* accepted_sum) {
   uint64_t s = 0;
   for (auto& r : v) s += r.accepted;
   *accepted_sum = s;
+  return 0;
+}
+
+int sadmc_accepted_moves_range(sadmc_engine* e, uint64_t* min_accepted, uint64_t* max_accepted) {
+  if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  std::vector<WalkerRec> v;
+  int rc = fetch_walkers(e, v);
+  if (rc) return rc;
+  uint64_t lo = ~0ull, hi = 0;
+  for (auto& r : v) {
+    if (r.accepted < lo) lo = r.accepted;
+    if (r.accepted > hi) hi = r.accepted;
+  }
+  if (min_accepted) *min_accepted = lo;
+  if (max_accepted) *max_accepted = hi;
   return 0;
 }
 
@@ -976,27 +1019,38 @@ int sadmc_cell_box(sadmc_engine* e, double box_diagonal[3], double* r_cutoff) {
 }
 
 // ---- merge for reporting -------------------------------------------------------
-int sadmc_fold_select(sadmc_engine* e, uint32_t first_walker, uint32_t walker_stride, int sad_range_only) {
+int sadmc_fold_select_ex(sadmc_engine* e, uint32_t first_walker, uint32_t walker_stride, uint32_t walker_count, int sad_range_only) {
   if (!e) return fail(SADMC_ERR_INVALID, "null engine");
   if (walker_stride == 0 || first_walker >= e->P.n_walkers) return fail(SADMC_ERR_INVALID, "fold selection (%u, %u) holds no walker", first_walker, walker_stride);
+  if (sad_range_only < 0 || sad_range_only > 2) return fail(SADMC_ERR_INVALID, "sad_range_only must be 0, 1 or 2");
   e->fold_sel.first = first_walker;
   e->fold_sel.stride = walker_stride;
-  e->fold_sel.sad_range_only = sad_range_only ? 1 : 0;
+  e->fold_sel.count = walker_count;
+  e->fold_sel.sad_range_only = sad_range_only;
   return 0;
 }
-int sadmc_fold_device(sadmc_engine* e, void* d_histogram, void* d_energy_total, void* d_energy_squared_total, void* d_lnw_sum,
-                      void* d_lnw_sq_sum, void* d_lnw_count) {
+int sadmc_fold_select(sadmc_engine* e, uint32_t first_walker, uint32_t walker_stride, int sad_range_only) {
+  return sadmc_fold_select_ex(e, first_walker, walker_stride, 0u, sad_range_only);
+}
+static int fold_launch(sadmc_engine* e, void* d_histogram, void* d_energy_total, void* d_energy_squared_total, void* d_lnw_sum,
+                       void* d_lnw_sq_sum, void* d_lnw_count, double* d_packed) {
   if (!e) return fail(SADMC_ERR_INVALID, "null engine");
   CK(cudaSetDevice(e->cfg.device));
-  if (!e->d_wmax) {
-    int rc = dev_alloc(e, (void**)&e->d_wmax, (size_t)e->P.n_walkers * 8, false);
-    if (rc) return rc;
-  }
   const FoldSel sel = e->fold_sel;
-  const uint32_t n_sel = sel.first < e->P.n_walkers ? (e->P.n_walkers - sel.first + sel.stride - 1) / sel.stride : 0;
+  uint32_t n_sel = sel.first < e->P.n_walkers ? (e->P.n_walkers - sel.first + sel.stride - 1) / sel.stride : 0;
+  if (sel.count && sel.count < n_sel) n_sel = sel.count;
   if (n_sel == 0) return fail(SADMC_ERR_INVALID, "fold selection holds no walker");
-  walker_max_lnw_kernel<<<n_sel, 256, 0, e->stream>>>(e->P, e->d_wmax, sel);
-  CK(cudaGetLastError());
+  const double* wmax = nullptr; // one pass: the walkers' running maxima (fold_kernels.cuh)
+  if (sel.sad_range_only != 0) {
+    if (!e->d_wmax) {
+      int rc = dev_alloc(e, (void**)&e->d_wmax, (size_t)e->P.n_walkers * 8, false);
+      if (rc) return rc;
+    }
+    walker_max_lnw_kernel<<<n_sel, 256, 0, e->stream>>>(e->P, e->d_wmax, sel);
+    CK(cudaGetLastError());
+    e->launches++;
+    wmax = e->d_wmax;
+  }
   // chunks of walkers so that the grid covers the chip several times over (148 SMs x 8 blocks)
   const uint32_t nbx = (e->P.cap + 255) / 256;
   uint32_t n_chunks = (1184 + nbx - 1) / nbx;
@@ -1011,14 +1065,22 @@ int sadmc_fold_device(sadmc_engine* e, void* d_histogram, void* d_energy_total, 
     if (rc) return rc;
     e->fold_part_bytes = part_bytes;
   }
-  fold_partial_kernel<<<dim3(nbx, n_chunks), 256, 0, e->stream>>>(e->P, e->d_wmax, e->d_fold_part, sel, n_sel, per_chunk);
+  fold_partial_kernel<<<dim3(nbx, n_chunks), 256, 0, e->stream>>>(e->P, wmax, e->d_fold_part, sel, n_sel, per_chunk);
   CK(cudaGetLastError());
   fold_final_kernel<<<nbx, 256, 0, e->stream>>>(e->P, e->d_fold_part, n_chunks, (unsigned long long*)d_histogram, (double*)d_energy_total,
                                                (double*)d_energy_squared_total, (double*)d_lnw_sum, (double*)d_lnw_sq_sum,
-                                               (unsigned long long*)d_lnw_count);
+                                               (unsigned long long*)d_lnw_count, d_packed);
   CK(cudaGetLastError());
-  e->launches += 3;
+  e->launches += 2;
   return 0;
+}
+int sadmc_fold_device(sadmc_engine* e, void* d_histogram, void* d_energy_total, void* d_energy_squared_total, void* d_lnw_sum,
+                      void* d_lnw_sq_sum, void* d_lnw_count) {
+  return fold_launch(e, d_histogram, d_energy_total, d_energy_squared_total, d_lnw_sum, d_lnw_sq_sum, d_lnw_count, nullptr);
+}
+int sadmc_fold_packed_device(sadmc_engine* e, void* d_packed) {
+  if (!d_packed) return fail(SADMC_ERR_INVALID, "null argument");
+  return fold_launch(e, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (double*)d_packed);
 }
 int sadmc_fold(sadmc_engine* e, uint64_t* histogram, double* energy_total, double* energy_squared_total, double* lnw_sum,
                double* lnw_sq_sum, uint64_t* lnw_count) {
@@ -1069,6 +1131,12 @@ int sadmc_sys_plan_move(sadmc_engine* e, uint32_t w, double mean_distance, int* 
     *some = o.some;
     *e_new = o.value;
   }
+  return rc;
+}
+int sadmc_sys_randomize(sadmc_engine* e, uint32_t w, double* energy) {
+  ShimOut o;
+  int rc = run_shim(e, w, OP_RANDOMIZE, 0, &o);
+  if (!rc && energy) *energy = o.value;
   return rc;
 }
 int sadmc_sys_confirm(sadmc_engine* e, uint32_t w) {

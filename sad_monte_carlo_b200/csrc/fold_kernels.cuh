@@ -10,17 +10,33 @@ namespace sadmc {
 // subtracting that walker's maximum lnw (plotting/parse-binning.py:169) before
 // it is summed; bins a walker never visited do not contribute to the lnw sums.
 //
-// Selection (sadmc_fold_select): walkers first, first + stride, ... take part (interleaved groups give
-// ensemble error bars); with sad_range_only a SAD walker contributes ln w only for the bins inside its own
-// [too_lo, too_hi] -- the part of ln w that SAD defines (plotting/parse-binning.py:150-164 replaces the rest).
+// Selection (sadmc_fold_select / sadmc_fold_select_ex): walkers first, first + stride, ... (at most `count` of them,
+// 0 = to the end) take part: interleaved groups give ensemble error bars, contiguous blocks are the shards of a
+// multi-GPU run.  sad_range_only: 1 = a SAD walker contributes ln w only for the bins inside its own [too_lo, too_hi] --
+// the part of ln w that SAD defines (plotting/parse-binning.py:150-164 replaces the rest); 2 = only the bins strictly
+// inside: too_lo / too_hi are bin centres and `update_weights` reverts the increment for energies outside the range
+// (energy.rs:535-538), so the two end bins receive the increments of only half of their visits.
+//
+// Alignment constant of a walker: its largest ln w over the bins that count.  Without a range restriction that is
+// the walker's running maximum max_S (energy.rs:950-953, kept by the move kernel also when the round-trip diagnostics
+// are switched off): ln w of a bin never decreases and a SAD range extension only writes values that exist already,
+// so the merge is ONE pass over the records.  With a range restriction the maximum over the restricted set is taken
+// by walker_max_lnw_kernel first.
 struct FoldSel {
-  uint32_t first, stride;
+  uint32_t first, stride, count;
   int sad_range_only;
 };
+__device__ __forceinline__ void fold_range(const WalkerRec& r, const FoldSel s, int& ilo, int& ihi) {
+  const bool ranged = s.sad_range_only != 0 && r.method == SADMC_METHOD_SAD;
+  const int shrink = s.sad_range_only == 2 ? 1 : 0;
+  ilo = ranged ? r.ilo + shrink : r.lo;
+  ihi = ranged ? r.ihi - shrink : r.lo + r.len - 1;
+}
 __device__ __forceinline__ bool fold_lnw_counts(const WalkerRec& r, const BinLo& b, int j, const FoldSel s) {
   if (b.hist == 0) return false;
-  if (s.sad_range_only && r.method == SADMC_METHOD_SAD) return j >= r.ilo && j <= r.ihi;
-  return true;
+  int ilo, ihi;
+  fold_range(r, s, ilo, ihi);
+  return j >= ilo && j <= ihi;
 }
 __global__ void __launch_bounds__(256) walker_max_lnw_kernel(const DevParams P, double* wmax, const FoldSel sel) {
   const uint32_t w = sel.first + blockIdx.x * sel.stride;
@@ -67,10 +83,8 @@ __global__ void __launch_bounds__(256) fold_partial_kernel(const DevParams P, co
       FoldMeta m;
       m.lo = r.lo;
       m.end = r.lo + r.len;
-      const bool ranged = sel.sad_range_only && r.method == SADMC_METHOD_SAD;
-      m.ilo = ranged ? r.ilo : m.lo;
-      m.ihi = ranged ? r.ihi : m.end - 1;
-      m.wmax = wmax[w];
+      fold_range(r, sel, m.ilo, m.ihi);
+      m.wmax = wmax ? wmax[w] : r.max_S; // one pass: the walker's running maximum (see above)
       meta[threadIdx.x] = m;
     }
     __syncthreads();
@@ -111,9 +125,13 @@ __global__ void __launch_bounds__(256) fold_partial_kernel(const DevParams P, co
   p[(size_t)5 * P.cap] = __longlong_as_double((long long)cnt);
 }
 
+// `packed` != nullptr: everything as ONE f64 buffer [7][cap] for a single collective -- histogram as two exact halves
+// (h >> 32, h & 0xffffffff: their sums over ranks stay below 2^53), lnw_count, energy_total, energy_squared_total,
+// lnw_sum, lnw_sq_sum (parallel.py recombines the histogram in integer arithmetic).
+constexpr int FOLD_PACKED_FIELDS = 7;
 __global__ void __launch_bounds__(256) fold_final_kernel(const DevParams P, const double* partial, uint32_t n_chunks, unsigned long long* histogram,
                                                         double* energy_total, double* energy_squared_total, double* lnw_sum, double* lnw_sq_sum,
-                                                        unsigned long long* lnw_count) {
+                                                        unsigned long long* lnw_count, double* packed) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= P.cap) return;
   unsigned long long h = 0, cnt = 0;
@@ -133,6 +151,16 @@ __global__ void __launch_bounds__(256) fold_final_kernel(const DevParams P, cons
   if (lnw_sum) lnw_sum[j] = ls;
   if (lnw_sq_sum) lnw_sq_sum[j] = lq;
   if (lnw_count) lnw_count[j] = cnt;
+  if (packed) {
+    const size_t n = P.cap;
+    packed[j] = (double)(h >> 32);
+    packed[n + j] = (double)(h & 0xffffffffull);
+    packed[2 * n + j] = (double)cnt;
+    packed[3 * n + j] = et;
+    packed[4 * n + j] = e2;
+    packed[5 * n + j] = ls;
+    packed[6 * n + j] = lq;
+  }
 }
 
 } // namespace sadmc

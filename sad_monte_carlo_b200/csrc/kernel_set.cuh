@@ -10,7 +10,7 @@
 namespace sadmc {
 
 // trait-shaped single-walker shims (src/system/mod.rs:54-120)
-enum SysOp { OP_ENERGY = 0, OP_COMPUTE_ENERGY = 1, OP_PLAN_MOVE = 2, OP_CONFIRM = 3, OP_VERIFY = 4 };
+enum SysOp { OP_ENERGY = 0, OP_COMPUTE_ENERGY = 1, OP_PLAN_MOVE = 2, OP_CONFIRM = 3, OP_VERIFY = 4, OP_RANDOMIZE = 5 };
 
 struct ShimOut {
   double value;

@@ -34,6 +34,17 @@ struct HasHelpers<S, decltype((void)S::HELPERS)> {
   static constexpr bool value = S::HELPERS;
 };
 
+// Systems that override `System::verify_energy` (lj.rs:249-261, wca.rs:237-251, optsquare.rs:199-201) declare
+// VERIFIES; for the others the trait default is a no-op (system/mod.rs:85) and the cadence check compiles away.
+template <class S, class = void>
+struct HasVerify {
+  static constexpr bool value = false;
+};
+template <class S>
+struct HasVerify<S, decltype((void)S::VERIFIES)> {
+  static constexpr bool value = S::VERIFIES;
+};
+
 template <int G>
 __device__ __forceinline__ unsigned group_mask() {
   if (G >= 32) return 0xffffffffu;
@@ -66,6 +77,7 @@ __device__ void first_bin(const DevParams& P, uint32_t w, WalkerRec& r, double e
   if (lo < 0 || lo >= (long long)P.cap || !(e0 == e0)) {
     r.lo = 0;
     r.status = SADMC_ERR_WINDOW;
+    atomicAdd(&P.halted[0], 1u);
     return;
   }
   r.lo = (int)lo;
@@ -195,9 +207,28 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
   constexpr bool PREDRAW = HasPredraw<Sys>::value;
   PreDraw pre; // the draws of the coming proposal when pre.ok, evaluated during the previous move
   pre.ok = false;
+  // energy.rs:907-911: `if moves % (len^2 * 1000) == 0 { system.verify_energy() }`.  The next multiple is kept and
+  // recomputed only when the number of bins changes, so a move pays one compare instead of a 64-bit modulo.
+  constexpr bool VERIFIES = HasVerify<Sys>::value;
+  int v_len = -1;
+  unsigned long long v_period = 0, v_at = 0;
 #pragma unroll 1
   for (unsigned long long m = 0; m < n_moves; m++) {
     moves += 1; // energy.rs:905
+    if constexpr (VERIFIES) {
+      if (bk.len != v_len) {
+        v_len = bk.len;
+        v_period = (unsigned long long)v_len * (unsigned long long)v_len * 1000ull;
+        v_at = ((moves - 1) / v_period + 1) * v_period; // smallest multiple >= moves
+      }
+      if (moves == v_at) {
+        v_at += v_period;
+        if (!halted && !sys.verify_energy()) { // the reference panics here (lj.rs:259, wca.rs:248, optsquare.rs:200)
+          bk.status = SADMC_ERR_VERIFY;
+          halted = true;
+        }
+      }
+    }
     const double e1 = sys.energy();
     const int i1 = bk.ci;
     const double recent_scale = recent_next;
@@ -335,6 +366,7 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
   }
   if (ghost) return;
   if (wr.status != 0) return; // was halted before this launch: leave its state alone
+  if (bk.status != 0 && lane == 0) atomicAdd(&P.halted[bk.status == SADMC_ERR_VERIFY ? 1 : 0], 1u); // surfaced by sadmc_sync
   bk.store(wr);
   sys.store(P, w, wr, lane == 0);
   if (lane == 0) {
@@ -378,6 +410,15 @@ __global__ void __launch_bounds__(Sys::BLOCK) shim_kernel(const DevParams P, uin
       }
       break;
     }
+    case OP_RANDOMIZE: // System::randomize (system/mod.rs:59), driven by the walker's own generator
+      o.value = sys.randomize(rng);
+      sys.store(P, w, wr, lane == 0);
+      if (lane == 0) {
+        wr.s0 = rng.s0;
+        wr.s1 = rng.s1;
+        pending[0] = 0.0;
+      }
+      break;
     case OP_CONFIRM:
       if (sys.set_pending(pending)) sys.confirm();
       sys.store(P, w, wr, lane == 0);

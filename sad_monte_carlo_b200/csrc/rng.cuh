@@ -58,7 +58,9 @@ struct Rng {
     for (;;) {
       const double res = (f12() - 1.0) * scale + low;
       if (res < high) return res;
-      scale = sadmc_bits_f64(sadmc_f64_bits(scale) - 1);
+      // the scale shrinks only when high - low overflowed (rand 0.7.3 `decrease_masked(!scale.finite_mask())`);
+      // a finite scale draws again
+      if (!(fabs(scale) <= 1.7976931348623157e308)) scale = sadmc_bits_f64(sadmc_f64_bits(scale) - 1);
     }
   }
   __host__ __device__ __forceinline__ double open01() { return f12() - (1.0 - 2.220446049250313e-16 / 2.0); }

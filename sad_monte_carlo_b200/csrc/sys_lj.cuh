@@ -28,6 +28,7 @@ struct LjSys {
   static constexpr int BLOCK = 128;
   static constexpr int MIN_BLOCKS = 4;
   static constexpr bool COOP = false;
+  static constexpr bool VERIFIES = true; // overrides System::verify_energy: run at the cadence of energy.rs:907-911
   __device__ __forceinline__ void set_cooperative(bool) {}
   __device__ __forceinline__ void finish_move() {}
   double px[A], py[A], pz[A];

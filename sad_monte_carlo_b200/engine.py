@@ -98,6 +98,18 @@ class WalkerEngine:
         self._check(self.L.sadmc_num_accepted_moves(self.h, C.byref(n)))
         return n.value
 
+    def accepted_moves_range(self):
+        """(min, max) of the per-walker accepted-move counts."""
+        lo, hi = C.c_uint64(), C.c_uint64()
+        self._check(self.L.sadmc_accepted_moves_range(self.h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def num_halted(self):
+        """(left the bin window, failed verify_energy) walker counts since creation."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self.L.sadmc_num_halted(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def walker(self, w=0) -> WalkerState:
         s = WalkerState()
         self._check(self.L.sadmc_get_walker(self.h, w, C.byref(s)))
@@ -179,10 +191,11 @@ class WalkerEngine:
         self._check(self.L.sadmc_cell_box(self.h, box, C.byref(rc)))
         return [box[0], box[1], box[2]], rc.value
 
-    def fold_select(self, first_walker=0, walker_stride=1, sad_range_only=False):
-        """Which walkers the following folds merge (interleaved groups: ensemble error bars) and whether SAD
-        walkers contribute ln w only inside their own [too_lo, too_hi]."""
-        self._check(self.L.sadmc_fold_select(self.h, first_walker, walker_stride, 1 if sad_range_only else 0))
+    def fold_select(self, first_walker=0, walker_stride=1, sad_range_only=False, walker_count=0):
+        """Which walkers the following folds merge (interleaved groups: ensemble error bars; stride 1 + walker_count: a
+        contiguous shard) and whether SAD walkers contribute ln w only inside their own [too_lo, too_hi]
+        (True / 1) or only strictly inside it (2: without the two half-updated end bins)."""
+        self._check(self.L.sadmc_fold_select_ex(self.h, first_walker, walker_stride, walker_count, int(sad_range_only)))
 
     def fold(self):
         """Window-aligned sums over the local walkers (device fold kernel), as host arrays."""
@@ -198,7 +211,17 @@ class WalkerEngine:
         """Same, into caller-owned DEVICE buffers given as raw pointers (e.g. torch tensors' data_ptr())."""
         self._check(self.L.sadmc_fold_device(self.h, *[C.c_void_p(p) for p in (hist, etot, e2tot, lnw_sum, lnw_sq, lnw_cnt)]))
 
+    def fold_packed_device(self, packed):
+        """The fold as one DEVICE buffer of 7 x nbins doubles (raw pointer), for a single collective."""
+        self._check(self.L.sadmc_fold_packed_device(self.h, C.c_void_p(packed)))
+
     # -- trait-shaped shims (src/system/mod.rs:54-120) -------------------------
+    def randomize(self, w=0):
+        """System::randomize driven by walker w's generator; returns the new energy."""
+        e = C.c_double()
+        self._check(self.L.sadmc_sys_randomize(self.h, w, C.byref(e)))
+        return e.value
+
     def energy(self, w=0):
         e = C.c_double()
         self._check(self.L.sadmc_sys_energy(self.h, w, C.byref(e)))

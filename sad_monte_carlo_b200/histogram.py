@@ -16,8 +16,11 @@ energy.rs:899-902), `--resume-from FILE` continues a checkpoint as it is, the ru
 What is added for the GPU: `--num-walkers W` independent walkers (walker w is the reference run with `--seed
 seed+w`; with W > 1 every walker gets its own file `name-w000017.yaml`), `--gpu-device`, `--bin-window-lo/-hi`
 (the device keeps a fixed bin window per walker), `--lanes-per-walker`, `--fast-math` (LJ: tolerance tier, <= 1e-12
-relative per move), `--checkpoint-walkers K` (write only the first K walkers), `--dry-run` (print the parsed
-configuration as JSON and stop: needs no GPU).  `--num-threads` is accepted and ignored, as `EnergyMC` ignores rayon.
+relative per move), `--checkpoint-walkers K` (write only the first K walkers: such a set is marked `name.partial` and
+cannot be resumed), `--dry-run` (print the parsed configuration as JSON and stop: needs no GPU).  `--num-threads` is
+accepted and ignored, as `EnergyMC` ignores rayon.  With W > 1 the per-run quantities of the reference are per-walker
+quantities: `--max-independent-samples S` ends the run when EVERY walker has accepted S moves, and the progress line
+reports the mean number of accepted moves per walker.  A walker that leaves the bin window ends the run with an error.
 """
 import json
 import math
@@ -413,7 +416,10 @@ def main(argv=None, out=print):
         path = rank_path(flags["resume-from"], rank, world)
         if os.path.splitext(path)[1].lstrip(".") not in ("yaml", "json", "cbor"):
             raise UsageError("I don't know how to read file %r" % path)
-        doc0 = checkpoint.load(checkpoint.walker_path(path, 0, n_walkers))
+        try:
+            doc0 = checkpoint.check_resumable(None, path, n_walkers)
+        except ValueError as ex:
+            raise UsageError(str(ex))
         over = {k: flags[f] for f, k in (("bin-window-lo", "bin_window_lo"), ("bin-window-hi", "bin_window_hi"), ("gpu-device", "device")) if f in flags}
         cfg = place(checkpoint.config_from_document(doc0, n_walkers=n_walkers, **over))
         save_as = doc0.get("save_as", path) if n_walkers == 1 else path
@@ -428,17 +434,32 @@ def main(argv=None, out=print):
         engine = checkpoint.resume(cfg, path)
         out("Resuming from file %r" % path)
         movie_state = doc0.get("movies")
+        resumed = True
     else:
         cfg = place(config_from_flags(flags))
         save_as = rank_path(flags.get("save-as", "resume.yaml"), rank, world)  # mc/mod.rs:88
         if os.path.splitext(save_as)[1].lstrip(".") not in ("yaml", "json", "cbor"):
             raise UsageError("I don't know how to create file %r" % save_as)  # mc/mod.rs:118
         first = checkpoint.walker_path(save_as, 0, n_walkers)
-        resuming = "save-as" in flags and os.path.exists(first)
+        # Every rank takes the same decision, from the files of ALL ranks (one node, one file system): a run resumes
+        # when some rank has a checkpoint, and then every rank's set must be complete and written for this command line.
+        all_sets = [rank_path(flags.get("save-as", "resume.yaml"), r, world) for r in range(world)]
+        resuming = "save-as" in flags and any(
+            os.path.exists(checkpoint.walker_path(p, 0, n_walkers)) or os.path.exists(os.path.splitext(p)[0] + ".partial") for p in all_sets)
+        if resuming:
+            if "checkpoint-walkers" in flags and flags["checkpoint-walkers"] < n_walkers:
+                raise UsageError("--checkpoint-walkers %d writes a partial set that cannot be resumed; %s exists: remove it or "
+                                 "drop --checkpoint-walkers" % (flags["checkpoint-walkers"], first))
+            try:
+                for p in all_sets:
+                    checkpoint.check_resumable(cfg, p, n_walkers)
+            except ValueError as ex:
+                raise UsageError(str(ex))
         if flags.get("dry-run"):
             out(json.dumps({"config": config_summary(cfg), "plugins": pp, "save_as": save_as, "resuming": resuming}))
             return 0
         movie_state = None
+        resumed = resuming
         if resuming:  # mc/mod.rs:70-84, then update_from_params (energy.rs:899-902): report + save come from the flags
             engine = checkpoint.resume(cfg, save_as)
             out("Resuming from file %r" % save_as)
@@ -447,8 +468,9 @@ def main(argv=None, out=print):
             from .engine import WalkerEngine
             engine = WalkerEngine(cfg)
 
-    report = plugins.Report(max_iter=pp["max_iter"], max_independent_samples=pp["max_independent_samples"], quiet=pp["quiet"], out=out)
-    save = plugins.Save(save_time_hours=pp["save_time"])
+    report = plugins.Report(max_iter=pp["max_iter"], max_independent_samples=pp["max_independent_samples"], quiet=pp["quiet"], out=out,
+                            resumed=resumed)
+    save = plugins.Save(save_time_hours=pp["save_time"], resumed=resumed)
     movies = plugins.Movie(movie_time=pp["movie_time"])
     if movie_state is not None:
         movies.restore(movie_state)

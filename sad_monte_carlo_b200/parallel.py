@@ -4,8 +4,8 @@ Every walker is a complete `EnergyMC` (reference src/mc/energy.rs:167-210: own s
 the hot path shards with no data-path collective: rank r of W holds the contiguous block of global walkers
 [offset, offset + n_local) and walker w is seeded `seed + w` -- results do not depend on the GPU count.
 Only the merged report (histogram, energy moments, aligned ln w sums) crosses NVLink: a device fold
-(sadmc_fold_device) straight into torch tensors followed by `torch.distributed.all_reduce` (NCCL on GPUs, gloo in
-the CPU tests), at reporting intervals.
+(sadmc_fold_packed_device) straight into one torch tensor followed by ONE `all_gather_into_tensor` (NCCL on GPUs, gloo
+in the CPU tests) and a rank-ordered sum, at reporting intervals.
 """
 import ctypes as C
 
@@ -37,13 +37,43 @@ def shard_config(cfg, n_walkers_total, rank, world, device=None):
     return local
 
 
-def all_reduce_merged(tensors, group=None):
-    """Sum the per-rank fold tensors in place over the process group (NCCL all-reduce over NVLink on GPUs)."""
+PACKED_FIELDS = 7  # sadmc_fold_packed_device: histogram >> 32, histogram & 0xffffffff, lnw_count, then the four f64 sums
+
+
+def merge_packed(packed, group=None):
+    """ONE collective for the whole report: every rank's packed fold [7, nbins] (f64) is all-gathered and the shards
+    are added in RANK ORDER on every rank.
+
+    The integer fields travel as exact doubles (32-bit halves of the histogram, walker counts), so their sums are
+    exact; the floating-point sums are added shard by shard in a fixed order, so the merged report does not depend on
+    NCCL's reduction tree and is bit-identical to folding the same shards one after the other on a single GPU
+    (tests/test_gpu_merge.py).  The payload is 56 bytes per bin and rank (LJ31: 0.75 MB per rank)."""
+    import torch
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        for k in MERGED_KEYS:
-            dist.all_reduce(tensors[k], op=dist.ReduceOp.SUM, group=group)
-    return tensors
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return packed
+    world = dist.get_world_size(group)
+    # concatenated along dim 0 (the form every backend accepts), then viewed as [world, 7, nbins]
+    gathered = torch.empty((world * packed.shape[0],) + tuple(packed.shape[1:]), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(gathered, packed.contiguous(), group=group)
+    return sum_shards(gathered.view((world,) + tuple(packed.shape)))
+
+
+def sum_shards(gathered):
+    """Shard-ordered sum of [n_shards, 7, nbins]."""
+    acc = gathered[0].clone()
+    for r in range(1, gathered.shape[0]):
+        acc += gathered[r]
+    return acc
+
+
+def unpack_merged(packed):
+    """Packed [7, nbins] f64 tensor (or array) -> the host arrays of MERGED_KEYS."""
+    p = packed.detach().cpu().numpy() if hasattr(packed, "detach") else np.asarray(packed)
+    hi = p[0].astype(np.uint64)
+    lo = p[1].astype(np.uint64)
+    return {"histogram": (hi << np.uint64(32)) + lo, "lnw_count": p[2].astype(np.uint64), "energy_total": p[3].copy(),
+            "energy_squared_total": p[4].copy(), "lnw_sum": p[5].copy(), "lnw_sq_sum": p[6].copy()}
 
 
 class ShardedEngine:
@@ -63,24 +93,23 @@ class ShardedEngine:
         self.engine = WalkerEngine(local)
         self.device = torch.device("cuda", local.device)
         _, _, nb = self.engine.window()
-        self._t = {k: torch.zeros(nb, dtype=torch.int64 if k in ("histogram", "lnw_count") else torch.float64,
-                                  device=self.device) for k in MERGED_KEYS}
+        self._packed = torch.zeros((PACKED_FIELDS, nb), dtype=torch.float64, device=self.device)
 
     def run(self, n_moves):
         self.engine.run(n_moves)
 
-    def merged(self):
-        """Fold the local walkers on the device, all-reduce across ranks; host arrays, identical on all ranks."""
+    def merged_device(self):
+        """Fold the local walkers on the device (one pass over the bin records) and merge the ranks with one
+        all-gather; returns the packed [7, nbins] tensor, identical on all ranks."""
         import torch
-        t = self._t
-        self.engine.fold_device(*[t[k].data_ptr() for k in MERGED_KEYS])
+        self.engine.fold_packed_device(self._packed.data_ptr())
         self.engine.sync()
         torch.cuda.synchronize(self.device)
-        all_reduce_merged(t, self.group)
-        out = {k: t[k].cpu().numpy() for k in MERGED_KEYS}
-        out["histogram"] = out["histogram"].astype(np.uint64)
-        out["lnw_count"] = out["lnw_count"].astype(np.uint64)
-        return out
+        return merge_packed(self._packed, self.group)
+
+    def merged(self):
+        """The merged report as host arrays (MERGED_KEYS), identical on all ranks."""
+        return unpack_merged(self.merged_device())
 
     def close(self):
         self.engine.close()

@@ -55,11 +55,14 @@ class Plugin:
 class Report(Plugin):
     """plugin.rs:149-310"""
 
-    def __init__(self, max_iter=None, max_independent_samples=None, quiet=True, out=print):
+    def __init__(self, max_iter=None, max_independent_samples=None, quiet=True, out=print, resumed=False, clock=time.monotonic):
         self.max_iter = total_moves(max_iter) if max_iter is not None else NEVER
         self.max_independent_samples = max_independent_samples
         self.quiet = quiet
-        self.start = (time.monotonic(), 0)
+        self.clock = clock
+        # `start` is #[serde(skip, default)] (plugin.rs:153-155): a deserialised Report has None and takes (now, moves)
+        # at its first log instead of printing (262-264), so the time per move is measured over THIS process only
+        self.start = None if resumed else (clock(), 0)
         self.out = out
 
     def document(self):
@@ -83,8 +86,11 @@ class Report(Plugin):
         if self.quiet:
             return
         moves = mc.num_moves()
+        if self.start is None:  # plugin.rs:262-264
+            self.start = (self.clock(), moves)
+            return
         t0, it0 = self.start
-        runtime = time.monotonic() - t0
+        runtime = self.clock() - t0
         per_move = runtime / max(1, moves - it0)
         if self.max_iter[0] == "TotalMoves":
             mx = self.max_iter[1]
@@ -94,7 +100,7 @@ class Report(Plugin):
         else:
             self.out("[%.3g] after %.0f s (%.3g us per move)" % (moves, runtime, per_move * 1e6))
 
-    def save(self, mc):  # 295-309
+    def save(self, mc):  # 295-309; with many walkers: the mean per walker (what one reference process would print)
         if self.quiet:
             return
         acc, moves = mc.num_accepted_moves(), mc.num_moves()
@@ -105,10 +111,13 @@ class Save(Plugin):
     """plugin.rs:313-400.  save_time_seconds None: checkpoints at moves 1, 2, 4, 8, ...; otherwise the schedule adapts
     to the measured time per move so that a checkpoint happens about every save_time_seconds."""
 
-    def __init__(self, save_time_hours=1.0, clock=time.monotonic):
-        self.next_output = 1
+    def __init__(self, save_time_hours=1.0, clock=time.monotonic, resumed=False):
         self.clock = clock
-        self.start = (clock(), 0)
+        # next_output and start are #[serde(skip, default)] (plugin.rs:315-320): a resumed run saves at its first tick
+        # (next_output = 0), takes (now, moves) as its start there and saves next 2^20 moves later (373-376) -- it
+        # never divides this process's run time by the move count of the earlier processes
+        self.next_output = 0 if resumed else 1
+        self.start = None if resumed else (clock(), 0)
         self.save_time_seconds = None if save_time_hours is None else 3600.0 * save_time_hours
 
     def document(self):
@@ -118,6 +127,10 @@ class Save(Plugin):
         if moves < self.next_output:
             return False
         if self.save_time_seconds is not None:
+            if self.start is None:  # plugin.rs:373-376
+                self.start = (self.clock(), moves)
+                self.next_output = moves + (1 << 20)
+                return True
             t0, it0 = self.start
             per_move = (self.clock() - t0) / max(1, moves - it0)
             per_move = max(per_move, 1e-30)
@@ -238,11 +251,14 @@ class EngineMC:
     def num_moves(self):
         return self.engine.num_moves()
 
+    # Every walker is one reference run (`--seed seed + w`), so the per-run quantities the plugins ask for are
+    # per-walker quantities: the progress line shows the mean over the walkers, and --max-independent-samples is
+    # reached when EVERY walker has that many (the slowest walker decides; all walkers make the same number of moves).
     def num_accepted_moves(self):
-        return self.engine.num_accepted_moves()
+        return self.engine.num_accepted_moves() // max(1, self.engine.n_walkers)
 
     def independent_samples(self):  # mc/mod.rs:134-136
-        return self.num_accepted_moves()
+        return self.engine.accepted_moves_range()[0]
 
     def verify_energy(self):  # PluginManager::run calls sys.verify_energy() before logging (plugin.rs:102-103)
         if not self.engine.verify_energy(0):

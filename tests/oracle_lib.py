@@ -48,6 +48,7 @@ def load_oracle():
     L.oracle_sw_compute_energy_slowly.argtypes = [C.c_void_p]
     L.oracle_sys_plan_move.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_int), f64p]
     L.oracle_sys_confirm.argtypes = [C.c_void_p]
+    L.oracle_sys_randomize.argtypes = [C.c_void_p, f64p]
     L.oracle_sys_verify_energy.argtypes = [C.c_void_p]
     L.oracle_rng_seed.argtypes = [C.c_uint64, u64p]
     L.oracle_rng_stream.argtypes = [u64p, C.c_int, C.c_uint64, C.c_double, C.c_double, C.c_uint64, u64p]
@@ -146,6 +147,12 @@ class OracleMC:
 
     def verify_energy(self):
         return self.L.oracle_sys_verify_energy(self.h) == 0
+
+    def randomize(self):
+        e = C.c_double(0)
+        if self.L.oracle_sys_randomize(self.h, C.byref(e)) != 0:
+            raise RuntimeError("oracle randomize: " + self.L.oracle_last_error().decode())
+        return e.value
 
 
 def rng_stream(state, kind, count, n_arg=0, lo=0.0, hi=1.0):

@@ -8,6 +8,8 @@ from sad_monte_carlo_b200 import WalkerEngine, make_config, _abi
 from tests.gpu_common import assert_walker_equal, clone_config
 from tests.oracle_lib import OracleMC
 
+from sad_monte_carlo_b200.engine import SadmcError
+
 pytestmark = pytest.mark.gpu
 
 
@@ -126,8 +128,13 @@ def test_fold_equals_sum_over_walkers():
 def test_window_overflow_is_reported_not_clamped():
     cfg = make_config("ising", "sad", N=16, sad_min_T=1.0, n_walkers=8, seed=1, bin_window_lo=-40.0, bin_window_hi=40.0)
     eng = WalkerEngine(cfg)
-    eng.run(20000)
+    with pytest.raises(SadmcError) as ei:  # the run says so at once (the reference would have grown its vectors)
+        eng.run(20000)
+    assert ei.value.code == _abi.ERR_WINDOW and "8 walker(s) left the device bin window" in str(ei.value)
     assert all(eng.walker(w).status == _abi.ERR_WINDOW for w in range(8))
+    assert eng.num_halted() == (8, 0)
+    eng.run(100)  # every halted walker is reported once; the engine stays usable
+    assert eng.num_halted() == (8, 0)
 
 
 def test_trait_shims_match_oracle_move_by_move():

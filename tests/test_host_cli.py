@@ -147,8 +147,11 @@ def test_main_glue_runs_with_a_stand_in_engine(monkeypatch, tmp_path):
         def num_moves(self):
             return self.moves
 
-        def num_accepted_moves(self):
-            return self.moves // 2
+        def num_accepted_moves(self):  # summed over the walkers, as the C ABI reports it
+            return self.n_walkers * (self.moves // 2)
+
+        def accepted_moves_range(self):
+            return self.moves // 2, self.moves // 2
 
         def verify_energy(self, w=0):
             return True

@@ -307,6 +307,52 @@ def test_plugin_schedule_equals_the_python_host(max_iter, movie_time, doubling, 
     assert got == want
 
 
+def test_resumed_run_restarts_its_clock_in_both_hosts(selftest_exe):
+    """plugin.rs:315-320, 373-376: a resumed Save has no start and next_output = 0 -- it saves at its first tick, 2^20 moves
+    later, and from then on about every save_time of THIS process's run time (not of run time / all moves since move 0)."""
+    from sad_monte_carlo_b200 import plugins
+    resumed_at, rate, save_time = 5_000_000_000, 1e6, 1800.0
+    got = subprocess.run([selftest_exe, "resumed", str(resumed_at), repr(rate), repr(save_time), "6"], capture_output=True, text=True, check=True)
+    cpp = [int(l.split()[1]) for l in got.stdout.splitlines()]
+
+    class Clock:
+        t = 0.0
+
+        def __call__(self):
+            return self.t
+
+    class MC:
+        moves = resumed_at
+        saved = []
+
+        def num_moves(self):
+            return self.moves
+
+        def num_accepted_moves(self):
+            return self.moves // 2
+
+        def independent_samples(self):
+            return self.moves // 2
+
+        def verify_energy(self):
+            pass
+
+        def checkpoint(self):
+            self.saved.append(self.moves)
+
+    clock, mc = Clock(), MC()
+    plugs = [plugins.Report(quiet=True, resumed=True, clock=clock), plugins.Save(save_time_hours=save_time / 3600.0, clock=clock, resumed=True)]
+    m = plugins.PluginManager()
+    while len(mc.saved) < 6:
+        n = m.moves_until_next_action()
+        mc.moves += n
+        clock.t += n / rate
+        m.run(mc, plugs, moves_made=n)
+    assert cpp == mc.saved
+    assert cpp[0] == resumed_at + 1 and cpp[1] == resumed_at + 1 + (1 << 20)
+    assert all(abs((b - a) / rate - save_time) < 0.05 * save_time for a, b in zip(cpp[2:], cpp[3:]))
+
+
 @pytest.mark.parametrize("rank,world,local", [(0, 2, 0), (3, 4, 3), (9, 16, 1)])
 def test_one_process_per_gpu_sharding_is_the_same_in_both_hosts(rank, world, local, monkeypatch):
     # torchrun / mpirun export WORLD_SIZE, RANK, LOCAL_RANK: --num-walkers is the total, every rank gets a contiguous block

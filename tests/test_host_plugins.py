@@ -156,3 +156,110 @@ def test_cbor_is_standard_cbor():
     assert enc({"a": 1, "b": [2, 3]}) == bytes.fromhex("a26161016162820203")
     assert enc(18446744073709551615) == bytes.fromhex("1bffffffffffffffff")
     assert checkpoint.loads(bytes.fromhex("f97c00"), "cbor") == np.inf  # half-precision floats decode too
+
+
+# ---- resumed runs: plugin.rs:315-320 (`next_output`, `start` are serde(skip)), 373-376, 262-264 ---------------------
+
+class FakeClock:
+    def __init__(self):
+        self.t = 0.0
+
+    def __call__(self):
+        return self.t
+
+
+def test_resumed_save_measures_time_per_move_over_this_process_only():
+    """A run resumed at 5e9 moves that makes 1e6 moves per second must checkpoint about every save_time, not after
+    another 5e9 moves: the reference restarts its clock at the resume point (start = None -> (now, moves)) and saves
+    again 2^20 moves after the first post-resume save."""
+    clock = FakeClock()
+    resumed_at = 5_000_000_000
+    rate = 1e6  # moves per second of this process
+    mc = FakeMC()
+    mc.moves = resumed_at
+    save = Save(save_time_hours=0.5, clock=clock, resumed=True)
+    report = Report(max_iter=resumed_at + 20_000_000_000, quiet=False, out=lambda s: lines.append(s), resumed=True, clock=clock)
+    lines = []
+    m = PluginManager()
+    for _ in range(40):
+        n = m.moves_until_next_action()
+        mc.run(n)
+        clock.t += n / rate
+        m.run(mc, [report, save])
+        if len(mc.saved) >= 6:
+            break
+    assert mc.saved[0] == resumed_at + 1            # first tick of a resumed run saves (next_output = 0)
+    assert mc.saved[1] == resumed_at + 1 + (1 << 20)  # plugin.rs:375
+    gaps = np.diff(mc.saved[2:])
+    assert len(gaps) >= 2 and np.all(np.abs(gaps / rate - 1800.0) < 0.05 * 1800.0), gaps  # then every half hour
+    # the report's time per move is this process's (1 us), not (run time) / (all moves since move 0)
+    progress = [ln for ln in lines if "per move" in ln]
+    assert progress and all("1 us per move" in ln for ln in progress), lines
+
+
+def test_fresh_save_schedule_is_unchanged():
+    clock = FakeClock()
+    mc = FakeMC()
+    save = Save(save_time_hours=None, clock=clock)
+    drive(mc, [save, Report(max_iter=100)])
+    assert mc.saved[:7] == [1, 2, 4, 8, 16, 32, 64]
+
+
+def test_incomplete_or_partial_checkpoint_sets_are_refused_before_any_engine_exists(tmp_path):
+    base = str(tmp_path / "run.json")
+    for w in (0, 1, 3):  # walker 2 of 4 is missing
+        open(checkpoint.walker_path(base, w, 4), "w").write("{}")
+    with pytest.raises(ValueError) as ei:
+        checkpoint.check_resumable(None, base, 4)
+    assert "incomplete" in str(ei.value) and "1 of 4" in str(ei.value) and "run-w000002.json" in str(ei.value)
+    open(str(tmp_path / "run.partial"), "w").write("2 of 4 walkers\n")
+    with pytest.raises(ValueError) as ei:
+        checkpoint.check_resumable(None, base, 4)
+    assert "--checkpoint-walkers" in str(ei.value) and "2 of 4 walkers" in str(ei.value)
+
+
+def test_checkpoint_set_is_written_all_or_nothing(tmp_path):
+    """A halted walker stops the save before any file is touched; a failure while documents are being staged leaves the
+    previous set in place and no temporaries behind."""
+    class Eng:
+        n_walkers = 3
+        halted = (0, 0)
+        fail_at = None
+
+        def num_halted(self):
+            return self.halted
+
+        def walker(self, w):
+            class S:
+                status = 0
+            return S()
+
+    eng = Eng()
+    base = str(tmp_path / "set.json")
+    real = checkpoint.walker_document
+    try:
+        def fake_document(engine, w, save_as="x", **kw):
+            if engine.fail_at == w:
+                raise RuntimeError("device read failed")
+            return {"moves": engine.moves, "walker": w}
+        checkpoint.walker_document = fake_document
+        eng.moves = 100
+        checkpoint.save(eng, base)
+        first = [open(checkpoint.walker_path(base, w, 3)).read() for w in range(3)]
+        eng.moves, eng.fail_at = 200, 2
+        with pytest.raises(RuntimeError):
+            checkpoint.save(eng, base)
+        assert [open(checkpoint.walker_path(base, w, 3)).read() for w in range(3)] == first  # still the complete old set
+        assert sorted(p.name for p in tmp_path.iterdir()) == ["set-w000000.json", "set-w000001.json", "set-w000002.json"]
+        eng.fail_at, eng.halted = None, (1, 0)
+        with pytest.raises(RuntimeError) as ei:
+            checkpoint.save(eng, base)
+        assert "no checkpoint written" in str(ei.value)
+        assert [open(checkpoint.walker_path(base, w, 3)).read() for w in range(3)] == first
+        eng.halted = (0, 0)
+        checkpoint.save(eng, base, walkers=range(2))
+        assert (tmp_path / "set.partial").read_text() == "2 of 3 walkers\n"
+        checkpoint.save(eng, base)
+        assert not (tmp_path / "set.partial").exists()
+    finally:
+        checkpoint.walker_document = real

@@ -129,6 +129,34 @@ def test_zig_tables_match_generator_and_survey_constants():
     assert np.all(np.diff(X) < 0) and np.all(np.diff(F) > 0)
 
 
+def test_zig_table_header_is_exactly_what_the_generator_writes():
+    """include/sadmc_zig_tables.h is shared by the oracle and the kernels, so no parity test can see an edit to it:
+    this one regenerates the header text from tools/gen_ziggurat_tables.py and compares it byte for byte."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_ziggurat_tables as g
+    with open(os.path.join(ROOT, "include", "sadmc_zig_tables.h")) as f:
+        assert f.read() == g.render()
+
+
+def test_gen_range_f64_redraws_with_the_same_scale():
+    """rand 0.7.3 UniformFloat::sample_single shrinks `scale` only when high - low overflowed; for finite bounds a
+    result that rounds up to `high` is redrawn with the SAME scale.  [1, 1 + 2 ulp) makes that case common:
+    value0_1 * scale + low rounds to `high` for about a quarter of the draws."""
+    lo, hi = 1.0, 1.0 + 2 * 2.220446049250313e-16
+    st = np.array([0xe220a8397b1dcdaf, 0x6e789e6aa1b965f4], np.uint64)
+    s = [int(st[0]), int(st[1])]
+    got = rng_stream(st, 7, 400, lo=lo, hi=hi).view(np.float64)
+    want = []
+    while len(want) < 400:
+        v = _py_next(s) >> 12
+        f = struct.unpack("<d", struct.pack("<Q", v | (1023 << 52)))[0]
+        res = (f - 1.0) * (hi - lo) + lo
+        if res < hi:
+            want.append(res)
+    assert list(got) == want
+    assert (int(st[0]), int(st[1])) == (s[0], s[1])  # the same number of words was consumed
+
+
 def test_standard_normal_moments_and_tail():
     st = np.array([0xe220a8397b1dcdaf, 0x6e789e6aa1b965f4], np.uint64)
     z = rng_stream(st, 4, 2_000_000).view(np.float64)

@@ -9,7 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from sad_monte_carlo_b200 import make_config
-from sad_monte_carlo_b200.parallel import MERGED_KEYS, all_reduce_merged, shard, shard_config
+from sad_monte_carlo_b200.parallel import MERGED_KEYS, PACKED_FIELDS, merge_packed, shard, shard_config, sum_shards, unpack_merged
 
 
 def test_shard_partitions_walkers_exactly():
@@ -47,25 +47,49 @@ def _free_port():
     return p
 
 
+def _packed_for_rank(rank, nb=50):
+    """A synthetic packed fold [7, nb]: histogram halves that need more than 53 bits when recombined, and
+    floating-point sums whose result depends on the order of addition."""
+    rng = np.random.default_rng(rank)
+    hist = rng.integers(0, 2 ** 62, nb, dtype=np.uint64)
+    p = np.zeros((PACKED_FIELDS, nb))
+    p[0] = (hist >> np.uint64(32)).astype(np.float64)
+    p[1] = (hist & np.uint64(0xffffffff)).astype(np.float64)
+    p[2] = rng.integers(0, 75776, nb)
+    p[3:] = rng.standard_normal((4, nb)) * 10.0 ** rng.integers(-8, 8, (4, nb))
+    return p, hist
+
+
 def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    nb = 50
-    rng = np.random.default_rng(rank)
-    t = {k: torch.from_numpy(rng.integers(0, 100, nb)).to(torch.int64 if k in ("histogram", "lnw_count") else torch.float64)
-         for k in MERGED_KEYS}
-    local = {k: v.clone() for k, v in t.items()}
-    all_reduce_merged(t)
-    torch.save({"local": local, "merged": t}, os.path.join(out, "r%d.pt" % rank))
+    p, _ = _packed_for_rank(rank)
+    merged = merge_packed(torch.from_numpy(p))
+    torch.save({"merged": merged}, os.path.join(out, "r%d.pt" % rank))
     dist.destroy_process_group()
 
 
-def test_merged_report_all_reduce_gloo_world2(tmp_path):
-    world = 2
+@pytest.mark.parametrize("world", [2, 3])
+def test_merged_report_one_collective_rank_ordered_gloo(tmp_path, world):
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    res = [torch.load(os.path.join(tmp_path, "r%d.pt" % r)) for r in range(world)]
-    for k in MERGED_KEYS:
-        want = res[0]["local"][k] + res[1]["local"][k]
-        for r in range(world):
-            assert torch.equal(res[r]["merged"][k], want), k
+    res = [torch.load(os.path.join(tmp_path, "r%d.pt" % r))["merged"] for r in range(world)]
+    shards = [_packed_for_rank(r) for r in range(world)]
+    # what a single process computes when it adds the same shards one after the other
+    want = sum_shards(torch.from_numpy(np.stack([p for p, _ in shards])))
+    for r in range(world):
+        assert torch.equal(res[r], want)  # bit-identical on every rank, floating-point sums included
+    m = unpack_merged(res[0])
+    assert set(m) == set(MERGED_KEYS)
+    hist = np.zeros(50, dtype=object)
+    for _, h in shards:
+        hist = hist + h.astype(object)
+    assert [int(x) for x in m["histogram"]] == [int(x) % 2 ** 64 for x in hist]  # exact beyond 2^53
+    assert np.array_equal(m["lnw_count"], sum(p[2] for p, _ in shards).astype(np.uint64))
+
+
+def test_merge_without_process_group_is_the_identity():
+    p, hist = _packed_for_rank(7)
+    t = torch.from_numpy(p)
+    assert merge_packed(t) is t
+    assert np.array_equal(unpack_merged(t)["histogram"], hist)
