@@ -28,9 +28,17 @@ sys.path.insert(0, ROOT)
 
 FLOPS_PER_MOVE = 900.0  # 30 (N - 1) FP64 flops for N = 31 (a divide counted as one flop)
 BYTES_PER_MOVE = 80.0   # 2 lnw reads + RMW of histogram, energy_total, energy_squared_total, lnw
-# dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the move kernel
-# (profiles/r01_lj31_sad_thread_fast_v3.txt: 29.97 GB for 75 776 walkers x 3 000 moves), per move
-NCU_DRAM_BYTES_PER_MOVE = 29.974067e9 / (75776 * 3000)
+TIMED_MOVES_PER_WALKER = 10_000_000  # the timed window covers at least this many moves of every walker
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the move kernel from the `ncu --set full` capture committed under
+    profiles/ (written by tools/ncu_traffic.py from the capture's raw page): bytes per move and what was captured."""
+    p = os.path.join(ROOT, "profiles", "r02_lj31_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
 
 
 def lj31_config(n_walkers, walker_offset=0, device=0, lanes=0, flags=0):
@@ -133,10 +141,12 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         # our arm's config; what this arm actually ran on the CPU is the bounded sample described in cpu_baseline.sample
-        "config": workload_config(args.walkers, args.moves_per_step, lanes_per_walker=args.lanes,
-                                  arithmetic="exact (reference operation order)" if args.exact else "fast-math (<= 1e-12 rel. per move)",
-                                  burn_in_moves=args.burn_in, round_trip_diagnostics=not args.no_round_trips),
+        "config": our_config(args),
         "cpu_baseline": {"value": value, "unit": "moves/s", "cores": threads, "kind": "port", "sample": sample},
+        # what THIS arm ran (the `config` above names the shared workload as the GPU arm runs it)
+        "ran": {"walkers": threads, "moves_per_walker_per_step": per_step, "untimed_moves_per_walker_per_step": 100000,
+                "arithmetic": "reference operation order (oracle/, g++ -O3 -ffp-contract=off)", "host_threads": threads,
+                "round_trip_diagnostics": True, "timed_s": t_total},
         "e2e": {"value": value, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -148,6 +158,16 @@ def workload_config(walkers_per_gpu, moves_per_step, **kw):
          "l2": "inputs larger than L2 (per-walker bin windows: tens of GB)"}
     c.update(kw)
     return c
+
+
+def our_config(args):
+    """The `config` block of the GPU arm (the reference arm repeats it and adds what it ran itself under `ran`)."""
+    return workload_config(args.walkers, args.moves_per_step, lanes_per_walker=args.lanes,
+                           arithmetic="exact (reference operation order)" if args.exact else "fast-math (<= 1e-12 rel. per move)",
+                           burn_in_moves=args.burn_in, round_trip_diagnostics=not args.no_round_trips,
+                           timed_window="moves %d to %d of every walker" % (
+                               args.burn_in + args.warmup * args.moves_per_step,
+                               args.burn_in + (args.warmup + args.steps) * args.moves_per_step))
 
 
 def run_ours(args):
@@ -232,27 +252,26 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = total_moves / float(te.item())
 
-    # ---- reporting-interval collective: device fold + NCCL all-reduce of the merged arrays ----
+    # ---- reporting-interval merge: one-pass device fold into ONE packed buffer + ONE collective (rank-ordered) ----
+    from sad_monte_carlo_b200.parallel import PACKED_FIELDS, merge_packed, unpack_merged
     dev = torch.device("cuda", local)
-    hist = torch.zeros(nb, dtype=torch.int64, device=dev)
-    f64s = [torch.zeros(nb, dtype=torch.float64, device=dev) for _ in range(4)]
-    cnt = torch.zeros(nb, dtype=torch.int64, device=dev)
+    packed = torch.zeros((PACKED_FIELDS, nb), dtype=torch.float64, device=dev)
+    merge_packed(packed)  # warm the communicator
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record(stream)
-    eng.fold_device(hist.data_ptr(), f64s[0].data_ptr(), f64s[1].data_ptr(), f64s[2].data_ptr(), f64s[3].data_ptr(), cnt.data_ptr())
-    if world > 1:
-        for x in [hist, cnt] + f64s:
-            dist.all_reduce(x)
+    eng.fold_packed_device(packed.data_ptr())
+    merged_packed = merge_packed(packed)
     f1.record(stream)
     torch.cuda.synchronize()
     fold_ms = f0.elapsed_time(f1)
     moves_now = eng.num_moves()
-    hist_total = int(hist.sum().item())
-    statuses = sum(1 for w in range(0, W, max(1, W // 64)) if eng.walker(w).status != 0)
+    hist_total = int(unpack_merged(merged_packed)["histogram"].sum())
+    halted = eng.num_halted()
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
+        traffic = measured_traffic()
         fp64 = C.c_double(0.0)
         lib.sadmc_measure_fp64_peak(local, 5, C.byref(fp64))
         per_gpu_moves_s = value / world
@@ -260,9 +279,7 @@ def run_ours(args):
             "metric": "LJ31 SAD MC moves/sec", "value": value, "unit": "moves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(W, args.moves_per_step, lanes_per_walker=args.lanes,
-                                      arithmetic="exact (reference operation order)" if args.exact else "fast-math (<= 1e-12 rel. per move)",
-                                      burn_in_moves=args.burn_in, round_trip_diagnostics=not args.no_round_trips),
+            "config": our_config(args),
             "clocks": clocks, "gpu_launches": int(gpu_launches),
             "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "what": "sadmc_set_systems + sadmc_set_rngs (pinned host) -> sadmc_run -> sadmc_fold + sadmc_get_energies (host)"},
@@ -274,13 +291,15 @@ def run_ours(args):
                          "kernel": "move_kernel<LjThreadSys<%s, 31, %d>, SAD>" % ("exact" if args.exact else "fast", args.lanes), "ms_per_launch": ms_max / args.steps},
             "roofline_hbm": {"bound": "hbm", "achieved": per_gpu_moves_s * BYTES_PER_MOVE / 1e9, "peak": peaks.get("hbm_gbs"),
                              "unit": "GB/s", "frac": per_gpu_moves_s * BYTES_PER_MOVE / 1e9 / peaks.get("hbm_gbs"),
-                             "traffic": NCU_DRAM_BYTES_PER_MOVE * W * args.moves_per_step,
-                             "per_unit": "80 B of bin traffic per move (algorithmic); traffic = DRAM bytes per launch scaled from "
-                                         "the ncu capture in profiles/ (131.8 B per move: 64-byte records, sector granularity)",
+                             "traffic": traffic["dram_bytes_per_move"] * W * args.moves_per_step if traffic else None,
+                             "traffic_source": traffic["source"] if traffic else "no ncu capture committed for this kernel",
+                             "per_unit": "80 B of bin traffic per move (algorithmic: 2 ln w reads + read-modify-write of 4 fields); "
+                                         "traffic = measured DRAM bytes per move of the ncu capture x moves per launch",
                              "peak_source": peak_src},
-            "fold_allreduce_ms": fold_ms,
+            "fold_merge_ms": fold_ms,
+            "fold_merge": "one-pass device fold into one packed buffer + one all-gather, shards added in rank order",
             "checks": {"merged_histogram_total": hist_total, "expected": int(world * W * (moves_now + 1)),
-                       "walkers_halted_in_sample": statuses},
+                       "walkers_halted": {"left_window": halted[0], "failed_verify": halted[1]}},
         }
         if not args.no_cpu_baseline and world == 1:
             try:
@@ -302,8 +321,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--walkers", type=int, default=int(os.environ.get("SADMC_BENCH_WALKERS", 0)),
                     help="walkers per GPU (default: whole waves of resident CTAs: 75 776 = two waves at one lane per walker, 85 248 = three at two)")
-    ap.add_argument("--moves-per-step", type=int, default=int(os.environ.get("SADMC_BENCH_MOVES", 20000)))
-    ap.add_argument("--burn-in", type=int, default=int(os.environ.get("SADMC_BENCH_BURN_IN", 200000)))
+    ap.add_argument("--moves-per-step", type=int, default=int(os.environ.get("SADMC_BENCH_MOVES", 0)),
+                    help="moves per walker and launch (default: so that the K timed steps cover 1e7 moves of every walker)")
+    ap.add_argument("--burn-in", type=int, default=int(os.environ.get("SADMC_BENCH_BURN_IN", 1000000)),
+                    help="un-timed moves per walker before the warm-up steps (BASELINE.md section 3: 1e6)")
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("SADMC_BENCH_LANES", 1)))
     ap.add_argument("--no-round-trips", action="store_true")
     ap.add_argument("--exact", action="store_true", help="reference operation order (bit-exact vs the oracle) instead of fast-math")
@@ -313,6 +334,10 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.steps < 1:
+        args.steps = 1
+    if args.moves_per_step <= 0:
+        args.moves_per_step = -(-TIMED_MOVES_PER_WALKER // args.steps)
     if args.exact and args.lanes != 1:
         args.lanes = 1  # the reference's sequential pair sum cannot be split across lanes
     if args.walkers == 0:

@@ -94,7 +94,9 @@ typedef enum {
 #define SADMC_FLAG_SUM_TREE 2u       /* reserved (oracle only): sum LJ pair terms in the kernel's lane order */
 /* LJ, lanes_per_walker = 1 only: FMA-contracted pair arithmetic with a Newton reciprocal and a
  * warp-cooperative energy recomputation instead of the reference's exact operation order.
- * Per-move energies then agree with the reference to <= 1e-12 relative instead of bit for bit. */
+ * Per-move energies then agree with the reference to <= 1e-12 relative instead of bit for bit.
+ * WCA (lanes_per_walker 4/8/16): the same arithmetic shortcuts, and the whole-system energy is re-summed every
+ * 65 536 accepted moves instead of every ~10 (wca.rs:164-177 with a 6 553.6 times larger error allowance). */
 #define SADMC_FLAG_FAST_MATH 4u
 /* EXPERIMENT, with SADMC_FLAG_FAST_MATH and lanes_per_walker = 1, LJ31 / LJ38 only: a helper warp per bookkeeping warp
  * sums half of the pair loop (csrc/sys_lj_paired.cuh).  Same tolerance tier as SADMC_FLAG_FAST_MATH. */
@@ -143,8 +145,9 @@ typedef struct sadmc_config {
    * SADMC_ERR_WINDOW.  NaN = derive from min/max_allowed_energy and the
    * system's lowest_possible_energy(). */
   double bin_window_lo, bin_window_hi;
-  int32_t lanes_per_walker; /* LJ only: 0 = auto; 32/16/8/4 = that many lanes of a warp cooperate on one walker
-                               (registers + shuffles); 1 = one thread per walker, cluster in shared memory */
+  int32_t lanes_per_walker; /* LJ: 0 = auto; 32/16/8/4 = that many lanes of a warp cooperate on one walker
+                               (registers + shuffles); 1 = one thread per walker, cluster in shared memory.
+                               WCA: 0 = 8; 4/8/16 = lanes sharing a walker's cell-list lookups; 32 = a warp per walker */
   uint32_t flags;
 } sadmc_config;
 
@@ -286,6 +289,11 @@ int sadmc_fold_select(sadmc_engine* e, uint32_t first_walker, uint32_t walker_st
  * lies outside the range (energy.rs:535-538), so their ln w is not an estimate of the entropy. */
 int sadmc_fold_select_ex(sadmc_engine* e, uint32_t first_walker, uint32_t walker_stride, uint32_t walker_count,
                          int sad_range_only);
+/* tl_max != 0: a SAD walker contributes its ln w to the following folds only if the bins of its range
+ * [too_lo, too_hi] have not changed since move tl_max: a bin that has just joined a walker's range starts from a copied
+ * or zero ln w (energy.rs:544-584) and settles slowly at gamma ~ 1/t.  (An engine-side record of the last range
+ * change is used, not `Sad::tL`: the reference refreshes tL far more often.)  0 (default) = every walker. */
+int sadmc_fold_settled(sadmc_engine* e, uint64_t tl_max);
 int sadmc_fold_device(sadmc_engine* e, void* d_histogram, void* d_energy_total, void* d_energy_squared_total,
                       void* d_lnw_sum, void* d_lnw_sq_sum, void* d_lnw_count);
 /* The same fold as ONE device buffer of 7 x nbins doubles, for a single collective: histogram >> 32,

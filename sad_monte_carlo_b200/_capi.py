@@ -43,6 +43,7 @@ PROTOTYPES = {
     "sadmc_cell_box": (C.c_int, [vp, f64p, f64p]),
     "sadmc_fold_select": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_int]),
     "sadmc_fold_select_ex": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
+    "sadmc_fold_settled": (C.c_int, [vp, C.c_uint64]),
     "sadmc_fold_device": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "sadmc_fold_packed_device": (C.c_int, [vp, vp]),
     "sadmc_fold": (C.c_int, [vp, u64p, f64p, f64p, f64p, f64p, u64p]),

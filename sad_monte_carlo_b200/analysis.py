@@ -250,7 +250,7 @@ def dos_gate(folds, groups, per_group, weights, min_fraction=0.9, min_weight=0.0
     per = grouped_entropy(folds, groups, per_group, min_fraction)
     common = np.isfinite(lnD)
     for _, ok in per:
-        common &= ok
+        common = common & ok
     rms = []
     Sall = np.zeros(len(weights))
     for S, _ in per:

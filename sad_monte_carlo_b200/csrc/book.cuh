@@ -100,6 +100,11 @@ struct __align__(16) WalkerRec {
   // system extras
   double d_squared; // two-wells
   unsigned long long verify_fail;
+  // engine-side diagnostic, not part of the reference's state: the last move at which the BIN INDICES of the SAD range
+  // (ilo, ihi) changed.  (`tL` cannot serve: the reference refreshes it whenever the end bin, which is visited twice as
+  // often as its neighbours, sets a new histogram record from the half that lies outside the range, energy.rs:540-584.)
+  // Written straight to HBM from the rare path; 0 after a resume.
+  unsigned long long t_range;
 };
 
 struct DevParams {
@@ -146,6 +151,7 @@ __device__ __forceinline__ int f64_as_index(double x) {
 // edge (index); the bit-exact tier never uses it.
 template <int METHOD, int G, bool FAST = false>
 struct Book {
+  static constexpr int METHOD_KIND = METHOD;
   const DevParams& P;
   const uint32_t w;
   const bool writer; // lane 0 of the walker's group
@@ -178,13 +184,16 @@ struct Book {
   // SAD: ln w of the two boundary bins (ilo, ihi) as they sit in HBM; reject_move needs them for every walker
   // outside [too_lo, too_hi] and a dependent global load there would sit on the critical path of the move
   double b_lnw_lo, b_lnw_hi;
+  bool wrote_bins; // set by the rare paths that rewrite other bins' records in HBM (move_kernel's deferred bookkeeping)
   // FAST only
   double inv_width, inv_tF, inv_ns, inv_min_T;
   unsigned long long g_tF, g_ns;
 
   __device__ Book(const DevParams& p, uint32_t walker, bool is_writer, unsigned mask)
       : P(p), w(walker), writer(is_writer), gmask(mask), rec(p.rec + (size_t)walker * p.cap), inv_width(1.0 / p.width), inv_tF(0.0),
-        inv_ns(0.0), inv_min_T(1.0 / p.min_T), g_tF(0), g_ns(0) {}
+        inv_ns(0.0), inv_min_T(1.0 / p.min_T), g_tF(0), g_ns(0) {
+    wrote_bins = false;
+  }
 
   __device__ __forceinline__ void sync() const {
     if (G > 1) __syncwarp(gmask);
@@ -417,6 +426,7 @@ struct Book {
   // ---- SAD part of update_weights (energy.rs:523-636) ------------------------
   __device__ __forceinline__ void sad_extend_range(double energy, unsigned long long moves) {
     // Reached when histogram[i] just exceeded highest_hist AND energy lies outside [too_lo, too_hi].
+    wrote_bins = true;
     flush();
     const int i = ci;
     if (energy > too_hi) {
@@ -450,6 +460,7 @@ struct Book {
       latest_parameter = (energy - too_lo) / P.min_T;
       tL = moves;
       too_hi = centre(i);
+      if (i != ihi && writer) P.walkers[w].t_range = moves;
       ihi = i;
     } else { // energy < too_lo
       const double lnw_lo = rec[ilo].lo.lnw;
@@ -482,6 +493,7 @@ struct Book {
       latest_parameter = (too_hi - energy) / P.min_T;
       tL = moves;
       too_lo = centre(i);
+      if (i != ilo && writer) P.walkers[w].t_range = moves;
       ilo = i;
     }
     sync();

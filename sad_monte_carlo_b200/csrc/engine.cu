@@ -62,7 +62,7 @@ struct sadmc_engine {
   double* d_fold_part = nullptr; // per-chunk partial sums of the two-stage fold
   size_t fold_part_bytes = 0;
   float last_ms = 0.f;
-  FoldSel fold_sel = {0u, 1u, 0u, 0};
+  FoldSel fold_sel = {0u, 1u, 0u, 0, 0ull};
   unsigned int* h_halted = nullptr;     // pinned copy of P.halted, refreshed behind every launch
   unsigned int halted_seen[2] = {0, 0}; // what sadmc_sync has reported already
   std::vector<void*> allocs;
@@ -86,7 +86,18 @@ static int pick_kernels(sadmc_engine* e) {
   switch (c.system) {
     case SADMC_SYS_ISING: e->ks = kernels_ising(P); return 0;
     case SADMC_SYS_FAKE: e->ks = kernels_fake(P); return 0;
-    case SADMC_SYS_WCA: e->ks = kernels_cell_fluid(false, P); return 0;
+    case SADMC_SYS_WCA: {
+      // lanes_per_walker: 0 = 8 (the fastest measured), 4 / 8 / 16 = that many lanes share a walker (sys_wca_group.cuh),
+      // 32 = one warp per walker (sys_cell_fluid.cuh, the kernel the square well uses)
+      const int G = c.lanes_per_walker == 0 ? 8 : c.lanes_per_walker;
+      const bool fast = (c.flags & SADMC_FLAG_FAST_MATH) != 0;
+      if (G == 32 && !fast) {
+        e->ks = kernels_cell_fluid(false, P);
+        return 0;
+      }
+      if (kernels_wca_group(G, fast, P, &e->ks)) return 0;
+      return fail(SADMC_ERR_UNSUPPORTED, "wca: lanes_per_walker must be 0, 4, 8, 16 or 32 (32 without SADMC_FLAG_FAST_MATH), not %d", G);
+    }
     case SADMC_SYS_SW: e->ks = kernels_cell_fluid(true, P); return 0;
     case SADMC_SYS_TWO_WELLS: e->ks = kernels_two_wells(P); return 0;
     case SADMC_SYS_FAKE_ERFINV: e->ks = kernels_erfinv(P); return 0;
@@ -1027,6 +1038,11 @@ int sadmc_fold_select_ex(sadmc_engine* e, uint32_t first_walker, uint32_t walker
   e->fold_sel.stride = walker_stride;
   e->fold_sel.count = walker_count;
   e->fold_sel.sad_range_only = sad_range_only;
+  return 0;
+}
+int sadmc_fold_settled(sadmc_engine* e, uint64_t tl_max) {
+  if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  e->fold_sel.tl_max = tl_max;
   return 0;
 }
 int sadmc_fold_select(sadmc_engine* e, uint32_t first_walker, uint32_t walker_stride, int sad_range_only) {

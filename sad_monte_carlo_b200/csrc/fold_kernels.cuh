@@ -22,15 +22,24 @@ namespace sadmc {
 // are switched off): ln w of a bin never decreases and a SAD range extension only writes values that exist already,
 // so the merge is ONE pass over the records.  With a range restriction the maximum over the restricted set is taken
 // by walker_max_lnw_kernel first.
+//
+// tl_max (sadmc_fold_settled; 0 = off): a SAD walker contributes ln w only if the bins of its range [too_lo, too_hi] have
+// not changed since move tl_max (WalkerRec::t_range).  A bin that has just joined a walker's range starts from a copied
+// or zero ln w (energy.rs:544-584), the former end bin from a ln w that received only half of its increments, and at
+// gamma ~ 1/t such a bin needs about as long again to settle; a minority of such walkers otherwise dominates the error
+// of an ensemble mean.  Histograms and energy moments are not filtered.
 struct FoldSel {
   uint32_t first, stride, count;
   int sad_range_only;
+  unsigned long long tl_max;
 };
 __device__ __forceinline__ void fold_range(const WalkerRec& r, const FoldSel s, int& ilo, int& ihi) {
-  const bool ranged = s.sad_range_only != 0 && r.method == SADMC_METHOD_SAD;
+  const bool sad = r.method == SADMC_METHOD_SAD;
+  const bool ranged = s.sad_range_only != 0 && sad;
   const int shrink = s.sad_range_only == 2 ? 1 : 0;
   ilo = ranged ? r.ilo + shrink : r.lo;
   ihi = ranged ? r.ihi - shrink : r.lo + r.len - 1;
+  if (sad && s.tl_max != 0 && r.t_range > s.tl_max) ihi = ilo - 1; // not settled: no bin counts
 }
 __device__ __forceinline__ bool fold_lnw_counts(const WalkerRec& r, const BinLo& b, int j, const FoldSel s) {
   if (b.hist == 0) return false;

@@ -39,6 +39,7 @@ KernelSet kernels_fake(const DevParams& P);
 KernelSet kernels_two_wells(const DevParams& P);
 KernelSet kernels_erfinv(const DevParams& P);
 KernelSet kernels_cell_fluid(bool square_well, const DevParams& P);
+bool kernels_wca_group(int G, bool fast, const DevParams& P, KernelSet* out);
 bool kernels_lj_thread_exact(int N, const DevParams& P, KernelSet* out);
 bool kernels_lj_thread_fast(int N, int G, const DevParams& P, KernelSet* out);
 bool kernels_lj_thread_paired(int N, const DevParams& P, KernelSet* out);

@@ -18,7 +18,7 @@ static KernelSet make_set(const DevParams& P) {
   k.shim = shim_kernel<Sys>;
   k.G = Sys::G;
   k.block = Sys::BLOCK;
-  k.smem = ZIG_SMEM_BYTES + Sys::smem_bytes(P, Sys::BLOCK);
+  k.smem = zig_smem_bytes<Sys>() + Sys::smem_bytes(P, Sys::BLOCK);
   return k;
 }
 

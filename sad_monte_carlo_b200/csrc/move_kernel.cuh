@@ -45,6 +45,19 @@ struct HasVerify<S, decltype((void)S::VERIFIES)> {
   static constexpr bool value = S::VERIFIES;
 };
 
+// Systems whose shared memory is better spent on walkers read the 4 KB ziggurat tables straight from global memory
+// (they stay L1-resident) and declare ZIG_GLOBAL.
+template <class S, class = void>
+struct HasZigGlobal {
+  static constexpr bool value = false;
+};
+template <class S>
+struct HasZigGlobal<S, decltype((void)S::ZIG_GLOBAL)> {
+  static constexpr bool value = S::ZIG_GLOBAL;
+};
+template <class S>
+__host__ __device__ constexpr int zig_smem_bytes();
+
 template <int G>
 __device__ __forceinline__ unsigned group_mask() {
   if (G >= 32) return 0xffffffffu;
@@ -52,11 +65,20 @@ __device__ __forceinline__ unsigned group_mask() {
   return ((1u << (G & 31)) - 1u) << (lane / G * G);
 }
 
+template <class S>
+__host__ __device__ constexpr int zig_smem_bytes() {
+  return HasZigGlobal<S>::value ? 0 : ZIG_SMEM_BYTES;
+}
+template <class S>
 __device__ __forceinline__ const double* stage_zig(const DevParams& P, unsigned char* smem) {
-  double* z = reinterpret_cast<double*>(smem);
-  for (int i = threadIdx.x; i < 2 * SADMC_ZIG_TABLE_LEN; i += blockDim.x) z[i] = P.zig[i];
-  __syncthreads();
-  return z;
+  if constexpr (HasZigGlobal<S>::value) {
+    return P.zig;
+  } else {
+    double* z = reinterpret_cast<double*>(smem);
+    for (int i = threadIdx.x; i < 2 * SADMC_ZIG_TABLE_LEN; i += blockDim.x) z[i] = P.zig[i];
+    __syncthreads();
+    return z;
+  }
 }
 
 // Sad/WL method state at construction, `Method::new` (energy.rs:246-313), and the
@@ -119,6 +141,7 @@ __device__ void first_bin(const DevParams& P, uint32_t w, WalkerRec& r, double e
   r.rt_fill_lo = (int)lo;
   r.rt_fill_hi = (int)lo + 1;
   r.verify_fail = 0;
+  r.t_range = 0;
 }
 
 // `from_params` for every walker: optional randomize, the downhill relaxation
@@ -127,7 +150,7 @@ template <class Sys>
 __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) init_kernel(const DevParams P, unsigned long long seed0, int init_mode, long long k_base,
                                                          int method_param, double samc_t0, unsigned long long max_relax) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const double* zx = stage_zig(P, smem);
+  const double* zx = stage_zig<Sys>(P, smem);
   const double* zf = zx + SADMC_ZIG_TABLE_LEN;
   constexpr int G = Sys::G;
   const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -136,7 +159,7 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) init_kernel(const
   if (w >= P.n_walkers) return;
   const unsigned gmask = group_mask<G>();
   WalkerRec& wr = P.walkers[w];
-  Sys sys(P, w, lane, gmask, smem + ZIG_SMEM_BYTES);
+  Sys sys(P, w, lane, gmask, smem + zig_smem_bytes<Sys>());
   sys.load(P, w, wr);
   Rng rng;
   seed_from_u64(seed0 + (unsigned long long)w, (uint64_t*)&rng.s0, (uint64_t*)&rng.s1); // energy.rs:835, walker w <-> --seed seed0+w
@@ -160,10 +183,54 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) init_kernel(const
   sys.store(P, w, wr, lane == 0);
 }
 
+// Systems whose move kernel may run a move's bookkeeping during the NEXT move declare DEFER_BOOK (see move_kernel).
+template <class S, class = void>
+struct HasDefer {
+  static constexpr bool value = false;
+};
+template <class S>
+struct HasDefer<S, decltype((void)S::DEFER_BOOK)> {
+  static constexpr bool value = S::DEFER_BOOK;
+};
+
+// What `move_once` does after the accept test, for the state the walker is in after move `mv` (energy.rs:934-965):
+// histogram and energy moments of its bin, `data_to_collect`, update_weights, round trips.  `i1_ref` = reference index
+// of the bin the walker was in before the move.  own_gamma: evaluate gamma(mv) here (deferred bookkeeping: the
+// method state has not changed since the accept test of move mv) instead of taking the caller's g.
+template <class Sys, class BookT>
+__device__ __forceinline__ void bookkeep(Sys& sys, BookT& bk, unsigned long long mv, int i1_ref, double g, bool own_gamma) {
+  constexpr int METHOD = BookT::METHOD_KIND;
+  const double energy = sys.energy(); // energy.rs:934
+  const bool first_visit = bk.c_hist == 0;
+  if (first_visit) { // energy.rs:938-940
+    bk.c_tfound = mv;
+    bk.hi_dirty = true;
+    if (METHOD == SADMC_METHOD_SAD && bk.ci >= bk.ilo && bk.ci <= bk.ihi) bk.tfmax = mv;
+  }
+  bk.c_hist += 1;
+  bk.c_etot += energy;
+  bk.c_e2 += energy * energy;
+  {
+    double xv;
+    if (sys.extra(mv, xv)) { // energy.rs:944-946, Bins::accumulate_extra 374-386
+      bk.c_xcnt += 1;
+      bk.c_xtot += xv;
+      bk.x_dirty = true;
+    }
+  }
+  if (own_gamma) g = bk.gamma(mv);
+  if (METHOD == SADMC_METHOD_SAD) bk.update_weights_sad(energy, mv, g); // energy.rs:948
+  if (METHOD == SADMC_METHOD_SAMC) bk.c_lnw += g;
+  if (METHOD == SADMC_METHOD_WL) bk.update_weights_wl(energy, mv, first_visit, g);
+#ifndef SADMC_ABL_NORT
+  bk.round_trips(i1_ref, mv); // energy.rs:950-965
+#endif
+}
+
 template <class Sys, int METHOD>
 __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const DevParams P, unsigned long long moves0, unsigned long long n_moves) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const double* zx = stage_zig(P, smem);
+  const double* zx = stage_zig<Sys>(P, smem);
   const double* zf = zx + SADMC_ZIG_TABLE_LEN;
   constexpr int G = Sys::G;
   constexpr bool HELPERS = HasHelpers<Sys>::value;
@@ -172,7 +239,7 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
     // the upper half of the CTA only ever runs the pair loop for the walkers of the lower half
     if (threadIdx.x >= Sys::WALKERS_PER_BLOCK) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Sys::HELPER_REGS));
-      Sys::helper_loop(P, smem + ZIG_SMEM_BYTES, n_moves);
+      Sys::helper_loop(P, smem + zig_smem_bytes<Sys>(), n_moves);
       return;
     }
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Sys::MAIN_REGS));
@@ -190,7 +257,7 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
   WalkerRec& wr = P.walkers[w];
   bool halted = ghost || wr.status != 0; // a walker that left the window stays halted
   if (halted && !Sys::COOP) return;
-  Sys sys(P, w, lane, gmask, smem + ZIG_SMEM_BYTES);
+  Sys sys(P, w, lane, gmask, smem + zig_smem_bytes<Sys>());
   sys.load(P, w, wr);
   sys.set_cooperative(true);
   Book<METHOD, G, Sys::FAST_BOOK> bk(P, w, lane == 0 && !ghost, gmask);
@@ -212,20 +279,35 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
   constexpr bool VERIFIES = HasVerify<Sys>::value;
   int v_len = -1;
   unsigned long long v_period = 0, v_at = 0;
+  // DEFER (Sys::DEFER_BOOK, SAD, fixed translation scale): the bookkeeping of move m -- histogram and moments, gamma,
+  // update_weights, round trips: ~500 dependent scalar instructions that touch no memory -- is run during move m + 1,
+  // in the shadow of that move's bin-record load, instead of between the accept test and the next proposal.  Nothing
+  // the proposal needs (configuration, energy, generator, translation scale) is touched by it; the accept test of move
+  // m + 1 comes after it, so ln w, the SAD range and gamma are what they would have been.  The record requested before
+  // the bookkeeping ran is requested again in the one case in which the bookkeeping rewrites bins in HBM (a SAD range
+  // extension, energy.rs:544-584); a proposal that needs new bins (prepare_for_state would grow the vectors) waits
+  // with its request until the bookkeeping is done, because round_trips works on the old extent.
+  constexpr bool DEFER = HasDefer<Sys>::value && METHOD == SADMC_METHOD_SAD && !HasPredraw<Sys>::value && !HELPERS;
+  const bool defer = DEFER && P.move_plan == SADMC_MOVE_TRANSLATION_SCALE;
+  bool pend = false; // the previous move's bookkeeping is still to do
+  int pend_i1 = 0;   // ... with this reference index of the bin the walker was in before that move
 #pragma unroll 1
-  for (unsigned long long m = 0; m < n_moves; m++) {
-    moves += 1; // energy.rs:905
+  for (unsigned long long m = 0; m < n_moves + (DEFER ? 1ull : 0ull); m++) {
+    const bool epilogue = DEFER && m == n_moves; // one extra pass that only settles the last move's bookkeeping
+    if (!epilogue) moves += 1; // energy.rs:905
     if constexpr (VERIFIES) {
-      if (bk.len != v_len) {
-        v_len = bk.len;
-        v_period = (unsigned long long)v_len * (unsigned long long)v_len * 1000ull;
-        v_at = ((moves - 1) / v_period + 1) * v_period; // smallest multiple >= moves
-      }
-      if (moves == v_at) {
-        v_at += v_period;
-        if (!halted && !sys.verify_energy()) { // the reference panics here (lj.rs:259, wca.rs:248, optsquare.rs:200)
-          bk.status = SADMC_ERR_VERIFY;
-          halted = true;
+      if (!epilogue) {
+        if (bk.len != v_len) {
+          v_len = bk.len;
+          v_period = (unsigned long long)v_len * (unsigned long long)v_len * 1000ull;
+          v_at = ((moves - 1) / v_period + 1) * v_period; // smallest multiple >= moves
+        }
+        if (moves == v_at) {
+          v_at += v_period;
+          if (!halted && !sys.verify_energy()) { // the reference panics here (lj.rs:259, wca.rs:248, optsquare.rs:200)
+            bk.status = SADMC_ERR_VERIFY;
+            halted = true;
+          }
         }
       }
     }
@@ -233,13 +315,13 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
     const int i1 = bk.ci;
     const double recent_scale = recent_next;
     double e2 = 0.0;
-    bool accepted = false, proposing = false;
+    bool accepted = false, proposing = false, need_bins = false;
     int i2 = i1;
     BinLo r2;
     BinHi h2;
     // ln w and histogram of the bin the proposal lands in: the current bin's cached values unless the load below
-    // replaces them (no select on the loaded registers afterwards: a copy right behind the load would stall the warp
-    // there for the whole DRAM latency instead of at the accept test)
+    // replaces them (no select on the loaded registers right behind the load: it would stall the warp there for the
+    // whole DRAM latency instead of at the accept test)
     r2.lnw = bk.c_lnw;
     r2.hist = bk.c_hist;
     r2.etot = 0.0;
@@ -250,7 +332,7 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
     h2.wl_hist = 0;
     bool some_paired = false;
     if constexpr (HELPERS) some_paired = sys.plan_move_paired(!halted, rng, bk.tscale, zx, zf, e2); // every thread: barriers inside
-    if (!halted) {
+    if (!halted && !epilogue) {
       bk.acc_rate *= 1.0 - recent_scale;
       bool some;
       if constexpr (HELPERS) {
@@ -271,12 +353,16 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
         if (P.has_max) out_of_bounds = e2 > P.max_allowed && e2 > e1;
         if (P.has_min) out_of_bounds = out_of_bounds || (e2 < P.min_allowed && e2 < e1);
         if (!out_of_bounds) {
-          if (!bk.prepare_for_state(e2)) { // energy.rs:925
-            bk.status = SADMC_ERR_WINDOW;
-            halted = true;
-          } else {
-            i2 = bk.widx(e2);
-            proposing = true;
+          // with bookkeeping pending, a proposal outside the current extent of the bins waits for it (see above)
+          need_bins = DEFER && pend && (e2 < bk.bmin || e2 >= bk.bmin + P.width * (double)bk.len);
+          if (!need_bins) {
+            if (!bk.prepare_for_state(e2)) { // energy.rs:925
+              bk.status = SADMC_ERR_WINDOW;
+              halted = true;
+            } else {
+              i2 = bk.widx(e2);
+              proposing = true;
+            }
           }
         }
       }
@@ -284,15 +370,39 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
     // The one access of a move that goes to HBM: the record of the proposed bin.  Both sectors are
     // requested together (one DRAM access, no second dependent load if the walker moves there) ...
 #ifdef SADMC_ABL_NOLOAD /* ablation experiment only */
-    const bool other_bin = false;
+    bool other_bin = false;
 #else
-    const bool other_bin = proposing && i2 != i1;
+    bool other_bin = proposing && i2 != i1;
 #endif
     if (other_bin) load_rec(bk.rec + i2, r2, h2);
-    // ... and what does not depend on it is computed while it is in flight: next move's sqrt(1/moves)
+    // ... and what does not depend on it is computed while it is in flight: next move's sqrt(1/moves),
+    recent_next = sqrt(1.0 / (double)(moves + 1));
+    // the previous move's bookkeeping (DEFER),
+    if constexpr (DEFER) {
+      if (pend) {
+        pend = false;
+        bk.wrote_bins = false;
+        bookkeep(sys, bk, moves - (epilogue ? 0ull : 1ull), pend_i1, 0.0, true);
+        if (need_bins) { // now the vectors may grow (energy.rs:925)
+          if (!bk.prepare_for_state(e2)) {
+            bk.status = SADMC_ERR_WINDOW;
+            halted = true;
+          } else {
+            i2 = bk.widx(e2);
+            proposing = true;
+#ifndef SADMC_ABL_NOLOAD
+            other_bin = i2 != i1;
+#endif
+            if (other_bin) load_rec(bk.rec + i2, r2, h2);
+          }
+        } else if (bk.wrote_bins && other_bin) {
+          load_rec(bk.rec + i2, r2, h2); // the range extension may have rewritten ln w of the requested bin
+        }
+      }
+      if (epilogue) break;
+    }
     // and this move's gamma (energy.rs:799-824; re-evaluated below in the rare case that reject_move's
     // first-visit hook changes its inputs).
-    recent_next = sqrt(1.0 / (double)(moves + 1));
     double gamma_now = bk.gamma(moves);
     // ... and the next proposal's random numbers, for both places the stream can be at after the accept test
     PreDraw pre_b;
@@ -307,8 +417,9 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
       }
     }
     if (proposing) {
-      const double lnw2 = r2.lnw;
-      const unsigned long long hist2 = r2.hist;
+      // DEFER: the bookkeeping that just ran has updated the current bin's cached record (the load has long landed)
+      const double lnw2 = DEFER ? (other_bin ? r2.lnw : bk.c_lnw) : r2.lnw;
+      const unsigned long long hist2 = DEFER ? (other_bin ? r2.hist : bk.c_hist) : r2.hist;
       const unsigned long long tL_before = bk.tL;
       if (!bk.reject_move(e1, e2, i2, lnw2, hist2, moves, rng)) { // energy.rs:927-931
         accepted = true;
@@ -338,30 +449,12 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
       }
     }
     if (!halted) {
-      const double energy = sys.energy(); // energy.rs:934
-      const bool first_visit = bk.c_hist == 0;
-      if (first_visit) { // energy.rs:938-940
-        bk.c_tfound = moves;
-        bk.hi_dirty = true;
-        if (METHOD == SADMC_METHOD_SAD && bk.ci >= bk.ilo && bk.ci <= bk.ihi) bk.tfmax = moves;
+      if (defer) { // settled during the next move (or by the epilogue pass)
+        pend = true;
+        pend_i1 = i1 - bk.lo;
+      } else {
+        bookkeep(sys, bk, moves, i1 - bk.lo, gamma_now, false);
       }
-      bk.c_hist += 1;
-      bk.c_etot += energy;
-      bk.c_e2 += energy * energy;
-      {
-        double xv;
-        if (sys.extra(moves, xv)) { // energy.rs:944-946, Bins::accumulate_extra 374-386
-          bk.c_xcnt += 1;
-          bk.c_xtot += xv;
-          bk.x_dirty = true;
-        }
-      }
-      if (METHOD == SADMC_METHOD_SAD) bk.update_weights_sad(energy, moves, gamma_now); // energy.rs:948
-      if (METHOD == SADMC_METHOD_SAMC) bk.c_lnw += gamma_now;
-      if (METHOD == SADMC_METHOD_WL) bk.update_weights_wl(energy, moves, first_visit, gamma_now);
-#ifndef SADMC_ABL_NORT
-      bk.round_trips(i1 - bk.lo, moves); // energy.rs:950-965
-#endif
     }
   }
   if (ghost) return;
@@ -379,14 +472,14 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
 template <class Sys>
 __global__ void __launch_bounds__(Sys::BLOCK) shim_kernel(const DevParams P, uint32_t w, int op, double arg, ShimOut* out, double* pending) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const double* zx = stage_zig(P, smem);
+  const double* zx = stage_zig<Sys>(P, smem);
   const double* zf = zx + SADMC_ZIG_TABLE_LEN;
   constexpr int G = Sys::G;
   const int lane = (int)threadIdx.x;
   if (lane >= G) return;
   const unsigned gmask = group_mask<G>();
   WalkerRec& wr = P.walkers[w];
-  Sys sys(P, w, lane, gmask, smem + ZIG_SMEM_BYTES);
+  Sys sys(P, w, lane, gmask, smem + zig_smem_bytes<Sys>());
   sys.load(P, w, wr);
   Rng rng;
   rng.s0 = wr.s0;

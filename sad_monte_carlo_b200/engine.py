@@ -197,6 +197,11 @@ class WalkerEngine:
         (True / 1) or only strictly inside it (2: without the two half-updated end bins)."""
         self._check(self.L.sadmc_fold_select_ex(self.h, first_walker, walker_stride, walker_count, int(sad_range_only)))
 
+    def fold_settled(self, tl_max=0):
+        """SAD walkers contribute ln w to the following folds only if their range has not changed since move tl_max
+        (Sad::tL <= tl_max); 0 = every walker."""
+        self._check(self.L.sadmc_fold_settled(self.h, int(tl_max)))
+
     def fold(self):
         """Window-aligned sums over the local walkers (device fold kernel), as host arrays."""
         _, _, n = self.window()

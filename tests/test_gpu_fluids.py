@@ -95,9 +95,17 @@ def _wca_pair(N, rho, n_walkers, method="samc", **kw):
     return cfg, eng, state
 
 
+# kernels: lanes_per_walker 32 = one warp per walker (sys_cell_fluid.cuh); 4 / 8 / 16 = lane groups (sys_wca_group.cuh),
+# with SADMC_FLAG_FAST_MATH their fast arithmetic and relaxed re-summation cadence
+KERNELS = [dict(lanes_per_walker=32), dict(lanes_per_walker=8), dict(lanes_per_walker=8, flags=_abi.FLAG_FAST_MATH),
+           dict(lanes_per_walker=4, flags=_abi.FLAG_FAST_MATH), dict(lanes_per_walker=16), dict(lanes_per_walker=16, flags=_abi.FLAG_FAST_MATH)]
+KERNEL_IDS = ["warp", "g8", "g8fast", "g4fast", "g16", "g16fast"]
+
+
+@pytest.mark.parametrize("kern", KERNELS, ids=KERNEL_IDS)
 @pytest.mark.parametrize("N,rho", [(50, 1.0), (100, 0.3), (256, 0.8)])
-def test_wca_per_move_energy_within_1e12(N, rho):
-    cfg, eng, state = _wca_pair(N, rho, 2)
+def test_wca_per_move_energy_within_1e12(N, rho, kern):
+    cfg, eng, state = _wca_pair(N, rho, 2, **kern)
     o = OracleMC(cfg, walker=1, system_state=state)
     rng = np.random.default_rng(0)
     for step in range(1200):
@@ -116,9 +124,10 @@ def test_wca_per_move_energy_within_1e12(N, rho):
     assert abs(eng.compute_energy(1) - o.compute_energy()) <= RTOL * max(1.0, abs(o.energy()))
 
 
+@pytest.mark.parametrize("kern", KERNELS, ids=KERNEL_IDS)
 @pytest.mark.parametrize("method,kw", [("samc", {}), ("sad", dict(sad_min_T=0.5)), ("inv-t-wl", dict(min_allowed_energy=0.0, max_allowed_energy=600.0))])
-def test_wca_trajectory_tracks_oracle(method, kw):
-    cfg, eng, state = _wca_pair(64, 0.7, 4, method=method, **kw)
+def test_wca_trajectory_tracks_oracle(method, kw, kern):
+    cfg, eng, state = _wca_pair(64, 0.7, 4, method=method, **kw, **kern)
     oracles = {w: OracleMC(cfg, walker=w, system_state=state) for w in (0, 3)}
     eng.run(20000)
     for w, o in oracles.items():
@@ -135,8 +144,23 @@ def test_wca_trajectory_tracks_oracle(method, kw):
         assert eng.verify_energy(w)
 
 
-def test_wca_pressure_extra_every_n_squared_moves():
-    cfg, eng, state = _wca_pair(27, 0.3, 3)
+def test_wca_fast_tier_energy_drift_between_resummations_is_far_below_1e12():
+    """The fast tier re-sums the whole energy every 65 536 accepted moves instead of every ~10 (wca.rs:164-177): in
+    between the cached energy only collects the rounding of the per-move differences."""
+    cfg, eng, state = _wca_pair(256, 0.8, 64, lanes_per_walker=8, flags=_abi.FLAG_FAST_MATH)
+    eng.run(60000)  # fewer accepted moves than one re-summation period: pure accumulation
+    worst = 0.0
+    for w in range(0, 64, 7):
+        assert eng.walker(w).accepted_moves < 65536
+        e, good = eng.energy(w), eng.compute_energy(w)
+        worst = max(worst, abs(e - good) / max(1.0, abs(good)))
+        assert eng.verify_energy(w)  # the reference's own tolerance (wca.rs:237-251)
+    assert worst <= 1e-13, worst
+
+
+@pytest.mark.parametrize("kern", KERNELS[:3], ids=KERNEL_IDS[:3])
+def test_wca_pressure_extra_every_n_squared_moves(kern):
+    cfg, eng, state = _wca_pair(27, 0.3, 3, **kern)
     o = OracleMC(cfg, walker=2, system_state=state)
     eng.run(27 * 27 * 20 + 5)
     o.run(27 * 27 * 20 + 5)
@@ -145,9 +169,10 @@ def test_wca_pressure_extra_every_n_squared_moves():
     assert np.allclose(gb["extra_total"], ob["extra_total"], rtol=1e-11, atol=1e-12)
 
 
-def test_wca_randomize_matches_reference_randomize():
+@pytest.mark.parametrize("kern", KERNELS[:3], ids=KERNEL_IDS[:3])
+def test_wca_randomize_matches_reference_randomize(kern):
     cfg = make_config("wca", "samc", N=30, reduced_density=0.05, samc_t0=10.0, energy_bin=1e9, n_walkers=3, seed=11,
-                      init_mode=_abi.INIT_RANDOMIZE, bin_window_lo=0.0, bin_window_hi=1e12)
+                      init_mode=_abi.INIT_RANDOMIZE, bin_window_lo=0.0, bin_window_hi=1e12, **kern)
     eng = WalkerEngine(cfg)
     for w in (0, 2):
         o = OracleMC(cfg, walker=w)
@@ -157,11 +182,12 @@ def test_wca_randomize_matches_reference_randomize():
         assert eng.walker(w).status == 0
 
 
-def test_wca_reference_constructor_start_tracks_oracle():
+@pytest.mark.parametrize("kern", KERNELS[:3], ids=KERNEL_IDS[:3])
+def test_wca_reference_constructor_start_tracks_oracle(kern):
     # SADMC_INIT_REFERENCE: every walker starts from the N*N-attempt configuration of wca.rs:448-496 (built on the
     # host by the library), then from_params relaxes it below max_allowed_energy (energy.rs:840-851) on the device
     cfg = make_config("wca", "samc", N=40, reduced_density=0.5, energy_bin=1.0, n_walkers=4, seed=9, samc_t0=1e3,
-                      max_allowed_energy=400.0)
+                      max_allowed_energy=400.0, **kern)
     eng = WalkerEngine(cfg)
     for w in (0, 3):
         o = OracleMC(cfg, walker=w)

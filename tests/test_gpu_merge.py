@@ -206,7 +206,9 @@ def test_randomize_shim_matches_oracle():
     from tests.oracle_lib import OracleMC
     for system, kw in (("lj", dict(N=13, lj_radius=3.0)), ("fake", dict(fake_function=_abi.FAKE_QUADRATIC, N=3)),
                        ("ising", dict(N=8))):
-        cfg = make_config(system, "sad", n_walkers=3, seed=5, lanes_per_walker=1 if system == "lj" else 0, **kw)
+        if system == "lj":
+            kw = dict(kw, lanes_per_walker=1, bin_window_lo=-60.0, bin_window_hi=1e4, energy_bin=1.0)
+        cfg = make_config(system, "sad", n_walkers=3, seed=5, **kw)
         eng = WalkerEngine(cfg)
         o = OracleMC(cfg, walker=2)
         for _ in range(3):

@@ -43,7 +43,7 @@ def cases(which):
     return out
 
 
-def run_case(name, kw, weights_fn, walkers, schedule, groups, seed=0):
+def run_case(name, kw, weights_fn, walkers, schedule, groups, seed=0, settled=0.5, dump=None):
     kw = dict(kw)
     system = kw.pop("system")
     cfg = make_config(system, "sad", n_walkers=walkers, seed=seed, **kw)
@@ -56,18 +56,30 @@ def run_case(name, kw, weights_fn, walkers, schedule, groups, seed=0):
     for target in schedule:
         eng.run(target - done)
         done = target
-        folds = []
-        for g in range(groups):
-            eng.fold_select(g, groups, True)
-            folds.append(eng.fold())
-        eng.fold_select(0, 1, False)
-        r = analysis.dos_gate(folds, groups, walkers // groups, weights)
-        halted = sum(1 for w in range(0, walkers, max(1, walkers // 128)) if eng.walker(w).status != 0)
-        line = {"case": name, "walkers": walkers, "groups": groups, "moves_per_walker": done, "rms_all_walkers": r["rms_all"],
-                "rms_group_mean": r["rms_mean"], "rms_group_sem": r["rms_sem"], "worst_bin": r["worst"], "bins_gated": r["n_bins"],
-                "bins_in_window": int(nb), "halted_in_sample": halted, "wall_s": round(time.time() - t0, 2)}
-        lines.append(line)
-        print(json.dumps(line), flush=True)
+        for frac in sorted({0.0, settled}):
+            # only walkers whose SAD range has been unchanged since move frac * done take part (0 = all walkers)
+            eng.fold_settled(int(frac * done))
+            folds = []
+            for g in range(groups):
+                eng.fold_select(g, groups, 2)  # strictly inside each walker's SAD range
+                folds.append(eng.fold())
+            eng.fold_select(0, 1, False)
+            eng.fold_settled(0)
+            taking_part = int(sum(f["lnw_count"].max() for f in folds))
+            r = analysis.dos_gate(folds, groups, taking_part / groups, weights)
+            line = {"case": name, "walkers": walkers, "groups": groups, "moves_per_walker": done, "settled_since": frac,
+                    "walkers_taking_part": taking_part, "rms_all_walkers": r["rms_all"], "rms_group_mean": r["rms_mean"],
+                    "rms_group_sem": r["rms_sem"], "worst_bin": r["worst"], "bins_gated": r["n_bins"], "bins_in_window": int(nb),
+                    "halted": list(eng.num_halted()), "wall_s": round(time.time() - t0, 2)}
+            lines.append(line)
+            print(json.dumps(line), flush=True)
+            if dump:
+                import numpy as np
+                ws = [eng.walker(w) for w in range(0, walkers, max(1, walkers // 2048))]
+                np.savez_compressed("%s_%s_%d_%g.npz" % (dump, name.split(" dE")[0].replace(" ", "_") + ("_dE%g" % width), done, frac),
+                                    residual=r["residual"], mask=r["mask"], window_lo=lo, width=width,
+                                    tL=np.array([w.tL for w in ws]), too_lo=np.array([w.too_lo for w in ws]),
+                                    too_hi=np.array([w.too_hi for w in ws]), lnw_count=np.array([f["lnw_count"] for f in folds]))
     eng.close()
     return lines
 
@@ -79,11 +91,13 @@ def main():
     ap.add_argument("--groups", type=int, default=8)
     ap.add_argument("--systems", default="linear,quadratic,two-wells")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--settled", type=float, default=0.5, help="also gate over the walkers whose SAD range is unchanged since this fraction of the run")
+    ap.add_argument("--dump", default=None, help="prefix for npz files with the residuals and a sample of walker states")
     a = ap.parse_args()
     schedule = [int(float(x)) for x in a.schedule.split(",")]
     lines = []
     for name, kw, wf in cases(a.systems.split(",")):
-        lines += run_case(name, kw, wf, a.walkers, schedule, a.groups)
+        lines += run_case(name, kw, wf, a.walkers, schedule, a.groups, settled=a.settled, dump=a.dump)
     if a.out:
         with open(a.out, "w") as f:
             for ln in lines:

@@ -28,6 +28,9 @@ def main():
     ap.add_argument("--energy-bin", type=float, default=0.01)
     ap.add_argument("--chunk", type=float, default=1e6)
     ap.add_argument("--exact", action="store_true")
+    ap.add_argument("--range-mode", type=int, default=2, help="1: bins inside [too_lo, too_hi]; 2: strictly inside (without the half-updated end bins)")
+    ap.add_argument("--settled", type=float, default=0.5, help="also fold only the walkers whose SAD range is unchanged since this fraction of the run (0: skip)")
+    ap.add_argument("--tag", default="lj31_cv")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out"))
     a = ap.parse_args()
     cfg = make_config("lj", "sad", N=31, lj_radius=2.5, max_allowed_energy=0.0, sad_min_T=a.min_T, energy_bin=a.energy_bin,
@@ -38,27 +41,38 @@ def main():
     os.makedirs(a.out, exist_ok=True)
     t0 = time.time()
     done = 0
+    age_log = []  # (walker age at the end of the chunk, moves/s of the chunk's launch): throughput against walker age
     for target in [int(float(x)) for x in a.schedule.split(",")]:
         while done < target:
             n = int(min(a.chunk, target - done))
             eng.run(n)
             done += n
-        out = {"window_lo": lo, "width": width, "moves": done, "walkers": a.walkers, "groups": a.groups, "min_T": a.min_T}
-        for g in range(a.groups):
-            eng.fold_select(g, a.groups, True)
-            f = eng.fold()
-            for k in ("histogram", "lnw_sum", "lnw_sq_sum", "lnw_count"):
-                out["%s_%d" % (k, g)] = f[k]
+            age_log.append((done, a.walkers * n / (eng.last_run_ms() * 1e-3)))
+        out = {"window_lo": lo, "width": width, "moves": done, "walkers": a.walkers, "groups": a.groups, "min_T": a.min_T,
+               "range_mode": a.range_mode, "settled": a.settled, "age_log": np.array(age_log)}
+        for frac, suffix in ((0.0, ""), (a.settled, "_settled")):
+            if suffix and not a.settled:
+                continue
+            eng.fold_settled(int(frac * done))
+            for g in range(a.groups):
+                eng.fold_select(g, a.groups, a.range_mode)
+                f = eng.fold()
+                for k in ("histogram", "lnw_sum", "lnw_sq_sum", "lnw_count"):
+                    if suffix and k == "histogram":
+                        continue
+                    out["%s%s_%d" % (k, suffix, g)] = f[k]
+        eng.fold_settled(0)
         eng.fold_select(0, 1, False)
         ws = [eng.walker(w) for w in range(0, a.walkers, max(1, a.walkers // 256))]
         out["too_lo"] = np.array([w.too_lo for w in ws])
         out["too_hi"] = np.array([w.too_hi for w in ws])
         out["energy"] = np.array([w.energy for w in ws])
         out["status"] = np.array([w.status for w in ws])
-        np.savez_compressed(os.path.join(a.out, "lj31_cv_%.0e.npz" % done), **out)
-        print("moves/walker %.1e  wall %.1f s  too_lo median %.2f min %.2f  too_hi median %.2f  halted %d" % (
-            done, time.time() - t0, np.median(out["too_lo"]), out["too_lo"].min(), np.median(out["too_hi"]),
-            int((out["status"] != 0).sum())), flush=True)
+        out["tL"] = np.array([w.tL for w in ws])
+        np.savez_compressed(os.path.join(a.out, "%s_%.0e.npz" % (a.tag, done)), **out)
+        print("moves/walker %.1e  wall %.1f s  %.3g moves/s (last chunk)  too_lo median %.2f min %.2f  too_hi median %.2f  settled %.0f%%  halted %s" % (
+            done, time.time() - t0, age_log[-1][1], np.median(out["too_lo"]), out["too_lo"].min(), np.median(out["too_hi"]),
+            100.0 * np.mean(out["tL"] <= a.settled * done), eng.num_halted()), flush=True)
     eng.close()
 
 
