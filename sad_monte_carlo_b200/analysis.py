@@ -239,8 +239,10 @@ def grouped_entropy(folds, groups, per_group, min_fraction=0.9):
     return out
 
 
-def dos_gate(folds, groups, per_group, weights, min_fraction=0.9, min_weight=0.0):
+def dos_gate(folds, groups, per_group, weights, min_fraction=0.9, min_weight=0.0, centres=None, energy_range=None):
     """RMS of S - ln(exact bin weight) after removing the additive constant, per interleaved walker group.
+
+    energy_range = (lo, hi) with `centres` (bin centres) restricts the gate to the bins whose centre lies inside.
 
     Returns dict(rms_mean, rms_sem, rms_all, n_bins, worst): `rms_mean`/`rms_sem` are the mean and the standard
     error over the groups' own RMS values (ensemble error bar); `rms_all` is the RMS of the all-walker mean entropy."""
@@ -249,6 +251,9 @@ def dos_gate(folds, groups, per_group, weights, min_fraction=0.9, min_weight=0.0
     lnD[pos] = np.log(weights[pos])
     per = grouped_entropy(folds, groups, per_group, min_fraction)
     common = np.isfinite(lnD)
+    if energy_range is not None:
+        c = np.asarray(centres, dtype=np.float64)
+        common = common & (c >= energy_range[0]) & (c <= energy_range[1])
     for _, ok in per:
         common = common & ok
     rms = []

@@ -388,6 +388,7 @@ struct Book {
     }
     if (METHOD == SADMC_METHOD_SAMC || method == SADMC_METHOD_SAMC) {
       const double t = (double)moves;
+      if (FAST) return t > samc_t0 ? samc_t0 * rcp_newton(t) : 1.0; // tolerance tier: no IEEE divide per move
       return t > samc_t0 ? samc_t0 / t : 1.0;
     }
     return wl_gamma;

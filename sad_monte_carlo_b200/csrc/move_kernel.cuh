@@ -288,7 +288,8 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
   // extension, energy.rs:544-584); a proposal that needs new bins (prepare_for_state would grow the vectors) waits
   // with its request until the bookkeeping is done, because round_trips works on the old extent.
   constexpr bool DEFER = HasDefer<Sys>::value && METHOD == SADMC_METHOD_SAD && !HasPredraw<Sys>::value && !HELPERS;
-  const bool defer = DEFER && P.move_plan == SADMC_MOVE_TRANSLATION_SCALE;
+  // (the engine only selects a DEFER kernel for runs with a fixed translation scale: with MoveParams::AcceptanceRate the
+  // bookkeeping can change the step size the next proposal uses, energy.rs:606-616)
   bool pend = false; // the previous move's bookkeeping is still to do
   int pend_i1 = 0;   // ... with this reference index of the bin the walker was in before that move
 #pragma unroll 1
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
       }
     }
     if (!halted) {
-      if (defer) { // settled during the next move (or by the epilogue pass)
+      if constexpr (DEFER) { // settled during the next move (or by the epilogue pass): ONE copy of the bookkeeping code
         pend = true;
         pend_i1 = i1 - bk.lo;
       } else {

@@ -132,6 +132,63 @@ struct Rng {
   // one word; if it rejects, w_{f+2} is the redraw and they shift by two.  Everything is selected from
   // registers without a branch.  Only a second irregular event in the same call (tail layer i == 0, two
   // failures, a failing redraw: ~0.1 % of calls) rewinds the stream and replays it serially.
+  struct Slow3Out {
+    double v0, v1, v2;
+    uint64_t s0, s1;
+  };
+  // What normal3 does once one of its three words has left the fast path.  (a0, a1) = generator state before the
+  // call, (b0, b1) = after the third word.  Out of line on request (SADMC_ZIG_SLOW_NOINLINE): 69 % of the warps
+  // come here every move for a lane or two, but its ~150 instructions then sit outside the move loop's
+  // instruction-cache footprint.
+#ifdef SADMC_ZIG_SLOW_NOINLINE
+  static __host__ __device__ __noinline__ Slow3Out
+#else
+  static __host__ __device__ __forceinline__ Slow3Out
+#endif
+  normal3_slow(uint64_t a0, uint64_t a1, uint64_t b0, uint64_t b1, uint64_t w0, uint64_t w1, uint64_t w2, const double* zx, const double* zf) {
+    Rng r;
+    r.s0 = b0;
+    r.s1 = b1;
+#define SADMC_ZIG_FAST(k)                                                                 \
+  const uint32_t i##k = (uint32_t)(w##k & 0xff);                                           \
+  const double n##k = (sadmc_bits_f64((w##k >> 12) | 0x4000000000000000ull) - 3.0) * zx[i##k]; \
+  const bool ok##k = fabs(n##k) < zx[i##k + 1];
+    SADMC_ZIG_FAST(0)
+    SADMC_ZIG_FAST(1)
+    SADMC_ZIG_FAST(2)
+    const uint64_t w3 = r.next();
+    const uint64_t p3 = r.s0, q3 = r.s1;
+    const uint64_t w4 = r.next();
+    const uint64_t p4 = r.s0, q4 = r.s1;
+    SADMC_ZIG_FAST(3)
+    SADMC_ZIG_FAST(4)
+#undef SADMC_ZIG_FAST
+    Slow3Out o;
+    const int f = !ok0 ? 0 : (!ok1 ? 1 : 2); // first word that left the fast path
+    const uint32_t fi = f == 0 ? i0 : (f == 1 ? i1 : i2);
+    const double fx = f == 0 ? n0 : (f == 1 ? n1 : n2);
+    const uint64_t fu = f == 0 ? w1 : (f == 1 ? w2 : w3); // the word the wedge test draws its uniform from
+    const double u01 = (double)(fu >> 11) * (1.0 / 9007199254740992.0);
+    const bool acc = exp_cmp(zf[fi + 1] + (zf[fi] - zf[fi + 1]) * u01, -fx * fx / 2.0) < 0;
+    // fast-path validity of the words that the shifted stream turns into normals
+    const bool need_ok = f == 0 ? (acc ? (ok2 && ok3) : (ok2 && ok3 && ok4)) : (f == 1 ? (acc ? ok3 : (ok3 && ok4)) : (acc ? true : ok4));
+    if (fi != 0 && need_ok) {
+      o.v0 = f == 0 ? (acc ? n0 : n2) : n0;
+      o.v1 = f == 0 ? (acc ? n2 : n3) : (f == 1 ? (acc ? n1 : n3) : n1);
+      o.v2 = f == 2 ? (acc ? n2 : n4) : (acc ? n3 : n4);
+      o.s0 = acc ? p3 : p4;
+      o.s1 = acc ? q3 : q4;
+      return o;
+    }
+    r.s0 = a0; // replay serially from the start of the call
+    r.s1 = a1;
+    o.v0 = r.normal(zx, zf);
+    o.v1 = r.normal(zx, zf);
+    o.v2 = r.normal(zx, zf);
+    o.s0 = r.s0;
+    o.s1 = r.s1;
+    return o;
+  }
   __host__ __device__ __forceinline__ void normal3(const double* zx, const double* zf, double& v0, double& v1, double& v2) {
     const uint64_t a0 = s0, a1 = s1; // for the replay
     const uint64_t w0 = next();
@@ -144,49 +201,20 @@ struct Rng {
     SADMC_ZIG_FAST(0)
     SADMC_ZIG_FAST(1)
     SADMC_ZIG_FAST(2)
-    if (ok0 && ok1 && ok2) {
-      v0 = n0;
-      v1 = n1;
-      v2 = n2;
-      return;
-    }
-#ifdef SADMC_ABL_NOSLOW /* ablation experiment only: wrong statistics */
+#undef SADMC_ZIG_FAST
     v0 = n0;
     v1 = n1;
     v2 = n2;
+    if (ok0 && ok1 && ok2) return;
+#ifdef SADMC_ABL_NOSLOW /* ablation experiment only: wrong statistics */
     return;
 #endif
-    const uint64_t p2 = s0, q2 = s1;
-    (void)p2;
-    (void)q2;
-    const uint64_t w3 = next();
-    const uint64_t p3 = s0, q3 = s1;
-    const uint64_t w4 = next();
-    const uint64_t p4 = s0, q4 = s1;
-    SADMC_ZIG_FAST(3)
-    SADMC_ZIG_FAST(4)
-#undef SADMC_ZIG_FAST
-    const int f = !ok0 ? 0 : (!ok1 ? 1 : 2); // first word that left the fast path
-    const uint32_t fi = f == 0 ? i0 : (f == 1 ? i1 : i2);
-    const double fx = f == 0 ? n0 : (f == 1 ? n1 : n2);
-    const uint64_t fu = f == 0 ? w1 : (f == 1 ? w2 : w3); // the word the wedge test draws its uniform from
-    const double u01 = (double)(fu >> 11) * (1.0 / 9007199254740992.0);
-    const bool acc = exp_cmp(zf[fi + 1] + (zf[fi] - zf[fi + 1]) * u01, -fx * fx / 2.0) < 0;
-    // fast-path validity of the words that the shifted stream turns into normals
-    const bool need_ok = f == 0 ? (acc ? (ok2 && ok3) : (ok2 && ok3 && ok4)) : (f == 1 ? (acc ? ok3 : (ok3 && ok4)) : (acc ? true : ok4));
-    if (fi != 0 && need_ok) {
-      v0 = f == 0 ? (acc ? n0 : n2) : n0;
-      v1 = f == 0 ? (acc ? n2 : n3) : (f == 1 ? (acc ? n1 : n3) : n1);
-      v2 = f == 2 ? (acc ? n2 : n4) : (acc ? n3 : n4);
-      s0 = acc ? p3 : p4;
-      s1 = acc ? q3 : q4;
-      return;
-    }
-    s0 = a0; // replay serially from the start of the call
-    s1 = a1;
-    v0 = normal(zx, zf);
-    v1 = normal(zx, zf);
-    v2 = normal(zx, zf);
+    const Slow3Out o = normal3_slow(a0, a1, s0, s1, w0, w1, w2, zx, zf);
+    v0 = o.v0;
+    v1 = o.v1;
+    v2 = o.v2;
+    s0 = o.s0;
+    s1 = o.s1;
   }
 };
 

@@ -56,7 +56,8 @@ struct WcaGroupSys {
 
   double *px, *py, *pz;
   short *next, *head;
-  int N, lig, ncx, ncy, ncz;
+  int N, lig, ncx, ncy, ncz, my_ncells;
+  unsigned long long my_cells; // this lane's neighbours lig, lig + G, ...: (dx+1) | (dy+1) << 2 | (dz+1) << 4, 6 bits each (up to 7)
   unsigned gmask;
   double Lx, Ly, Lz, sx, sy, sz, rc2; // s* = n* / L* (FAST subcell index)
   double E, err;
@@ -85,6 +86,12 @@ struct WcaGroupSys {
     pz = py + N;
     next = reinterpret_cast<short*>(pz + N);
     head = next + N;
+    my_cells = 0;
+    my_ncells = 0;
+    for (int k = lig; k < 27; k += G_) {
+      my_cells |= (unsigned long long)((k / 9) | (((k / 3) % 3) << 2) | ((k % 3) << 4)) << (6 * my_ncells);
+      my_ncells++;
+    }
   }
   __device__ __forceinline__ void gsync() const { __syncwarp(gmask); }
   __device__ __forceinline__ int ncells() const { return ncx * ncy * ncz; }
@@ -113,10 +120,19 @@ struct WcaGroupSys {
     return v;
   }
   __device__ __forceinline__ double potential(double r2) const { // wca.rs:66-76
-    if (r2 < rc2) {
-      const double s = FAST ? rcp_newton(r2) : 1.0 / r2;
+    if (FAST) {
+      // no branch: most candidates of a lookup lie beyond the cutoff, but with four walkers in a warp some lane is
+      // nearly always inside, so the branch only added divergence.  The argument is clamped so that two overlapping
+      // atoms of a random start (r^2 ~ 1e-6) still give a finite number where the reference does.
+      const double s = rcp_newton(r2 > 1e-300 ? r2 : 1e-300);
       const double s3 = s * s * s;
-      return FAST ? fma(4.0, fma(s3, s3, -s3), 1.0) : 4.0 * (s3 * s3 - s3) + 1.0;
+      const double u = fma(4.0, fma(s3, s3, -s3), 1.0);
+      return r2 < rc2 ? u : 0.0;
+    }
+    if (r2 < rc2) {
+      const double s = 1.0 / r2;
+      const double s3 = s * s * s;
+      return 4.0 * (s3 * s3 - s3) + 1.0;
     }
     return 0.0;
   }
@@ -134,43 +150,47 @@ struct WcaGroupSys {
     return v;
   }
 
-  // neighbour subcell number k (0..26) of (cx, cy, cz): its list head and the image shift of its atoms
-  __device__ __forceinline__ int neighbour(int k, int cx, int cy, int cz, double& shx, double& shy, double& shz) const {
-    int qx = cx + k / 9 - 1, qy = cy + (k / 3) % 3 - 1, qz = cz + k % 3 - 1;
-    shx = shy = shz = 0.0;
-    if (qx < 0) {
-      qx += ncx;
-      shx = -Lx;
-    } else if (qx >= ncx) {
-      qx -= ncx;
-      shx = Lx;
-    }
-    if (qy < 0) {
-      qy += ncy;
-      shy = -Ly;
-    } else if (qy >= ncy) {
-      qy -= ncy;
-      shy = Ly;
-    }
-    if (qz < 0) {
-      qz += ncz;
-      shz = -Lz;
-    } else if (qz >= ncz) {
-      qz -= ncz;
-      shz = Lz;
-    }
+  // neighbour subcell number k (0..26) of (cx, cy, cz): its list and the image shift of its atoms (optcell.rs:135-157:
+  // -L when the neighbour wrapped below 0, +L when it wrapped past the last subcell).  Branch-free.
+  __device__ __forceinline__ int neighbour_d(int dx, int dy, int dz, int cx, int cy, int cz, double& shx, double& shy, double& shz) const {
+    int qx = cx + dx, qy = cy + dy, qz = cz + dz;
+    const bool xl = qx < 0, xh = qx >= ncx, yl = qy < 0, yh = qy >= ncy, zl = qz < 0, zh = qz >= ncz;
+    qx += xl ? ncx : (xh ? -ncx : 0);
+    qy += yl ? ncy : (yh ? -ncy : 0);
+    qz += zl ? ncz : (zh ? -ncz : 0);
+    shx = xl ? -Lx : (xh ? Lx : 0.0);
+    shy = yl ? -Ly : (yh ? Ly : 0.0);
+    shz = zl ? -Lz : (zh ? Lz : 0.0);
     return flat(qx, qy, qz);
   }
+  __device__ __forceinline__ int neighbour(int k, int cx, int cy, int cz, double& shx, double& shy, double& shz) const {
+    return neighbour_d(k / 9 - 1, (k / 3) % 3 - 1, k % 3 - 1, cx, cy, cz, shx, shy, shz);
+  }
   // Every candidate the reference's `maybe_interacting_atoms_excluding(r, exclude)` returns for a position in subcell
-  // (cx, cy, cz) (optcell.rs:93-110): f(j, image position).  The group's lanes share the 27 lists.
+  // (cx, cy, cz) (optcell.rs:93-110): f(j, image position).  The group's lanes share the 27 lists: lane l walks
+  // neighbours l, l + G, ... whose offsets it keeps packed in `my_cells` (2 bits per axis, 6 bits per neighbour).
+  // Two of the lane's lists are walked side by side: the two pointer chases (head -> next -> next, ~30 cycles of
+  // shared-memory latency per hop) overlap, and the loop runs max(len_a, len_b) times instead of len_a + len_b.  A
+  // list that has run out keeps feeding atom 0 with skip = true.
   template <class F>
   __device__ __forceinline__ void visit(int cx, int cy, int cz, int exclude, F&& f) const {
-    for (int k = lig; k < 27; k += G) {
-      double shx, shy, shz;
-      const int q = neighbour(k, cx, cy, cz, shx, shy, shz);
-      for (int j = head[q]; j >= 0; j = next[j]) {
-        if (j == exclude) continue;
-        f(px[j] + shx, py[j] + shy, pz[j] + shz);
+    unsigned long long cells = my_cells;
+#pragma unroll 1
+    for (int r = 0; r < my_ncells; r += 2, cells >>= 12) {
+      double ax, ay, az, bx, by, bz;
+      const int qa = neighbour_d((int)(cells & 3ull) - 1, (int)((cells >> 2) & 3ull) - 1, (int)((cells >> 4) & 3ull) - 1, cx, cy, cz, ax, ay, az);
+      const int qb = neighbour_d((int)((cells >> 6) & 3ull) - 1, (int)((cells >> 8) & 3ull) - 1, (int)((cells >> 10) & 3ull) - 1, cx, cy, cz, bx, by, bz);
+      int ja = head[qa];
+      int jb = r + 1 < my_ncells ? head[qb] : -1; // (bits past the lane's last neighbour decode to offset -1: a valid cell, not used)
+      while ((ja & jb) >= 0 || ja >= 0 || jb >= 0) {
+        const int ia = ja >= 0 ? ja : 0, ib = jb >= 0 ? jb : 0;
+        const double xa = px[ia] + ax, ya = py[ia] + ay, za = pz[ia] + az;
+        const double xb = px[ib] + bx, yb = py[ib] + by, zb = pz[ib] + bz;
+        const int na = next[ia], nb = next[ib];
+        f(ja < 0 || ja == exclude, xa, ya, za);
+        f(jb < 0 || jb == exclude, xb, yb, zb);
+        ja = ja >= 0 ? na : -1;
+        jb = jb >= 0 ? nb : -1;
       }
     }
   }
@@ -239,22 +259,22 @@ struct WcaGroupSys {
     double snew = 0.0, sold = 0.0;
     const double ttx = tx, tty = ty, ttz = tz;
     if (ch_cnew == ch_cold) { // one walk over the 27 lists serves both sums
-      visit(cx, cy, cz, which, [&](double ix, double iy, double iz) {
+      visit(cx, cy, cz, which, [&](bool skip, double ix, double iy, double iz) {
         const double ax = ix - ttx, ay = iy - tty, az = iz - ttz;
         const double bx = ix - fx, by = iy - fy, bz = iz - fz;
         const double rn = FAST ? fma(az, az, fma(ay, ay, ax * ax)) : ax * ax + ay * ay + az * az;
         const double ro = FAST ? fma(bz, bz, fma(by, by, bx * bx)) : bx * bx + by * by + bz * bz;
-        snew += potential(rn);
-        sold += potential(ro);
+        snew += potential(skip ? 1e300 : rn); // the moved atom itself is not a neighbour (`_excluding`)
+        sold += potential(skip ? 1e300 : ro);
       });
     } else {
-      visit(cx, cy, cz, which, [&](double ix, double iy, double iz) {
+      visit(cx, cy, cz, which, [&](bool skip, double ix, double iy, double iz) {
         const double ax = ix - ttx, ay = iy - tty, az = iz - ttz;
-        snew += potential(FAST ? fma(az, az, fma(ay, ay, ax * ax)) : ax * ax + ay * ay + az * az);
+        snew += potential(skip ? 1e300 : (FAST ? fma(az, az, fma(ay, ay, ax * ax)) : ax * ax + ay * ay + az * az));
       });
-      visit(ox, oy, oz, which, [&](double ix, double iy, double iz) {
+      visit(ox, oy, oz, which, [&](bool skip, double ix, double iy, double iz) {
         const double bx = ix - fx, by = iy - fy, bz = iz - fz;
-        sold += potential(FAST ? fma(bz, bz, fma(by, by, bx * bx)) : bx * bx + by * by + bz * bz);
+        sold += potential(skip ? 1e300 : (FAST ? fma(bz, bz, fma(by, by, bx * bx)) : bx * bx + by * by + bz * bz));
       });
     }
     snew = group_sum(snew);
@@ -345,7 +365,7 @@ struct WcaGroupSys {
       int cx, cy, cz;
       subcell(x, y, z, cx, cy, cz);
       double dabse = 0.0;
-      visit(cx, cy, cz, -1, [&](double ix, double iy, double iz) { // Wca::add_atom_at, wca.rs:104-116
+      visit(cx, cy, cz, -1, [&](bool, double ix, double iy, double iz) { // Wca::add_atom_at, wca.rs:104-116
         const double ax = ix - x, ay = iy - y, az = iz - z;
         dabse += potential(FAST ? fma(az, az, fma(ay, ay, ax * ax)) : ax * ax + ay * ay + az * az);
       });

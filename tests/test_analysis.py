@@ -2,6 +2,7 @@
 import os
 
 import numpy as np
+import pytest
 
 from sad_monte_carlo_b200 import analysis
 
@@ -89,3 +90,50 @@ def test_lj31_heat_capacity_converges_with_moves():
         errs.append(np.abs(err).mean())
     assert errs[0] > errs[1] > errs[2]
     assert errs[2] < 0.01
+
+
+# ---- exact bin weights of the analytic systems and the DOS gate (sad_monte_carlo_b200.analysis) ---------------------------
+
+def test_fake_bin_weights_integrate_the_exact_dos_over_each_bin():
+    lo, w, n = -0.025, 0.01, 106  # bins centred on multiples of the width: half bins at E = 0 and E = 1
+    lin = analysis.fake_bin_weights("linear", lo, w, n)
+    assert np.isclose(lin.sum(), 1.0) and np.isclose(lin[2], 0.005) and np.isclose(lin[50], 0.01) and lin[1] == 0.0
+    quad = analysis.fake_bin_weights("quadratic", lo, w, n, 3)
+    E = lo + (np.arange(n) + 0.5) * w
+    inside = (E > 0.05) & (E < 0.95)
+    assert np.allclose(quad[inside], 1.5 * np.sqrt(E[inside]) * w, rtol=2e-3)  # analyze-boundaries.py:24-25 at the centre
+    assert np.isclose(quad.sum(), 1.0)
+
+
+@pytest.mark.parametrize("barrier", [0.0, 0.1, 0.2])
+def test_two_wells_closed_form_equals_quadrature_of_find_energy(barrier):
+    """two-wells/system.py:86-90 (sum of two hypersphere wells) is EXACT for the geometry of two_wells.rs:266-315 at
+    every barrier height: the lens the wells share inside the big sphere reappears, mirrored, in the small sphere."""
+    N, h, r2 = 12, 1.1, 0.5
+    lo, w, n = -1.125, 0.05, 23
+    exact = analysis.two_wells_bin_weights(lo, w, n, N, h, r2)
+    quad = analysis.two_wells_bin_weights_quadrature(lo, w, n, N, h, r2, barrier, grid=6000)
+    m = (exact > 0) & (quad > 0)
+    assert m.sum() >= 20
+    d = np.log(quad[m]) - np.log(exact[m])
+    d -= d[-3]
+    assert np.abs(d).max() < 1.5e-3  # the midpoint rule's own error at this grid; 3e-4 at grid 8000
+
+
+def test_dos_gate_recovers_a_planted_error():
+    n, groups, per = 60, 4, 100
+    weights = analysis.fake_bin_weights("quadratic", -0.025, 0.02, n, 3)
+    rng = np.random.default_rng(3)
+    folds = []
+    for g in range(groups):
+        S = np.where(weights > 0, np.log(np.where(weights > 0, weights, 1.0)), 0.0) + 7.0 + 0.01 * np.sin(np.arange(n))
+        cnt = np.where(weights > 0, per, 0).astype(np.float64)
+        cnt[40:] = 0.5 * per  # covered by half of the walkers only: not gated
+        folds.append({"lnw_sum": (S + 1e-3 * rng.standard_normal(n)) * cnt, "lnw_count": cnt})
+    r = analysis.dos_gate(folds, groups, per, weights)
+    gated = r["mask"]
+    assert gated.sum() == r["n_bins"] and not gated[40:].any() and gated[5:40].all()
+    want = 0.01 * np.sin(np.arange(n))[gated]
+    want = want - want.mean()
+    assert abs(r["rms_all"] - np.sqrt(np.mean(want ** 2))) < 5e-4
+    assert r["rms_sem"] < 1e-3

@@ -34,7 +34,12 @@ def cases(which):
             out.append(("fake-quadratic d=3 dE=%g" % de, dict(system="fake", fake_function=_abi.FAKE_QUADRATIC, N=3, energy_bin=de,
                                                               move_value=0.05, sad_min_T=0.001, bin_window_lo=-2 * de, bin_window_hi=1 + 2 * de),
                         lambda lo, w, n: analysis.fake_bin_weights("quadratic", lo, w, n, 3)))
-    if "two-wells" in which:
+    if "two-wells-bigstep" in which:  # not a reference parameter set: a five times larger step, to see the same gate converge sooner
+        out.append(("two-wells T-trans-1 barrier=0 dE=1e-3 scale=5e-2",
+                    dict(system="two-wells", N=12, tw_h2_to_h1=1.1, tw_barrier_over_h1=0.0, tw_r2=0.5, sad_min_T=0.001,
+                         energy_bin=1e-3, move_value=5e-2),
+                    lambda lo, w, n: analysis.two_wells_bin_weights(lo, w, n, 12, 1.1, 0.5)))
+    if "two-wells" in [x for x in which if x == "two-wells"]:
         for barrier in (0.0, 0.1):
             out.append(("two-wells T-trans-1 barrier=%g dE=1e-3 scale=1e-2" % barrier,
                         dict(system="two-wells", N=12, tw_h2_to_h1=1.1, tw_barrier_over_h1=barrier, tw_r2=0.5, sad_min_T=0.001,
