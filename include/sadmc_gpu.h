@@ -263,6 +263,14 @@ int sadmc_set_walker_bins(sadmc_engine* e, uint32_t w, const sadmc_walker_state*
                           const double* extra_total, const uint64_t* extra_count);
 int sadmc_resume(sadmc_engine* e, uint64_t moves);
 
+/* ---- fixed weights: a production run -------------------------------------------------
+ * Every walker's ln w := lnw_window[j] for window bin j (n must equal sadmc_window's nbins).  With
+ * SADMC_METHOD_SAMC and samc_t0 = 0 (gamma = t0 / t = 0, energy.rs:816-820) the weights then never change: all walkers
+ * sample the same multicanonical ensemble, their histograms add up, and S(E) = ln w(E) + ln H(E) + const holds without
+ * any bias from the weight-learning phase -- the many-walker counterpart of the reference's WL production mode
+ * (energy.rs:649-655).  tools/lj31_production.py uses it for the heat capacity of LJ31. */
+int sadmc_set_lnw(sadmc_engine* e, const double* lnw_window, uint32_t n);
+
 /* ---- window geometry ---------------------------------------------------- */
 /* Device window: bin j of every walker covers [lo + j*width, lo + (j+1)*width). */
 int sadmc_window(sadmc_engine* e, double* lo, double* width, uint32_t* nbins);

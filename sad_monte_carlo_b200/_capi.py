@@ -39,6 +39,7 @@ PROTOTYPES = {
     "sadmc_set_rngs": (C.c_int, [vp, u64p]),
     "sadmc_set_walker_bins": (C.c_int, [vp, C.c_uint32, C.POINTER(WalkerState), u64p, u64p, f64p, f64p, f64p, u64p, u8p, u64p, f64p, u64p]),
     "sadmc_resume": (C.c_int, [vp, C.c_uint64]),
+    "sadmc_set_lnw": (C.c_int, [vp, f64p, C.c_uint32]),
     "sadmc_window": (C.c_int, [vp, f64p, f64p, C.POINTER(C.c_uint32)]),
     "sadmc_cell_box": (C.c_int, [vp, f64p, f64p]),
     "sadmc_fold_select": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_int]),

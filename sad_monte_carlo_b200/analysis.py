@@ -269,3 +269,47 @@ def dos_gate(folds, groups, per_group, weights, min_fraction=0.9, min_weight=0.0
     return {"rms_mean": float(rms.mean()), "rms_sem": float(rms.std(ddof=1) / np.sqrt(groups)) if groups > 1 else 0.0,
             "rms_all": float(np.sqrt(np.mean(d * d))), "n_bins": int(common.sum()),
             "worst": float(np.abs(d).max()) if common.any() else float("nan"), "residual": d, "mask": common}
+
+
+def cv_low_edge_weight(folds, T, min_fraction=0.5, edge_bins=20):
+    """How much of the canonical distribution at temperature T sits in the lowest `edge_bins` covered bins of the
+    all-walker mean entropy: where this is not small, energies below the covered range (below the walkers' too_lo)
+    would contribute and Cv(T) from the covered bins alone is not converged."""
+    G = int(folds["groups"])
+    cnt = sum(np.asarray(folds["lnw_count_%d" % g], dtype=np.float64) for g in range(G))
+    tot = sum(np.asarray(folds["lnw_sum_%d" % g], dtype=np.float64) for g in range(G))
+    ok = cnt >= min_fraction * int(folds["walkers"])
+    nb = len(cnt)
+    E = float(folds["window_lo"]) + (np.arange(nb) + 0.5) * float(folds["width"])
+    S = tot[ok] / cnt[ok]
+    Eo = E[ok]
+    out = []
+    for t in np.atleast_1d(T):
+        a = S - Eo / t
+        P = np.exp(a - a.max())
+        P /= P.sum()
+        out.append(P[:edge_bins].sum())
+    return np.array(out), float(Eo.min())
+
+
+def cv_from_production(run, T, min_count=1.0):
+    """Cv(T) from a fixed-weight production run (tools/lj31_production.py): per interleaved walker group
+    S_g(E) = ln w(E) + ln H_g(E) on the bins the group visited; ensemble mean, standard error, per-group curves."""
+    w = np.asarray(run["weights"], dtype=np.float64)
+    H = np.asarray(run["histogram_groups"], dtype=np.float64)
+    nb = len(w)
+    E = float(run["window_lo"]) + (np.arange(nb) + 0.5) * float(run["width"])
+    cvs = []
+    for g in range(H.shape[0]):
+        ok = H[g] >= min_count
+        cvs.append(heat_capacity(T, E[ok], w[ok] + np.log(H[g][ok])))
+    cvs = np.array(cvs)
+    return cvs.mean(0), cvs.std(0, ddof=1) / np.sqrt(H.shape[0]), cvs
+
+
+def cv_production_vs_reference(run, ref_csv, T_min, T_max=np.inf):
+    """plotting/final_heat_capacity.py:185-194 for a production run: (T, Cv, sem, Cv_ref, Err) at the curve's temperatures."""
+    Tr, Cr = load_lj31_reference(ref_csv)
+    m = (Tr >= T_min) & (Tr <= T_max)
+    mean, sem, _ = cv_from_production(run, Tr[m])
+    return Tr[m], mean, sem, Cr[m], (mean - Cr[m]) / Cr[m]

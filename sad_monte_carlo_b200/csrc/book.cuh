@@ -295,8 +295,22 @@ struct Book {
     if (i < rt_fill_lo || i >= rt_fill_hi) return true; // created after the last bulk fill (energy.rs:417,431)
     return stamp > rt_fill_time ? true : (rt_fill_val != 0);
   }
-  // make bin i the cached current bin from an already loaded record
-  __device__ __forceinline__ void adopt_bin(int i, const BinLo& l, const BinHi& h) {
+  // the `extra` accumulators of bin i (data_to_collect systems), requested together with its record: volatile like
+  // load_rec, so that the loads are not sunk to adopt_bin (a second DRAM latency per accepted move)
+  __device__ __forceinline__ void load_extra(int i, double& xt, unsigned long long& xc) const {
+    unsigned long long a, b;
+    asm volatile("ld.global.u64 %0, [%1];" : "=l"(a) : "l"(P.extra_total + side(i)));
+    asm volatile("ld.global.u64 %0, [%1];" : "=l"(b) : "l"(P.extra_count + side(i)));
+    xt = __longlong_as_double((long long)a);
+    xc = b;
+  }
+  // make bin i the cached current bin from an already loaded record (+ already loaded extras, if the system has any)
+  __device__ __forceinline__ void adopt_bin(int i, const BinLo& l, const BinHi& h, double xt, unsigned long long xc) {
+    adopt_bin(i, l, h, false);
+    c_xtot = xt;
+    c_xcnt = xc;
+  }
+  __device__ __forceinline__ void adopt_bin(int i, const BinLo& l, const BinHi& h, bool fetch_extra = true) {
     ci = i;
     c_lnw = l.lnw;
     c_hist = l.hist;
@@ -308,7 +322,7 @@ struct Book {
     c_wlh = h.wl_hist;
     c_visited = visited_flag(i, h.rt_stamp);
     hi_dirty = false;
-    if (P.extra_total) {
+    if (fetch_extra && P.extra_total) {
       c_xtot = P.extra_total[side(i)];
       c_xcnt = P.extra_count[side(i)];
     }

@@ -1029,6 +1029,13 @@ int sadmc_cell_box(sadmc_engine* e, double box_diagonal[3], double* r_cutoff) {
   return 0;
 }
 
+// ---- fixed weights for a production run -------------------------------------------
+__global__ void __launch_bounds__(256) set_lnw_kernel(const DevParams P, const double* lnw) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t w = blockIdx.y;
+  if (j < P.cap) P.rec[(size_t)w * P.cap + j].lo.lnw = lnw[j];
+}
+
 // ---- merge for reporting -------------------------------------------------------
 int sadmc_fold_select_ex(sadmc_engine* e, uint32_t first_walker, uint32_t walker_stride, uint32_t walker_count, int sad_range_only) {
   if (!e) return fail(SADMC_ERR_INVALID, "null engine");
@@ -1038,6 +1045,29 @@ int sadmc_fold_select_ex(sadmc_engine* e, uint32_t first_walker, uint32_t walker
   e->fold_sel.stride = walker_stride;
   e->fold_sel.count = walker_count;
   e->fold_sel.sad_range_only = sad_range_only;
+  return 0;
+}
+int sadmc_set_lnw(sadmc_engine* e, const double* lnw_window, uint32_t n) {
+  if (!e || !lnw_window) return fail(SADMC_ERR_INVALID, "null argument");
+  if (n != e->P.cap) return fail(SADMC_ERR_INVALID, "ln w array holds %u bins, the device window %u", n, e->P.cap);
+  CK(cudaSetDevice(e->cfg.device));
+  double* d = nullptr;
+  CK(cudaMalloc(&d, (size_t)n * 8));
+  cudaError_t er = cudaMemcpyAsync(d, lnw_window, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream);
+  if (er == cudaSuccess) {
+    const uint32_t wmax = 65535; // grid.y limit
+    for (uint32_t w0 = 0; w0 < e->P.n_walkers && er == cudaSuccess; w0 += wmax) {
+      DevParams Q = e->P;
+      Q.rec = e->P.rec + (size_t)w0 * e->P.cap;
+      const uint32_t nw = e->P.n_walkers - w0 < wmax ? e->P.n_walkers - w0 : wmax;
+      set_lnw_kernel<<<dim3((n + 255) / 256, nw), 256, 0, e->stream>>>(Q, d);
+      er = cudaGetLastError();
+      e->launches++;
+    }
+  }
+  if (er == cudaSuccess) er = cudaStreamSynchronize(e->stream);
+  cudaFree(d);
+  if (er != cudaSuccess) return fail(SADMC_ERR_CUDA, "sadmc_set_lnw failed: %s", cudaGetErrorString(er));
   return 0;
 }
 int sadmc_fold_settled(sadmc_engine* e, uint64_t tl_max) {

@@ -45,6 +45,17 @@ struct HasVerify<S, decltype((void)S::VERIFIES)> {
   static constexpr bool value = S::VERIFIES;
 };
 
+// Systems that report `data_to_collect` values (energy.rs:944-946: WCA pressure, two-wells `which`) declare HAS_EXTRA:
+// the move loop then requests the proposed bin's `extra` accumulators together with its record.
+template <class S, class = void>
+struct HasExtra {
+  static constexpr bool value = false;
+};
+template <class S>
+struct HasExtra<S, decltype((void)S::HAS_EXTRA)> {
+  static constexpr bool value = S::HAS_EXTRA;
+};
+
 // Systems whose shared memory is better spent on walkers read the 4 KB ziggurat tables straight from global memory
 // (they stay L1-resident) and declare ZIG_GLOBAL.
 template <class S, class = void>
@@ -375,7 +386,14 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
 #else
     bool other_bin = proposing && i2 != i1;
 #endif
-    if (other_bin) load_rec(bk.rec + i2, r2, h2);
+    double x2tot = 0.0;
+    unsigned long long x2cnt = 0;
+    if (other_bin) {
+      load_rec(bk.rec + i2, r2, h2);
+      if constexpr (HasExtra<Sys>::value) {
+        if (P.extra_total) bk.load_extra(i2, x2tot, x2cnt);
+      }
+    }
     // ... and what does not depend on it is computed while it is in flight: next move's sqrt(1/moves),
     recent_next = sqrt(1.0 / (double)(moves + 1));
     // the previous move's bookkeeping (DEFER),
@@ -394,7 +412,12 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
 #ifndef SADMC_ABL_NOLOAD
             other_bin = i2 != i1;
 #endif
-            if (other_bin) load_rec(bk.rec + i2, r2, h2);
+            if (other_bin) {
+              load_rec(bk.rec + i2, r2, h2);
+              if constexpr (HasExtra<Sys>::value) {
+                if (P.extra_total) bk.load_extra(i2, x2tot, x2cnt);
+              }
+            }
           }
         } else if (bk.wrote_bins && other_bin) {
           load_rec(bk.rec + i2, r2, h2); // the range extension may have rewritten ln w of the requested bin
@@ -440,7 +463,10 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
       if (inew != i1) {
         bk.flush();
         if (inew == i2) {
-          bk.adopt_bin(i2, r2, h2);
+          if (HasExtra<Sys>::value && P.extra_total)
+            bk.adopt_bin(i2, r2, h2, x2tot, x2cnt);
+          else
+            bk.adopt_bin(i2, r2, h2);
         } else if (inew < bk.lo || inew >= bk.lo + bk.len) {
           bk.status = SADMC_ERR_WINDOW;
           halted = true;

@@ -36,6 +36,7 @@ struct CellFluidSys {
 #endif
   static constexpr int MIN_BLOCKS = SADMC_FLUID_MIN_BLOCKS;
   static constexpr bool COOP = false;
+  static constexpr bool HAS_EXTRA = !SW; // WCA reports the pressure (wca.rs:202-218)
   static constexpr bool VERIFIES = true; // overrides System::verify_energy: run at the cadence of energy.rs:907-911
   __device__ __forceinline__ void set_cooperative(bool) {}
   __device__ __forceinline__ void finish_move() {}

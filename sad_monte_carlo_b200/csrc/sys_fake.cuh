@@ -113,6 +113,7 @@ struct TwoWellsSys {
   static constexpr int BLOCK = 128;
   static constexpr int MIN_BLOCKS = 4;
   static constexpr bool COOP = false;
+  static constexpr bool HAS_EXTRA = true; // `which` well, two_wells.rs:408-418
   __device__ __forceinline__ void set_cooperative(bool) {}
   __device__ __forceinline__ void finish_move() {}
   double pos[TW_MAX_DIM];

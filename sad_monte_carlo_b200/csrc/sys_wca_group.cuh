@@ -48,6 +48,7 @@ struct WcaGroupSys {
   static constexpr bool COOP = false;
   static constexpr bool VERIFIES = true; // wca.rs:237-251
   static constexpr bool ZIG_GLOBAL = true;
+  static constexpr bool HAS_EXTRA = true; // the pressure, wca.rs:202-218
   // how much larger than the reference's the error allowance is before the energy is re-summed (FAST)
   static constexpr double RELAX = FAST ? 6553.6 : 1.0;
 

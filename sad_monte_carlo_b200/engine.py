@@ -180,6 +180,11 @@ class WalkerEngine:
         """Instead of start(): continue from restored walkers at move count `moves`."""
         self._check(self.L.sadmc_resume(self.h, int(moves)))
 
+    def set_lnw(self, lnw_window):
+        """Every walker's ln w := the window-aligned array (fixed weights: use with method "samc", samc_t0 = 0)."""
+        a = np.ascontiguousarray(lnw_window, dtype=np.float64)
+        self._check(self.L.sadmc_set_lnw(self.h, _p(a, f64p), a.size))
+
     def window(self):
         lo, width, n = C.c_double(), C.c_double(), C.c_uint32()
         self._check(self.L.sadmc_window(self.h, C.byref(lo), C.byref(width), C.byref(n)))

@@ -137,3 +137,56 @@ def test_dos_gate_recovers_a_planted_error():
     want = want - want.mean()
     assert abs(r["rms_all"] - np.sqrt(np.mean(want ** 2))) < 5e-4
     assert r["rms_sem"] < 1e-3
+
+
+# ---- round 2: canonical cross-check and the run at the headline SAD parameters (tests/golden/lj31_cv_run_r02) -----------
+
+def _r02(name):
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lj31_cv_run_r02", name)
+
+
+def test_lj31_canonical_metropolis_on_the_engine_matches_restmc_and_the_sad_run():
+    """Sampler-independent check of the physics: plain Metropolis sampling at fixed T on the same engine (18 944 walkers x
+    1e7 moves per temperature, tools/lj31_canonical.py; Cv from the walkers' exact energy moments, no entropy, no bins).
+    It reproduces RESTMC (`LJ31_Cv_Reference_alt.csv`, the curve with the reference's 2.5 sigma container) to 2 % and
+    t-REM to 2 % for T in [0.2, 0.4], agrees with the round-1 SAD run (min_T 0.1, bin 0.1) to 1.5 %, and lies 2-13 % below
+    `LJ31_Cv_Reference.csv` (REM) exactly where RESTMC / t-REM do: the gap to the CSV BASELINE.json names is between the
+    literature curves (different constraining volume / constraint), not between the engine and the model."""
+    import json
+    canon = [c for c in json.load(open(_r02("r02_lj31_canonical.json"))) if c["T"] >= 0.2]  # T = 0.1 does not equilibrate from a quench
+    T = np.array([c["T"] for c in canon])
+    cv = np.array([c["Cv"] for c in canon])
+    sem = np.array([c["Cv_sem"] for c in canon])
+    assert len(T) == 5 and (sem / cv).max() < 1e-3
+    for name, tol in (("LJ31_Cv_Reference_alt.csv", 0.02), ("tRem_Ref.csv", 0.02)):
+        Tr, Cr = analysis.load_lj31_reference(_lit(name))
+        err = (cv - np.interp(T, Tr, Cr)) / np.interp(T, Tr, Cr)
+        assert np.abs(err).max() < tol, (name, err)
+    Tr, Cr = analysis.load_lj31_reference(_lit("LJ31_Cv_Reference.csv"))
+    err = (cv - np.interp(T, Tr, Cr)) / np.interp(T, Tr, Cr)
+    Ta, Ca = analysis.load_lj31_reference(_lit("LJ31_Cv_Reference_alt.csv"))
+    gap = (np.interp(T, Ta, Ca) - np.interp(T, Tr, Cr)) / np.interp(T, Tr, Cr)
+    assert -0.16 < err.min() < -0.10 and np.abs(err - gap).max() < 0.02  # the literature's own gap, reproduced
+    sad, _, _ = analysis.cv_from_grouped_folds(_cv_run("1e+08"), T)
+    assert np.abs(sad / cv - 1.0).max() < 0.015
+
+
+def test_lj31_sad_at_the_headline_parameters_is_still_converging_after_2e8_moves_per_walker():
+    """run-lj-clusters.sh:53 parameters (min_T 0.01, energy bin 0.01: 13 365 bins), 37 888 walkers x 2e8 moves on one
+    B200 (7.6e12 moves, 15 min).  Stated result, not a pass: the merged SAD entropy is converged only where every walker's
+    range was established early -- Cv within 5 % of t-REM for T >= 0.32 -- and far off below (+83 % at T = 0.21), improving
+    monotonically with moves per walker.  A SAD walker needs many round trips through its 13 000 bins; the reference's own
+    runs use --max-iter 1e12 per walker, and no number of parallel walkers shortens one walker's learning."""
+    errs = []
+    for tag in ("1e+07", "3e+07", "1e+08", "2e+08"):
+        d = np.load(_r02("lj31_cv_headline_%s.npz" % tag))
+        T, cv, sem, ref, err = analysis.cv_error_vs_reference(d, _lit("tRem_Ref.csv"), 0.15, 0.41)
+        errs.append((np.abs(err).max(), np.abs(err[T >= 0.32]).max()))
+    worst = [e[0] for e in errs]
+    assert worst[1] >= worst[2] >= worst[3] and worst[3] < 0.9 and worst[0] > 1.4   # 1.59 -> 1.53 -> 1.28 -> 0.835
+    assert errs[3][1] < 0.05                                                          # T >= 0.32 at 2e8: 4.6 %
+    d = np.load(_r02("lj31_cv_headline_2e+08.npz"))
+    assert np.median(d["too_lo"]) < -132.8 and float(d["moves"]) == 2e8
+    # against the CSV BASELINE.json names, same temperatures: the REM curve's own offset on top
+    T, cv, sem, ref, err = analysis.cv_error_vs_reference(d, _lit("LJ31_Cv_Reference.csv"), 0.32, 0.41)
+    assert np.abs(err).max() < 0.16

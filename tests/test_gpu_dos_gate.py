@@ -78,3 +78,44 @@ def test_fake_linear_coarse_bins_range_creep():
     assert r["n_bins"] >= 95 and r["rms_all"] < 0.05, r["rms_all"]  # measured 0.024 (0.016 at 1e7)
     low = _gate(eng, w, energy_range=(0.02, 0.4))
     assert low["n_bins"] >= 35 and low["rms_all"] < 3e-3, low["rms_all"]
+
+
+def test_two_wells_sampler_against_the_exact_dos():
+    """two-wells "T-trans-1" (N = 12, h2/h1 = 1.1, r2 = 0.5, barrier 0).  SAD's own convergence on this system takes far
+    longer than a test may run (profiles/r02_dos_gate.md: RMS 0.30 after 1e7 moves per walker at the reference's step
+    1e-2), so the gate here separates the two questions.  (1) The SAMPLER -- proposal, `find_energy`, accept test, histogram
+    -- against the exact density of states (two-wells/system.py:86-90, exact for this geometry): a fixed-weight production
+    run (weights = exact ln D with a deliberate tilt) must reweight to the exact DOS.  (2) SAD's learning on it converges:
+    the error falls between 3e5 and 1e6 moves."""
+    N, h, r2 = 12, 1.1, 0.5
+    kw = dict(N=N, tw_h2_to_h1=h, tw_barrier_over_h1=0.0, tw_r2=r2, energy_bin=1e-2, move_value=5e-2, n_walkers=WALKERS, seed=0)
+    eng = WalkerEngine(make_config("two-wells", "samc", samc_t0=0.0, **kw))
+    lo, width, nb = eng.window()
+    E = lo + (np.arange(nb) + 0.5) * width
+    exact = analysis.two_wells_bin_weights(lo, width, nb, N, h, r2)
+    pos = exact > 0
+    w = np.zeros(nb)
+    w[pos] = np.log(exact[pos]) + 2.0 * (E[pos] + 0.5)
+    w[~pos] = w[pos].min() - 5.0
+    eng.set_lnw(w)
+    eng.run(300_000)
+    h0 = eng.fold()["histogram"].astype(np.float64)
+    eng.run(700_000)
+    H = eng.fold()["histogram"].astype(np.float64) - h0
+    ok = pos & (H > 0) & (E > -1.05)  # the lowest bins hold 1e-12 of the volume: too few visits to gate
+    d = w[ok] + np.log(H[ok]) - np.log(exact[ok])
+    d -= d.mean()
+    rms = float(np.sqrt(np.mean(d * d)))
+    print("two-wells fixed-weight production: bins %d rms %.4f worst %.4f" % (ok.sum(), rms, np.abs(d).max()))
+    assert ok.sum() >= 95 and rms < 0.05, rms
+    eng.close()
+    # (2) SAD's learning, reference parameters except the coarser bin and larger step of this test
+    eng = WalkerEngine(make_config("two-wells", "sad", sad_min_T=0.001, **kw))
+    lo, width, nb = eng.window()
+    exact = analysis.two_wells_bin_weights(lo, width, nb, N, h, r2)
+    eng.run(300_000)
+    r1 = _gate(eng, exact)
+    eng.run(700_000)
+    r2_ = _gate(eng, exact)
+    print("two-wells SAD: rms %.3f -> %.3f over %d bins" % (r1["rms_all"], r2_["rms_all"], r2_["n_bins"]))
+    assert r2_["rms_all"] < r1["rms_all"]

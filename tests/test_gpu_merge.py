@@ -242,3 +242,32 @@ def test_in_loop_verify_energy_runs_at_the_reference_cadence_and_halts_a_corrupt
     g, s = eng.walker(2), o.walker()
     assert s.bins_len ** 2 * 1000 <= 600_000  # the cadence was reached
     assert g.status == 0 and (g.rng_s0, g.rng_s1, g.energy) == (s.rng_s0, s.rng_s1, s.energy)
+
+
+def test_fixed_weights_production_run_reweights_to_the_exact_dos():
+    """sadmc_set_lnw + Method::Samc with t0 = 0: the weights never change (gamma = 0), every walker samples the same
+    multicanonical ensemble, and S = ln w + ln H recovers the exact density of states whatever the weights are --
+    here deliberately wrong ones (a tilt of +-1.5 across the range)."""
+    from sad_monte_carlo_b200 import analysis
+    W = 16384
+    cfg = make_config("fake", "samc", fake_function=_abi.FAKE_QUADRATIC, N=3, samc_t0=0.0, energy_bin=0.02, move_value=0.1, n_walkers=W,
+                      seed=9, bin_window_lo=-0.04, bin_window_hi=1.04)
+    eng = WalkerEngine(cfg)
+    lo, width, nb = eng.window()
+    E = lo + (np.arange(nb) + 0.5) * width
+    exact = analysis.fake_bin_weights("quadratic", lo, width, nb, 3)
+    w = np.where(exact > 0, np.log(np.where(exact > 0, exact, 1.0)), 0.0) + 3.0 * (E - 0.5)  # exact ln D, tilted
+    eng.set_lnw(w)
+    eng.run(20000)   # equilibration from the common start at the origin
+    h0 = eng.fold()["histogram"].astype(np.float64)
+    eng.run(200000)
+    H = eng.fold()["histogram"].astype(np.float64) - h0
+    for wk in (0, W - 1):  # the weights are still exactly what was set
+        s, b = eng.walker(wk), eng.bins(wk)
+        sl = slice(s.window_first, s.window_first + s.bins_len)
+        assert np.array_equal(b["lnw"], w[sl])
+    ok = (exact > 0) & (H > 0)
+    assert ok.sum() >= 50
+    d = w[ok] + np.log(H[ok]) - np.log(exact[ok])
+    d -= d.mean()
+    assert np.sqrt(np.mean(d * d)) < 5e-3 and np.abs(d).max() < 2e-2, (np.sqrt(np.mean(d * d)), np.abs(d).max())
