@@ -147,7 +147,8 @@ typedef struct sadmc_config {
   double bin_window_lo, bin_window_hi;
   int32_t lanes_per_walker; /* LJ: 0 = auto; 32/16/8/4 = that many lanes of a warp cooperate on one walker
                                (registers + shuffles); 1 = one thread per walker, cluster in shared memory.
-                               WCA: 0 = 8; 4/8/16 = lanes sharing a walker's cell-list lookups; 32 = a warp per walker */
+                               WCA: 0 = auto (8 with SADMC_FLAG_FAST_MATH, else 32); 4/8/16 = lanes sharing a walker's cell-list
+                               lookups; 32 = a warp per walker */
   uint32_t flags;
 } sadmc_config;
 

@@ -87,10 +87,12 @@ static int pick_kernels(sadmc_engine* e) {
     case SADMC_SYS_ISING: e->ks = kernels_ising(P); return 0;
     case SADMC_SYS_FAKE: e->ks = kernels_fake(P); return 0;
     case SADMC_SYS_WCA: {
-      // lanes_per_walker: 0 = 8 (the fastest measured), 4 / 8 / 16 = that many lanes share a walker (sys_wca_group.cuh),
+      // lanes_per_walker: 0 = auto (below), 4 / 8 / 16 = that many lanes share a walker (sys_wca_group.cuh),
       // 32 = one warp per walker (sys_cell_fluid.cuh, the kernel the square well uses)
-      const int G = c.lanes_per_walker == 0 ? 8 : c.lanes_per_walker;
       const bool fast = (c.flags & SADMC_FLAG_FAST_MATH) != 0;
+      // auto: the fast tier runs 8 lanes per walker (0.99e9 moves/s at N = 256); with the reference's re-summation of the
+      // whole energy every ~10 accepted moves that sum is the kernel, and a warp per walker does it fastest (1.3e8 vs 0.8e8)
+      const int G = c.lanes_per_walker == 0 ? (fast ? 8 : 32) : c.lanes_per_walker;
       if (G == 32 && !fast) {
         e->ks = kernels_cell_fluid(false, P);
         return 0;

@@ -62,7 +62,12 @@ def test_many_walkers_one_file_each_and_walker_w_is_seed_plus_w(tmp_path):
     base = ["--lj-N", "13", "--lj-radius", "2", "--max-allowed-energy=0", "--sad-min-T", "0.05", "--energy-bin", "0.05",
             "--translation-scale", "0.05", "--max-iter", "2e4", "--quiet", "--lanes-per-walker", "1"]
     run(base + ["--seed", "3", "--num-walkers", "4", "--checkpoint-walkers", "3", "--save-as", "many.cbor"], tmp_path)
-    assert sorted(os.listdir(tmp_path)) == ["many-w%06d.cbor" % w for w in range(3)]
+    # three of four walkers written: the set is marked as partial (and a later --save-as on it refuses to resume)
+    assert sorted(os.listdir(tmp_path)) == ["many-w%06d.cbor" % w for w in range(3)] + ["many.partial"]
+    assert (tmp_path / "many.partial").read_text() == "3 of 4 walkers\n"
+    with pytest.raises(SystemExit) as ei:  # histogram.UsageError
+        run(base + ["--seed", "3", "--num-walkers", "4", "--save-as", "many.cbor"], tmp_path)
+    assert "cannot be resumed" in str(ei.value)
     run(base + ["--seed", "5", "--save-as", "one.cbor"], tmp_path)
     many, one = checkpoint.load(str(tmp_path / "many-w000002.cbor")), checkpoint.load(str(tmp_path / "one.cbor"))
     for k in ("bins", "method", "rng", "system", "accepted_moves"):
