@@ -101,6 +101,14 @@ typedef enum {
 /* EXPERIMENT, with SADMC_FLAG_FAST_MATH and lanes_per_walker = 1, LJ31 / LJ38 only: a helper warp per bookkeeping warp
  * sums half of the pair loop (csrc/sys_lj_paired.cuh).  Same tolerance tier as SADMC_FLAG_FAST_MATH. */
 #define SADMC_FLAG_HELPER_WARPS 8u
+/* The bookkeeping of the reference's `binning` binary instead of `histogram`'s: `EnergyMC` of src/mc/energy_binning.rs
+ * (reject_move 276-321, update_weights 323-503, gamma 507-533, move_once 592-633) over `binning::histogram::Bins`
+ * (src/mc/binning/histogram.rs; `--histogram-bin`, what fake/run-fake.py:25-26 runs).  `energy_bin` is the histogram bin.
+ * Methods: SAD, SAMC, WL, 1/t-WL.  State out: sadmc_get_binning_walker / sadmc_get_binning_bins (sadmc_get_bins,
+ * sadmc_set_walker_bins, sadmc_resume and sadmc_set_lnw are for the energy.rs layout and refuse such an engine).
+ * Built for the one-thread-per-walker systems (Ising, fake, two-wells, erfinv, LJ with lanes_per_walker = 1) and the
+ * warp-per-walker fluids (square well, WCA with lanes_per_walker = 32).  Not built: `binning::linear`, `high_resolution_de`. */
+#define SADMC_FLAG_BINNING 16u
 
 typedef struct sadmc_config {
   uint32_t abi_version; /* = SADMC_ABI_VERSION */
@@ -180,6 +188,30 @@ typedef struct sadmc_walker_state {
   uint32_t _pad;
 } sadmc_walker_state;
 
+/* SADMC_FLAG_BINNING: the non-vector fields of energy_binning.rs's `EnergyMC` (92-126), `Method` (128-148) and
+ * `histogram::Bins` (histogram.rs:99-111), plus the `BinCounts` aggregates (histogram.rs:12-32) that the sampler reads. */
+typedef struct sadmc_binning_state {
+  uint64_t moves, accepted_moves;
+  double acceptance_rate, translation_scale;
+  uint64_t rng_s0, rng_s1;
+  double energy;
+  double bins_min, bins_width; /* Bins::min, Bins::width */
+  double bins_min_e, bins_max_e; /* lowest / highest energy counted so far (histogram.rs:182-187) */
+  uint32_t bins_len;     /* lnw.total.len(): 0 until the first move */
+  uint32_t window_first; /* device window index of bin 0 */
+  int32_t method;        /* current sadmc_method_kind (1/t-WL may have become SAMC, energy_binning.rs:496-498) */
+  int32_t status;
+  /* Sad (energy_binning.rs:131-139): too_lo / too_hi are raw energies, tF an f64 */
+  double too_lo, too_hi, latest_parameter, tF;
+  uint64_t tL, num_states;
+  double samc_t0;  /* Samc */
+  double wl_gamma; /* WL */
+  int32_t wl_inv_t, _pad;
+  uint64_t lnw_max_count, lnw_total_count;  /* bins.lnw.max_count (SAD's old_highest_hist), bins.lnw.total_count */
+  double t_found_max_total;                 /* bins.extra["t_found"].max_total (SAD's tF source) */
+  uint64_t hist_min_count, hist_total_count; /* bins.extra["hist"] (WL flatness) */
+} sadmc_binning_state;
+
 typedef struct sadmc_engine sadmc_engine;
 
 /* ---- lifecycle --------------------------------------------------------- */
@@ -239,6 +271,13 @@ int sadmc_get_bins(sadmc_engine* e, uint32_t w, uint32_t cap, uint64_t* histogra
                    double* lnw, double* energy_total, double* energy_squared_total,
                    uint64_t* round_trips, uint8_t* have_visited_since_maxentropy, uint64_t* wl_hist,
                    double* extra_total, uint64_t* extra_count);
+/* SADMC_FLAG_BINNING engines: scalars and per-bin vectors of walker w in reference index order (element 0 = bin at
+ * bins_min): bins.lnw.{total,count}, bins.extra["energy"|"t_found"].{total,count}, bins.extra["hist"].count (its total
+ * is always 0), and the system's data_to_collect accumulator ("pressure" / "which").  Any pointer may be NULL. */
+int sadmc_get_binning_walker(sadmc_engine* e, uint32_t w, sadmc_binning_state* out);
+int sadmc_get_binning_bins(sadmc_engine* e, uint32_t w, uint32_t cap, double* lnw_total, uint64_t* lnw_count,
+                           double* energy_total, uint64_t* energy_count, double* t_found_total, uint64_t* t_found_count,
+                           uint64_t* hist_count, double* extra_total, uint64_t* extra_count);
 /* System configuration of walker w as f64s.  Layout: LJ/WCA/SW: x0,y0,z0,x1,..
  * (3N), then E, then error (WCA/LJ; 0 for SW).  Fake/ErfInv/TwoWells:
  * position[dim] (+ d_squared for two-wells).  Ising: N*N spins as +-1.0, then E. */

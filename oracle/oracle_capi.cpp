@@ -10,6 +10,7 @@
 #include <thread>
 
 #include "../include/sadmc_gpu.h" // config / state structs only (shared vocabulary with the engine)
+#include "oracle_binning.hpp"
 #include "oracle_mc.hpp"
 
 namespace oracle {
@@ -317,6 +318,125 @@ int oracle_sys_verify_energy(oracle_mc* o) { return o->mc->system->verify_energy
 double oracle_sw_compute_energy_slowly(oracle_mc* o) {
   SquareWell* s = dynamic_cast<SquareWell*>(o->mc->system.get());
   return s ? s->compute_energy_slowly() : NAN;
+}
+
+// ---- the `binning` binary: energy_binning.rs over binning::histogram (oracle_binning.hpp) ----
+struct oracle_bmc {
+  std::unique_ptr<binning::EnergyMC> mc;
+};
+oracle_bmc* oracle_binning_create(const sadmc_config* cfg, uint32_t walker, const double* system_state, size_t n_state,
+                                  uint64_t attempts_override) {
+  try {
+    std::unique_ptr<System> sys = make_system(*cfg, attempts_override);
+    if (system_state) sys->set_state(std::vector<double>(system_state, system_state + n_state));
+    MCParams p = mc_params(*cfg, walker);
+    if (system_state) p.randomize_first = false;
+    oracle_bmc* o = new oracle_bmc;
+    o->mc.reset(new binning::EnergyMC(p, std::move(sys)));
+    return o;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return nullptr;
+  }
+}
+void oracle_binning_destroy(oracle_bmc* o) { delete o; }
+int oracle_binning_reference_test(void) { return binning::reference_test_binning(); }
+int oracle_binning_run(oracle_bmc* o, uint64_t n) {
+  try {
+    for (uint64_t k = 0; k < n; k++) o->mc->move_once();
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+static const binning::BinCounts* find_extra(const binning::Bins& b, const char* name) {
+  auto it = b.extra.find(name);
+  return it == b.extra.end() ? nullptr : &it->second;
+}
+int oracle_binning_get_walker(oracle_bmc* o, sadmc_binning_state* s) {
+  const binning::EnergyMC& m = *o->mc;
+  std::memset(s, 0, sizeof(*s));
+  s->moves = m.moves;
+  s->accepted_moves = m.accepted_moves;
+  s->acceptance_rate = m.acceptance_rate;
+  s->translation_scale = m.translation_scale;
+  s->rng_s0 = m.rng.s0;
+  s->rng_s1 = m.rng.s1;
+  s->energy = m.system->energy();
+  s->bins_min = m.bins.min;
+  s->bins_width = m.bins.width;
+  s->bins_min_e = m.bins.min_e;
+  s->bins_max_e = m.bins.max_e;
+  s->bins_len = (uint32_t)m.bins.lnw.total.size();
+  const binning::Method& me = m.method;
+  s->method = me.kind == binning::B_WL ? (me.inv_t ? SADMC_METHOD_INV_T_WL : SADMC_METHOD_WL) : me.kind;
+  s->status = m.verify_failures ? SADMC_ERR_VERIFY : 0;
+  s->too_lo = me.too_lo;
+  s->too_hi = me.too_hi;
+  s->latest_parameter = me.latest_parameter;
+  s->tF = me.tF;
+  s->tL = me.tL;
+  s->num_states = me.num_states;
+  s->samc_t0 = me.t0;
+  s->wl_gamma = me.gamma;
+  s->wl_inv_t = me.inv_t;
+  s->lnw_max_count = m.bins.lnw.max_count;
+  s->lnw_total_count = m.bins.lnw.total_count;
+  if (const binning::BinCounts* t = find_extra(m.bins, "t_found")) s->t_found_max_total = t->max_total;
+  if (const binning::BinCounts* h = find_extra(m.bins, "hist")) {
+    s->hist_min_count = h->min_count;
+    s->hist_total_count = h->total_count;
+  }
+  return 0;
+}
+int oracle_binning_get_bins(oracle_bmc* o, uint32_t cap, double* lnw_total, uint64_t* lnw_count, double* energy_total, uint64_t* energy_count,
+                            double* t_found_total, uint64_t* t_found_count, uint64_t* hist_count, double* extra_total, uint64_t* extra_count) {
+  const binning::Bins& b = o->mc->bins;
+  const size_t n = b.lnw.total.size();
+  if (cap < n) {
+    g_err = "capacity too small";
+    return -1;
+  }
+  const binning::BinCounts* en = find_extra(b, "energy");
+  const binning::BinCounts* tf = find_extra(b, "t_found");
+  const binning::BinCounts* hi = find_extra(b, "hist");
+  const binning::BinCounts* sx = nullptr; // the system's own data_to_collect key
+  for (const auto& kv : b.extra)
+    if (kv.first != "energy" && kv.first != "t_found" && kv.first != "hist") sx = &kv.second;
+  for (size_t i = 0; i < n; i++) {
+    if (lnw_total) lnw_total[i] = b.lnw.total[i];
+    if (lnw_count) lnw_count[i] = b.lnw.count[i];
+    if (energy_total) energy_total[i] = en ? en->total[i] : 0.0;
+    if (energy_count) energy_count[i] = en ? en->count[i] : 0;
+    if (t_found_total) t_found_total[i] = tf ? tf->total[i] : 0.0;
+    if (t_found_count) t_found_count[i] = tf ? tf->count[i] : 0;
+    if (hist_count) hist_count[i] = hi ? hi->count[i] : 0;
+    if (extra_total) extra_total[i] = sx ? sx->total[i] : 0.0;
+    if (extra_count) extra_count[i] = sx ? sx->count[i] : 0;
+  }
+  return 0;
+}
+// the lazily maintained aggregates of one BinCounts (histogram.rs:12-32); name "" = bins.lnw.  out: min_total, max_total,
+// e_max_total, min_count, max_count, e_max_count, total_count (counts as doubles)
+int oracle_binning_get_aggregates(oracle_bmc* o, const char* name, double* out) {
+  const binning::BinCounts* c = name[0] ? find_extra(o->mc->bins, name) : &o->mc->bins.lnw;
+  if (!c) return -1;
+  out[0] = c->min_total;
+  out[1] = c->max_total;
+  out[2] = c->e_max_total;
+  out[3] = (double)c->min_count;
+  out[4] = (double)c->max_count;
+  out[5] = c->e_max_count;
+  out[6] = (double)c->total_count;
+  return 0;
+}
+size_t oracle_binning_system_len(oracle_bmc* o) { return o->mc->system->get_state().size(); }
+int oracle_binning_get_system(oracle_bmc* o, double* buf, size_t n) {
+  const std::vector<double> s = o->mc->system->get_state();
+  if (n < s.size()) return -1;
+  std::memcpy(buf, s.data(), s.size() * sizeof(double));
+  return 0;
 }
 
 // ---- RNG / math probes for tests ----

@@ -23,6 +23,7 @@ INIT_REFERENCE, INIT_RANDOMIZE, INIT_EXTERNAL = 0, 1, 2
 FLAG_NO_ROUND_TRIPS = 1
 FLAG_SUM_TREE = 2
 FLAG_FAST_MATH = 4
+FLAG_BINNING = 16  # energy_binning.rs bookkeeping over binning::histogram (the `binning` binary)
 FLAG_HELPER_WARPS = 8  # experiment: helper warps for the LJ pair loop (with FLAG_FAST_MATH, lanes_per_walker = 1)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WINDOW, ERR_UNSUPPORTED, ERR_VERIFY = 0, -1, -2, -3, -4, -5
@@ -70,6 +71,29 @@ class WalkerState(C.Structure):
         ("wl_lowest_hist", C.c_uint64), ("wl_highest_hist", C.c_uint64), ("wl_total_hist", C.c_uint64),
         ("wl_hist_len", C.c_uint32), ("wl_inv_t", C.c_int32),
         ("max_S", C.c_double), ("max_S_index", C.c_uint32), ("_pad", C.c_uint32),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}
+
+
+class BinningState(C.Structure):
+    """struct sadmc_binning_state (FLAG_BINNING engines)"""
+    _fields_ = [
+        ("moves", C.c_uint64), ("accepted_moves", C.c_uint64),
+        ("acceptance_rate", C.c_double), ("translation_scale", C.c_double),
+        ("rng_s0", C.c_uint64), ("rng_s1", C.c_uint64),
+        ("energy", C.c_double), ("bins_min", C.c_double), ("bins_width", C.c_double),
+        ("bins_min_e", C.c_double), ("bins_max_e", C.c_double),
+        ("bins_len", C.c_uint32), ("window_first", C.c_uint32),
+        ("method", C.c_int32), ("status", C.c_int32),
+        ("too_lo", C.c_double), ("too_hi", C.c_double), ("latest_parameter", C.c_double), ("tF", C.c_double),
+        ("tL", C.c_uint64), ("num_states", C.c_uint64),
+        ("samc_t0", C.c_double), ("wl_gamma", C.c_double),
+        ("wl_inv_t", C.c_int32), ("_pad", C.c_int32),
+        ("lnw_max_count", C.c_uint64), ("lnw_total_count", C.c_uint64),
+        ("t_found_max_total", C.c_double),
+        ("hist_min_count", C.c_uint64), ("hist_total_count", C.c_uint64),
     ]
 
     def as_dict(self):

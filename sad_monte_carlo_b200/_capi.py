@@ -1,7 +1,7 @@
 """ctypes prototypes for every symbol include/sadmc_gpu.h declares."""
 import ctypes as C
 
-from ._abi import Config, WalkerState
+from ._abi import BinningState, Config, WalkerState
 
 u64p = C.POINTER(C.c_uint64)
 f64p = C.POINTER(C.c_double)
@@ -30,6 +30,8 @@ PROTOTYPES = {
     "sadmc_get_walker": (C.c_int, [vp, C.c_uint32, C.POINTER(WalkerState)]),
     "sadmc_get_energies": (C.c_int, [vp, f64p]),
     "sadmc_get_bins": (C.c_int, [vp, C.c_uint32, C.c_uint32, u64p, u64p, f64p, f64p, f64p, u64p, u8p, u64p, f64p, u64p]),
+    "sadmc_get_binning_walker": (C.c_int, [vp, C.c_uint32, C.POINTER(BinningState)]),
+    "sadmc_get_binning_bins": (C.c_int, [vp, C.c_uint32, C.c_uint32, f64p, u64p, f64p, u64p, f64p, u64p, u64p, f64p, u64p]),
     "sadmc_system_len": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
     "sadmc_get_system": (C.c_int, [vp, C.c_uint32, f64p, C.c_size_t]),
     "sadmc_set_system": (C.c_int, [vp, C.c_uint32, f64p, C.c_size_t]),
@@ -66,4 +68,5 @@ def bind(lib):
         fn.argtypes = args
     lib.sadmc_sizeof_config.restype = C.c_size_t
     lib.sadmc_sizeof_walker_state.restype = C.c_size_t
+    lib.sadmc_sizeof_binning_state.restype = C.c_size_t
     return lib

@@ -105,6 +105,12 @@ struct __align__(16) WalkerRec {
   // often as its neighbours, sets a new histogram record from the half that lies outside the range, energy.rs:540-584.)
   // Written straight to HBM from the rare path; 0 after a resume.
   unsigned long long t_range;
+  // SADMC_FLAG_BINNING (book_binning.cuh): Method::Sad::tF is an f64 there; aggregates of the `extra` BinCounts that the
+  // sampler reads ("t_found".max_total, "hist".min_count with the number of bins that hold it, "hist".total_count) and
+  // Bins::min_e / max_e
+  double b_tF, b_tf_max, b_min_e, b_max_e;
+  unsigned long long b_hist_min, b_hist_total;
+  long long b_hist_nmin;
 };
 
 struct DevParams {

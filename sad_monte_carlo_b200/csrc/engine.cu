@@ -62,7 +62,7 @@ struct sadmc_engine {
   double* d_fold_part = nullptr; // per-chunk partial sums of the two-stage fold
   size_t fold_part_bytes = 0;
   float last_ms = 0.f;
-  FoldSel fold_sel = {0u, 1u, 0u, 0, 0ull};
+  FoldSel fold_sel = {0u, 1u, 0u, 0, 0ull, 0};
   unsigned int* h_halted = nullptr;     // pinned copy of P.halted, refreshed behind every launch
   unsigned int halted_seen[2] = {0, 0}; // what sadmc_sync has reported already
   std::vector<void*> allocs;
@@ -107,6 +107,7 @@ static int pick_kernels(sadmc_engine* e) {
       int G = c.lanes_per_walker;
       const bool fast = (c.flags & SADMC_FLAG_FAST_MATH) != 0;
       // many walkers: one thread per walker, cluster in shared memory (the fastest measured); few: a warp or part of one
+      if (G == 0 && (c.flags & SADMC_FLAG_BINNING)) G = 1; // the energy_binning.rs kernels exist for one thread per walker
       if (G == 0) G = c.n_walkers >= 16384 ? 1 : (c.n_walkers >= 4096 ? 8 : 32);
       if (G == 1 || (fast && (G == 2 || G == 4))) { // configuration in shared memory (sys_lj_thread.cuh)
         if (c.N > 64) return fail(SADMC_ERR_UNSUPPORTED, "lj: shared-memory kernels hold N <= 64 atoms (N=%u)", c.N);
@@ -269,11 +270,19 @@ static int setup_params(sadmc_engine* e) {
   if (is_none(wlo) || is_none(whi))
     return fail(SADMC_ERR_INVALID, "cannot derive the bin window: give bin_window_lo/hi or min/max_allowed_energy");
   if (!(whi > wlo)) return fail(SADMC_ERR_INVALID, "empty bin window [%g, %g)", wlo, whi);
-  e->k_base = (long long)std::floor(wlo / P.width + 0.5) - 1;
+  const bool binning = (c.flags & SADMC_FLAG_BINNING) != 0;
+  if (binning && c.method == SADMC_METHOD_CANONICAL) return fail(SADMC_ERR_INVALID, "energy_binning.rs has no canonical method (MethodParams, energy_binning.rs:22-40)");
+  // energy.rs centres bins on multiples of the width (energy.rs:852), histogram.rs puts their edges there (histogram.rs:149-151)
+  e->k_base = binning ? (long long)std::floor(wlo / P.width) - 1 : (long long)std::floor(wlo / P.width + 0.5) - 1;
   const long long k_top = (long long)std::ceil(whi / P.width + 0.5) + 1;
   const long long cap = k_top - e->k_base + 1;
   if (cap > (1ll << 28)) return fail(SADMC_ERR_INVALID, "bin window needs %lld bins per walker", cap);
   P.cap = (uint32_t)cap;
+  return 0;
+}
+
+static int refuse_binning(const sadmc_engine* e, const char* what) {
+  if (e && (e->cfg.flags & SADMC_FLAG_BINNING)) return fail(SADMC_ERR_INVALID, "%s works on the energy.rs bin layout; this engine runs SADMC_FLAG_BINNING", what);
   return 0;
 }
 
@@ -432,6 +441,7 @@ const char* sadmc_last_error(void) { return g_err.c_str(); }
 int sadmc_abi_version(void) { return SADMC_ABI_VERSION; }
 size_t sadmc_sizeof_config(void) { return sizeof(sadmc_config); }
 size_t sadmc_sizeof_walker_state(void) { return sizeof(sadmc_walker_state); }
+size_t sadmc_sizeof_binning_state(void) { return sizeof(sadmc_binning_state); }
 
 int sadmc_reference_system(const sadmc_config* cfg, double* buf, size_t n, size_t* needed) {
   if (!cfg) return fail(SADMC_ERR_INVALID, "null argument");
@@ -481,6 +491,8 @@ int sadmc_create(const sadmc_config* cfg, sadmc_engine** out) {
     return rc;
   }
   rc = pick_kernels(e);
+  if (!rc && (e->cfg.flags & SADMC_FLAG_BINNING) && !e->ks.move_binning[e->cfg.method])
+    rc = fail(SADMC_ERR_UNSUPPORTED, "SADMC_FLAG_BINNING: no energy_binning.rs kernel for this system / lanes_per_walker / method %d", e->cfg.method);
   if (rc) {
     delete e;
     return rc;
@@ -545,6 +557,9 @@ int sadmc_create(const sadmc_config* cfg, sadmc_engine** out) {
       if (e->ks.move[m])
         CKB(cudaFuncSetAttribute((const void*)e->ks.move[m], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(e->ks.move_smem ? e->ks.move_smem : e->ks.smem)));
+    for (int m = 1; m <= 5; m++)
+      if (e->ks.move_binning[m])
+        CKB(cudaFuncSetAttribute((const void*)e->ks.move_binning[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ks.smem));
     CKB(cudaFuncSetAttribute((const void*)e->ks.init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ks.smem));
     CKB(cudaFuncSetAttribute((const void*)e->ks.shim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ks.smem));
   }
@@ -598,7 +613,8 @@ int sadmc_run_async(sadmc_engine* e, uint64_t n_moves) {
     const long long threads = (long long)e->cfg.n_walkers * e->ks.move_threads_per_walker;
     grid = (int)((threads + block - 1) / block);
   }
-  move_fn f = e->ks.move[e->cfg.method];
+  move_fn f = (e->cfg.flags & SADMC_FLAG_BINNING) ? e->ks.move_binning[e->cfg.method] : e->ks.move[e->cfg.method];
+  if (!f) return fail(SADMC_ERR_UNSUPPORTED, "no move kernel for method %d with these flags", e->cfg.method);
   CK(cudaEventRecord(e->ev0, e->stream));
   f<<<grid, block, smem, e->stream>>>(e->P, e->moves, n_moves);
   CK(cudaGetLastError());
@@ -749,6 +765,7 @@ int sadmc_get_bins(sadmc_engine* e, uint32_t w, uint32_t cap, uint64_t* histogra
                    double* energy_squared_total, uint64_t* round_trips, uint8_t* have_visited, uint64_t* wl_hist, double* extra_total,
                    uint64_t* extra_count) {
   if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  if (refuse_binning(e, "sadmc_get_bins")) return SADMC_ERR_INVALID;
   WalkerRec r;
   int rc = fetch_walker(e, w, &r);
   if (rc) return rc;
@@ -792,12 +809,105 @@ int sadmc_get_bins(sadmc_engine* e, uint32_t w, uint32_t cap, uint64_t* histogra
   return 0;
 }
 
+// ---- SADMC_FLAG_BINNING: the state of energy_binning.rs's EnergyMC over binning::histogram::Bins ----
+static int need_binning(sadmc_engine* e) {
+  if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  if (!(e->cfg.flags & SADMC_FLAG_BINNING)) return fail(SADMC_ERR_INVALID, "engine was not created with SADMC_FLAG_BINNING");
+  return 0;
+}
+int sadmc_get_binning_walker(sadmc_engine* e, uint32_t w, sadmc_binning_state* s) {
+  int rc = need_binning(e);
+  if (rc) return rc;
+  if (!s) return fail(SADMC_ERR_INVALID, "null argument");
+  WalkerRec r;
+  rc = fetch_walker(e, w, &r);
+  if (rc) return rc;
+  memset(s, 0, sizeof *s);
+  s->moves = e->moves;
+  s->accepted_moves = r.accepted;
+  s->acceptance_rate = r.acc_rate;
+  s->translation_scale = r.tscale;
+  s->rng_s0 = r.s0;
+  s->rng_s1 = r.s1;
+  s->energy = r.E;
+  s->bins_width = e->P.width;
+  if (e->moves == 0) { // nothing has called prep_for_e yet: Bins::new (histogram.rs:170-180) with empty vectors
+    s->bins_min = (std::round(r.E / e->P.width) - 0.5) * e->P.width;
+    s->bins_len = 0;
+  } else {
+    s->bins_min = r.bmin;
+    s->bins_len = (uint32_t)r.len;
+  }
+  s->bins_min_e = r.b_min_e;
+  s->bins_max_e = r.b_max_e;
+  s->window_first = (uint32_t)r.lo;
+  s->method = r.method == SADMC_METHOD_WL && e->P.inv_t ? SADMC_METHOD_INV_T_WL : r.method;
+  s->status = r.status;
+  s->too_lo = r.too_lo;
+  s->too_hi = r.too_hi;
+  s->latest_parameter = r.latest_parameter;
+  s->tF = r.b_tF;
+  s->tL = r.tL;
+  s->num_states = r.num_states;
+  s->samc_t0 = r.samc_t0;
+  s->wl_gamma = r.wl_gamma;
+  s->wl_inv_t = e->P.inv_t;
+  s->lnw_max_count = r.highest_hist;
+  s->lnw_total_count = e->moves;
+  s->t_found_max_total = r.b_tf_max;
+  s->hist_min_count = r.b_hist_min;
+  s->hist_total_count = r.b_hist_total;
+  return 0;
+}
+int sadmc_get_binning_bins(sadmc_engine* e, uint32_t w, uint32_t cap, double* lnw_total, uint64_t* lnw_count, double* energy_total,
+                           uint64_t* energy_count, double* t_found_total, uint64_t* t_found_count, uint64_t* hist_count, double* extra_total,
+                           uint64_t* extra_count) {
+  int rc = need_binning(e);
+  if (rc) return rc;
+  WalkerRec r;
+  rc = fetch_walker(e, w, &r);
+  if (rc) return rc;
+  const size_t n = e->moves == 0 ? 0 : (size_t)r.len;
+  if (cap < n) return fail(SADMC_ERR_INVALID, "capacity %u < bins_len %zu", cap, n);
+  if (n == 0) return 0;
+  const size_t base = (size_t)w * e->P.cap + (size_t)r.lo;
+  std::vector<BinRec> recs(n);
+  CK(cudaMemcpyAsync(recs.data(), e->P.rec + base, n * sizeof(BinRec), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  for (size_t i = 0; i < n; i++) { // record layout: book_binning.cuh
+    const BinRec& b = recs[i];
+    if (lnw_total) lnw_total[i] = b.lo.lnw;
+    if (lnw_count) lnw_count[i] = b.lo.hist;
+    if (energy_total) energy_total[i] = b.lo.etot;
+    if (energy_count) memcpy(&energy_count[i], &b.lo.e2tot, 8);
+    if (t_found_total) memcpy(&t_found_total[i], &b.hi.t_found, 8);
+    if (t_found_count) t_found_count[i] = b.hi.rt_stamp;
+    if (hist_count) hist_count[i] = b.hi.wl_hist;
+  }
+  if (extra_total) {
+    if (e->P.extra_total) {
+      CK(cudaMemcpyAsync(extra_total, e->P.extra_total + base, n * 8, cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+    } else
+      for (size_t i = 0; i < n; i++) extra_total[i] = 0;
+  }
+  if (extra_count) {
+    if (e->P.extra_count) {
+      CK(cudaMemcpyAsync(extra_count, e->P.extra_count + base, n * 8, cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+    } else
+      for (size_t i = 0; i < n; i++) extra_count[i] = 0;
+  }
+  return 0;
+}
+
 // ---- resume: the inverse of sadmc_get_walker / sadmc_get_bins (mc/mod.rs:70-84 deserialises a whole EnergyMC) ----
 int sadmc_set_walker_bins(sadmc_engine* e, uint32_t w, const sadmc_walker_state* s, const uint64_t* histogram, const uint64_t* t_found,
                           const double* lnw, const double* energy_total, const double* energy_squared_total, const uint64_t* round_trips,
                           const uint8_t* have_visited, const uint64_t* wl_hist, const double* extra_total, const uint64_t* extra_count) {
   if (!e || !s || !histogram || !lnw || !energy_total || !energy_squared_total)
     return fail(SADMC_ERR_INVALID, "null argument (histogram, lnw, energy_total, energy_squared_total are required)");
+  if (refuse_binning(e, "sadmc_set_walker_bins")) return SADMC_ERR_INVALID;
   if (w >= e->P.n_walkers) return fail(SADMC_ERR_INVALID, "walker %u out of range", w);
   if (e->started && e->cfg.init_mode != SADMC_INIT_EXTERNAL) return fail(SADMC_ERR_INVALID, "resume needs an engine created with SADMC_INIT_EXTERNAL");
   const DevParams& P = e->P;
@@ -898,6 +1008,7 @@ int sadmc_resume(sadmc_engine* e, uint64_t moves) {
   if (!e) return fail(SADMC_ERR_INVALID, "null engine");
   if (e->started) return fail(SADMC_ERR_INVALID, "engine already started");
   if (e->cfg.init_mode != SADMC_INIT_EXTERNAL) return fail(SADMC_ERR_INVALID, "resume needs an engine created with SADMC_INIT_EXTERNAL");
+  if (refuse_binning(e, "sadmc_resume")) return SADMC_ERR_INVALID;
   e->started = true;
   e->moves = moves;
   return 0;
@@ -1016,7 +1127,7 @@ int sadmc_set_rngs(sadmc_engine* e, const uint64_t* s) {
 
 int sadmc_window(sadmc_engine* e, double* lo, double* width, uint32_t* nbins) {
   if (!e) return fail(SADMC_ERR_INVALID, "null engine");
-  if (lo) *lo = ((double)e->k_base - 0.5) * e->P.width;
+  if (lo) *lo = ((double)e->k_base - ((e->cfg.flags & SADMC_FLAG_BINNING) ? 0.0 : 0.5)) * e->P.width;
   if (width) *width = e->P.width;
   if (nbins) *nbins = e->P.cap;
   return 0;
@@ -1051,6 +1162,7 @@ int sadmc_fold_select_ex(sadmc_engine* e, uint32_t first_walker, uint32_t walker
 }
 int sadmc_set_lnw(sadmc_engine* e, const double* lnw_window, uint32_t n) {
   if (!e || !lnw_window) return fail(SADMC_ERR_INVALID, "null argument");
+  if (refuse_binning(e, "sadmc_set_lnw")) return SADMC_ERR_INVALID;
   if (n != e->P.cap) return fail(SADMC_ERR_INVALID, "ln w array holds %u bins, the device window %u", n, e->P.cap);
   CK(cudaSetDevice(e->cfg.device));
   double* d = nullptr;
@@ -1084,12 +1196,13 @@ static int fold_launch(sadmc_engine* e, void* d_histogram, void* d_energy_total,
                        void* d_lnw_sq_sum, void* d_lnw_count, double* d_packed) {
   if (!e) return fail(SADMC_ERR_INVALID, "null engine");
   CK(cudaSetDevice(e->cfg.device));
-  const FoldSel sel = e->fold_sel;
+  FoldSel sel = e->fold_sel;
+  sel.binning = (e->cfg.flags & SADMC_FLAG_BINNING) ? 1 : 0;
   uint32_t n_sel = sel.first < e->P.n_walkers ? (e->P.n_walkers - sel.first + sel.stride - 1) / sel.stride : 0;
   if (sel.count && sel.count < n_sel) n_sel = sel.count;
   if (n_sel == 0) return fail(SADMC_ERR_INVALID, "fold selection holds no walker");
   const double* wmax = nullptr; // one pass: the walkers' running maxima (fold_kernels.cuh)
-  if (sel.sad_range_only != 0) {
+  if (sel.sad_range_only != 0 || sel.binning) {
     if (!e->d_wmax) {
       int rc = dev_alloc(e, (void**)&e->d_wmax, (size_t)e->P.n_walkers * 8, false);
       if (rc) return rc;

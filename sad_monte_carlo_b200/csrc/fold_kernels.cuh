@@ -28,11 +28,20 @@ namespace sadmc {
 // or zero ln w (energy.rs:544-584), the former end bin from a ln w that received only half of its increments, and at
 // gamma ~ 1/t such a bin needs about as long again to settle; a minority of such walkers otherwise dominates the error
 // of an ensemble mean.  Histograms and energy moments are not filtered.
+//
+// SADMC_FLAG_BINNING engines (binning != 0; record layout of book_binning.cuh): the histogram that is merged is the count of
+// the "energy" accumulator -- every visit, never zeroed, whereas lnw.count is reset by SAD range extensions
+// (energy_binning.rs:355-361) -- energy_squared_total is not collected by the reference (0), and the alignment constant
+// is always taken by walker_max_lnw_kernel (set_lnw can lower a walker's largest ln w).
 struct FoldSel {
   uint32_t first, stride, count;
   int sad_range_only;
   unsigned long long tl_max;
+  int binning;
 };
+__device__ __forceinline__ unsigned long long fold_visits(const BinLo& b, const FoldSel s) {
+  return s.binning ? (unsigned long long)__double_as_longlong(b.e2tot) : b.hist;
+}
 __device__ __forceinline__ void fold_range(const WalkerRec& r, const FoldSel s, int& ilo, int& ihi) {
   const bool sad = r.method == SADMC_METHOD_SAD;
   const bool ranged = s.sad_range_only != 0 && sad;
@@ -42,7 +51,7 @@ __device__ __forceinline__ void fold_range(const WalkerRec& r, const FoldSel s, 
   if (sad && s.tl_max != 0 && r.t_range > s.tl_max) ihi = ilo - 1; // not settled: no bin counts
 }
 __device__ __forceinline__ bool fold_lnw_counts(const WalkerRec& r, const BinLo& b, int j, const FoldSel s) {
-  if (b.hist == 0) return false;
+  if (fold_visits(b, s) == 0) return false;
   int ilo, ihi;
   fold_range(r, s, ilo, ihi);
   return j >= ilo && j <= ihi;
@@ -112,10 +121,11 @@ __global__ void __launch_bounds__(256) fold_partial_kernel(const DevParams P, co
       for (int u = 0; u < 8; u++) {
         if (!in[u]) continue;
         const FoldMeta m = meta[k0 + u];
-        h += b[u].hist;
+        const unsigned long long visits = fold_visits(b[u], sel);
+        h += visits;
         et += b[u].etot;
-        e2 += b[u].e2tot;
-        if (b[u].hist != 0 && (int)j >= m.ilo && (int)j <= m.ihi) {
+        if (!sel.binning) e2 += b[u].e2tot;
+        if (visits != 0 && (int)j >= m.ilo && (int)j <= m.ihi) {
           const double a = b[u].lnw - m.wmax;
           ls += a;
           lq += a * a;

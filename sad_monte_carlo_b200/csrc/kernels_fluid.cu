@@ -3,6 +3,6 @@
 #include "sys_cell_fluid.cuh"
 namespace sadmc {
 KernelSet kernels_cell_fluid(bool square_well, const DevParams& P) {
-  return square_well ? make_set<CellFluidSys<true>>(P) : make_set<CellFluidSys<false>>(P);
+  return square_well ? make_set<CellFluidSys<true>, true>(P) : make_set<CellFluidSys<false>, true>(P);
 }
 } // namespace sadmc

@@ -5,11 +5,11 @@ namespace sadmc {
 bool kernels_lj_thread_exact(int N, const DevParams& P, KernelSet* out) {
   if (N > 64) return false;
   if (N == 31)
-    *out = make_set<LjThreadSys<false, 31, 1>>(P);
+    *out = make_set<LjThreadSys<false, 31, 1>, true>(P);
   else if (N == 38)
-    *out = make_set<LjThreadSys<false, 38, 1>>(P);
+    *out = make_set<LjThreadSys<false, 38, 1>, true>(P);
   else
-    *out = make_set<LjThreadSys<false, 0, 1>>(P);
+    *out = make_set<LjThreadSys<false, 0, 1>, true>(P);
   return true;
 }
 } // namespace sadmc

@@ -3,8 +3,8 @@
 #include "sys_fake.cuh"
 #include "sys_ising.cuh"
 namespace sadmc {
-KernelSet kernels_ising(const DevParams& P) { return make_set<IsingSys>(P); }
-KernelSet kernels_fake(const DevParams& P) { return make_set<FakeSys>(P); }
-KernelSet kernels_two_wells(const DevParams& P) { return make_set<TwoWellsSys>(P); }
-KernelSet kernels_erfinv(const DevParams& P) { return make_set<ErfInvSys>(P); }
+KernelSet kernels_ising(const DevParams& P) { return make_set<IsingSys, true>(P); }
+KernelSet kernels_fake(const DevParams& P) { return make_set<FakeSys, true>(P); }
+KernelSet kernels_two_wells(const DevParams& P) { return make_set<TwoWellsSys, true>(P); }
+KernelSet kernels_erfinv(const DevParams& P) { return make_set<ErfInvSys, true>(P); }
 } // namespace sadmc

@@ -1,11 +1,13 @@
 // make_set.cuh -- instantiates every kernel of one system type (included by the kernels_*.cu units).
 #pragma once
 #include "kernel_set.cuh"
+#include "book_binning.cuh"
 #include "move_kernel.cuh"
 
 namespace sadmc {
 
-template <class Sys>
+// BINNING: also build the energy_binning.rs move kernels for this system (the `binning` binary's bookkeeping)
+template <class Sys, bool BINNING = false>
 static KernelSet make_set(const DevParams& P) {
   KernelSet k;
   memset(&k, 0, sizeof k);
@@ -14,6 +16,12 @@ static KernelSet make_set(const DevParams& P) {
   k.move[SADMC_METHOD_WL] = move_kernel<Sys, SADMC_METHOD_WL>;
   k.move[SADMC_METHOD_INV_T_WL] = move_kernel<Sys, SADMC_METHOD_WL>;
   k.move[SADMC_METHOD_CANONICAL] = move_kernel<Sys, SADMC_METHOD_CANONICAL>;
+  if constexpr (BINNING) {
+    k.move_binning[SADMC_METHOD_SAD] = move_kernel_binning<Sys, SADMC_METHOD_SAD>;
+    k.move_binning[SADMC_METHOD_SAMC] = move_kernel_binning<Sys, SADMC_METHOD_SAMC>;
+    k.move_binning[SADMC_METHOD_WL] = move_kernel_binning<Sys, SADMC_METHOD_WL>;
+    k.move_binning[SADMC_METHOD_INV_T_WL] = move_kernel_binning<Sys, SADMC_METHOD_WL>;
+  }
   k.init = init_kernel<Sys>;
   k.shim = shim_kernel<Sys>;
   k.G = Sys::G;

@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi, load_library
-from ._abi import Config, WalkerState
+from ._abi import BinningState, Config, WalkerState
 from ._capi import f64p, u64p, u8p
 
 
@@ -114,6 +114,24 @@ class WalkerEngine:
         s = WalkerState()
         self._check(self.L.sadmc_get_walker(self.h, w, C.byref(s)))
         return s
+
+    def binning_walker(self, w=0) -> BinningState:
+        """FLAG_BINNING engines: scalars of energy_binning.rs's EnergyMC / histogram::Bins of walker w."""
+        s = BinningState()
+        self._check(self.L.sadmc_get_binning_walker(self.h, w, C.byref(s)))
+        return s
+
+    def binning_bins(self, w=0):
+        """FLAG_BINNING engines: bins.lnw and the `extra` accumulators of walker w, element 0 = bin at bins_min."""
+        n = self.binning_walker(w).bins_len
+        out = {"lnw_total": np.zeros(n), "lnw_count": np.zeros(n, np.uint64), "energy_total": np.zeros(n),
+               "energy_count": np.zeros(n, np.uint64), "t_found_total": np.zeros(n), "t_found_count": np.zeros(n, np.uint64),
+               "hist_count": np.zeros(n, np.uint64), "extra_total": np.zeros(n), "extra_count": np.zeros(n, np.uint64)}
+        self._check(self.L.sadmc_get_binning_bins(
+            self.h, w, n, _p(out["lnw_total"], f64p), _p(out["lnw_count"], u64p), _p(out["energy_total"], f64p),
+            _p(out["energy_count"], u64p), _p(out["t_found_total"], f64p), _p(out["t_found_count"], u64p),
+            _p(out["hist_count"], u64p), _p(out["extra_total"], f64p), _p(out["extra_count"], u64p)))
+        return out
 
     def energies(self):
         e = np.zeros(self.n_walkers)

@@ -5,7 +5,7 @@ import subprocess
 
 import numpy as np
 
-from sad_monte_carlo_b200._abi import Config, WalkerState
+from sad_monte_carlo_b200._abi import BinningState, Config, WalkerState
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _LIB = None
@@ -62,6 +62,16 @@ def load_oracle():
     L.oracle_bench.restype = C.c_double
     L.oracle_bench.argtypes = [C.POINTER(Config), C.c_uint32, C.c_uint64, C.c_uint64]
     L.oracle_set_math_mode.argtypes = [C.c_int]
+    L.oracle_binning_create.restype = C.c_void_p
+    L.oracle_binning_create.argtypes = [C.POINTER(Config), C.c_uint32, f64p, C.c_size_t, C.c_uint64]
+    L.oracle_binning_destroy.argtypes = [C.c_void_p]
+    L.oracle_binning_run.argtypes = [C.c_void_p, C.c_uint64]
+    L.oracle_binning_get_walker.argtypes = [C.c_void_p, C.POINTER(BinningState)]
+    L.oracle_binning_get_bins.argtypes = [C.c_void_p, C.c_uint32, f64p, u64p, f64p, u64p, f64p, u64p, u64p, f64p, u64p]
+    L.oracle_binning_get_aggregates.argtypes = [C.c_void_p, C.c_char_p, f64p]
+    L.oracle_binning_system_len.restype = C.c_size_t
+    L.oracle_binning_system_len.argtypes = [C.c_void_p]
+    L.oracle_binning_get_system.argtypes = [C.c_void_p, f64p, C.c_size_t]
     _LIB = L
     return L
 
@@ -161,3 +171,63 @@ def rng_stream(state, kind, count, n_arg=0, lo=0.0, hi=1.0):
     out = np.zeros(count, np.uint64)
     L.oracle_rng_stream(_ptr(state, u64p), kind, n_arg, lo, hi, count, _ptr(out, u64p))
     return out
+
+
+class OracleBinningMC:
+    """One reference walker of the `binning` binary: energy_binning.rs `EnergyMC<Any>` over binning::histogram."""
+
+    def __init__(self, cfg, walker=0, system_state=None, attempts_override=0):
+        self.L = load_oracle()
+        self.cfg = cfg
+        st, n = None, 0
+        if system_state is not None:
+            st = np.ascontiguousarray(system_state, dtype=np.float64)
+            n = st.size
+        self.h = self.L.oracle_binning_create(C.byref(cfg), walker, _ptr(st, f64p), n, attempts_override)
+        if not self.h:
+            raise RuntimeError("oracle_binning_create: " + self.L.oracle_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.oracle_binning_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, n):
+        if self.L.oracle_binning_run(self.h, int(n)) != 0:
+            raise RuntimeError("oracle_binning_run: " + self.L.oracle_last_error().decode())
+
+    def walker(self):
+        s = BinningState()
+        self.L.oracle_binning_get_walker(self.h, C.byref(s))
+        return s
+
+    def bins(self):
+        n = self.walker().bins_len
+        out = {"lnw_total": np.zeros(n), "lnw_count": np.zeros(n, np.uint64), "energy_total": np.zeros(n),
+               "energy_count": np.zeros(n, np.uint64), "t_found_total": np.zeros(n), "t_found_count": np.zeros(n, np.uint64),
+               "hist_count": np.zeros(n, np.uint64), "extra_total": np.zeros(n), "extra_count": np.zeros(n, np.uint64)}
+        rc = self.L.oracle_binning_get_bins(
+            self.h, n, _ptr(out["lnw_total"], f64p), _ptr(out["lnw_count"], u64p), _ptr(out["energy_total"], f64p),
+            _ptr(out["energy_count"], u64p), _ptr(out["t_found_total"], f64p), _ptr(out["t_found_count"], u64p),
+            _ptr(out["hist_count"], u64p), _ptr(out["extra_total"], f64p), _ptr(out["extra_count"], u64p))
+        assert rc == 0
+        return out
+
+    def aggregates(self, name=""):
+        """(min_total, max_total, e_max_total, min_count, max_count, e_max_count, total_count) of bins.lnw ("") or an extra."""
+        out = np.zeros(7)
+        if self.L.oracle_binning_get_aggregates(self.h, name.encode(), _ptr(out, f64p)) != 0:
+            return None
+        return out
+
+    def system(self):
+        n = self.L.oracle_binning_system_len(self.h)
+        buf = np.zeros(n)
+        assert self.L.oracle_binning_get_system(self.h, _ptr(buf, f64p), n) == 0
+        return buf
