@@ -364,6 +364,37 @@ int sadmc_sys_confirm(sadmc_engine* e, uint32_t w);                           /*
 int sadmc_sys_randomize(sadmc_engine* e, uint32_t w, double* energy);
 int sadmc_sys_verify_energy(sadmc_engine* e, uint32_t w);                     /* System::verify_energy   */
 
+/* ---- replica exchange: the `tempering` binary (src/mc/tempering.rs) ------------------------------------------
+ * `n_sim` independent tempering simulations x `n_T` temperatures on one GPU; simulation k is the reference process run
+ * with `--seed (cfg->seed + cfg->walker_offset + k)` (MC::from_params, tempering.rs:152-175: every replica starts from
+ * the SAME system and a CLONE of the same generator; the simulation's own generator is that generator after jump()).
+ * cfg: the system parameters, seed, walker_offset, device, init_mode (SADMC_INIT_REFERENCE, or SADMC_INIT_EXTERNAL +
+ * sadmc_tempering_set_system) and n_walkers = n_sim; method / bins are not used.  Same systems as SADMC_FLAG_BINNING. */
+typedef struct sadmc_tempering sadmc_tempering;
+/* `Replica` (tempering.rs:46-73) without its system */
+typedef struct sadmc_replica_state {
+  double T;
+  uint64_t rejected_count, accepted_count, rejected_swap_count, accepted_swap_count, ignored_count;
+  double total_energy, total_energy_squared;
+  double translation_scale; /* always 1.0 (tempering.rs:88) */
+  uint64_t rng_s0, rng_s1;
+  double energy; /* system.energy() */
+} sadmc_replica_state;
+int sadmc_tempering_create(const sadmc_config* cfg, const double* T, uint32_t n_T, uint64_t canonical_steps, sadmc_tempering** out);
+void sadmc_tempering_destroy(sadmc_tempering* t);
+/* n_rounds x `MC::run_once` (tempering.rs:272-342): min_moves_to_randomize() * canonical_steps moves for every replica
+ * (one launch), then one swap attempt per neighbouring pair (one launch).  Blocking. */
+int sadmc_tempering_run(sadmc_tempering* t, uint64_t n_rounds);
+int sadmc_tempering_num_moves(sadmc_tempering* t, uint64_t* moves);        /* MC::moves of each simulation */
+int sadmc_tempering_steps_per_round(sadmc_tempering* t, uint64_t* steps); /* moves per replica and round (274) */
+int sadmc_tempering_get_replicas(sadmc_tempering* t, uint32_t sim, sadmc_replica_state* out /* [n_T] */);
+int sadmc_tempering_get_rng(sadmc_tempering* t, uint32_t sim, uint64_t s[2]); /* MC::rng */
+int sadmc_tempering_system_len(sadmc_tempering* t, size_t* n_doubles);
+int sadmc_tempering_get_system(sadmc_tempering* t, uint32_t sim, uint32_t replica, double* buf, size_t n);
+int sadmc_tempering_set_system(sadmc_tempering* t, uint32_t sim, uint32_t replica, const double* buf, size_t n);
+/* Device time of the last sadmc_tempering_run (move and swap kernels), CUDA events. */
+int sadmc_tempering_last_run_ms(sadmc_tempering* t, float* ms);
+
 /* ---- measurement utility (bench.py) --------------------------------------- */
 /* Achievable FP64 FMA throughput of `device` in TFLOP/s (independent DFMA chains,
  * best of `reps`): the denominator of the FP64 roofline fraction. */

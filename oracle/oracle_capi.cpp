@@ -12,6 +12,7 @@
 #include "../include/sadmc_gpu.h" // config / state structs only (shared vocabulary with the engine)
 #include "oracle_binning.hpp"
 #include "oracle_mc.hpp"
+#include "oracle_tempering.hpp"
 
 namespace oracle {
 
@@ -437,6 +438,96 @@ int oracle_binning_get_system(oracle_bmc* o, double* buf, size_t n) {
   if (n < s.size()) return -1;
   std::memcpy(buf, s.data(), s.size() * sizeof(double));
   return 0;
+}
+
+// ---- the `tempering` binary (oracle_tempering.hpp) ----
+struct oracle_tmc {
+  std::unique_ptr<tempering::MC> mc;
+};
+static uint64_t min_moves_to_randomize(const sadmc_config& c) {
+  switch (c.system) {
+    case SADMC_SYS_ISING: return (uint64_t)c.N * c.N; // ising.rs:86-88
+    case SADMC_SYS_FAKE: return c.fake_function == SADMC_FAKE_LINEAR ? 1 : (c.fake_function == SADMC_FAKE_QUADRATIC ? c.N : 3);
+    default: return c.N;
+  }
+}
+// simulation `sim` = the reference process `tempering <flags> --seed (cfg->seed + sim)`; system_state (optional):
+// the image every replica starts from instead of the reference constructor's
+oracle_tmc* oracle_tempering_create(const sadmc_config* cfg, uint32_t sim, const double* T, uint32_t n_T, uint64_t canonical_steps,
+                                    const double* system_state, size_t n_state, uint64_t attempts_override) {
+  try {
+    std::vector<double> img;
+    if (system_state) {
+      img.assign(system_state, system_state + n_state);
+    } else {
+      sadmc_config c0 = *cfg;
+      c0.init_mode = SADMC_INIT_REFERENCE;
+      img = make_system(c0, attempts_override)->get_state();
+    }
+    std::vector<std::unique_ptr<System>> systems;
+    for (uint32_t r = 0; r < n_T; r++) { // system.clone()
+      sadmc_config c1 = *cfg;
+      c1.init_mode = SADMC_INIT_EXTERNAL;
+      std::unique_ptr<System> s = make_system(c1, attempts_override);
+      s->set_state(img);
+      systems.push_back(std::move(s));
+    }
+    oracle_tmc* o = new oracle_tmc;
+    o->mc.reset(new tempering::MC(cfg->seed + sim, std::vector<double>(T, T + n_T), canonical_steps, min_moves_to_randomize(*cfg), std::move(systems)));
+    return o;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return nullptr;
+  }
+}
+void oracle_tempering_destroy(oracle_tmc* o) { delete o; }
+int oracle_tempering_run(oracle_tmc* o, uint64_t n_rounds) {
+  try {
+    for (uint64_t k = 0; k < n_rounds; k++) o->mc->run_once();
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+uint64_t oracle_tempering_num_moves(oracle_tmc* o) { return o->mc->moves; }
+void oracle_tempering_get_rng(oracle_tmc* o, uint64_t* s) {
+  s[0] = o->mc->rng.s0;
+  s[1] = o->mc->rng.s1;
+}
+int oracle_tempering_get_replicas(oracle_tmc* o, sadmc_replica_state* out) {
+  for (size_t r = 0; r < o->mc->replicas.size(); r++) {
+    const tempering::Replica& q = o->mc->replicas[r];
+    out[r].T = q.T;
+    out[r].rejected_count = q.rejected_count;
+    out[r].accepted_count = q.accepted_count;
+    out[r].rejected_swap_count = q.rejected_swap_count;
+    out[r].accepted_swap_count = q.accepted_swap_count;
+    out[r].ignored_count = q.ignored_count;
+    out[r].total_energy = q.total_energy;
+    out[r].total_energy_squared = q.total_energy_squared;
+    out[r].translation_scale = q.translation_scale;
+    out[r].rng_s0 = q.rng.s0;
+    out[r].rng_s1 = q.rng.s1;
+    out[r].energy = q.energy();
+  }
+  return 0;
+}
+size_t oracle_tempering_system_len(oracle_tmc* o) { return o->mc->replicas[0].system->get_state().size(); }
+int oracle_tempering_get_system(oracle_tmc* o, uint32_t replica, double* buf, size_t n) {
+  const std::vector<double> s = o->mc->replicas[replica].system->get_state();
+  if (n < s.size()) return -1;
+  std::memcpy(buf, s.data(), s.size() * sizeof(double));
+  return 0;
+}
+// xoroshiro128+ jump applied to a state (test probe)
+void oracle_rng_jump(uint64_t* s) {
+  Rng g;
+  g.s0 = s[0];
+  g.s1 = s[1];
+  tempering::jump(g);
+  s[0] = g.s0;
+  s[1] = g.s1;
 }
 
 // ---- RNG / math probes for tests ----

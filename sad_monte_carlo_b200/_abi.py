@@ -100,6 +100,20 @@ class BinningState(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}
 
 
+class ReplicaState(C.Structure):
+    """struct sadmc_replica_state (`Replica` of src/mc/tempering.rs:46-73 without its system)"""
+    _fields_ = [
+        ("T", C.c_double),
+        ("rejected_count", C.c_uint64), ("accepted_count", C.c_uint64), ("rejected_swap_count", C.c_uint64),
+        ("accepted_swap_count", C.c_uint64), ("ignored_count", C.c_uint64),
+        ("total_energy", C.c_double), ("total_energy_squared", C.c_double), ("translation_scale", C.c_double),
+        ("rng_s0", C.c_uint64), ("rng_s1", C.c_uint64), ("energy", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 def make_config(system, method="sad", **kw):
     """Build a Config with the reference's defaults (EnergyMCParams::default, energy.rs:99-115)."""
     c = Config()

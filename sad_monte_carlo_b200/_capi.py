@@ -1,7 +1,7 @@
 """ctypes prototypes for every symbol include/sadmc_gpu.h declares."""
 import ctypes as C
 
-from ._abi import BinningState, Config, WalkerState
+from ._abi import BinningState, Config, ReplicaState, WalkerState
 
 u64p = C.POINTER(C.c_uint64)
 f64p = C.POINTER(C.c_double)
@@ -56,6 +56,17 @@ PROTOTYPES = {
     "sadmc_sys_confirm": (C.c_int, [vp, C.c_uint32]),
     "sadmc_sys_randomize": (C.c_int, [vp, C.c_uint32, f64p]),
     "sadmc_sys_verify_energy": (C.c_int, [vp, C.c_uint32]),
+    "sadmc_tempering_create": (C.c_int, [C.POINTER(Config), f64p, C.c_uint32, C.c_uint64, C.POINTER(vp)]),
+    "sadmc_tempering_destroy": (None, [vp]),
+    "sadmc_tempering_run": (C.c_int, [vp, C.c_uint64]),
+    "sadmc_tempering_num_moves": (C.c_int, [vp, u64p]),
+    "sadmc_tempering_steps_per_round": (C.c_int, [vp, u64p]),
+    "sadmc_tempering_get_replicas": (C.c_int, [vp, C.c_uint32, C.POINTER(ReplicaState)]),
+    "sadmc_tempering_get_rng": (C.c_int, [vp, C.c_uint32, u64p]),
+    "sadmc_tempering_system_len": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
+    "sadmc_tempering_get_system": (C.c_int, [vp, C.c_uint32, C.c_uint32, f64p, C.c_size_t]),
+    "sadmc_tempering_set_system": (C.c_int, [vp, C.c_uint32, C.c_uint32, f64p, C.c_size_t]),
+    "sadmc_tempering_last_run_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "sadmc_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, f64p]),
     "sadmc_selftest_exp_cmp": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, u64p, u64p]),
 }
@@ -69,4 +80,5 @@ def bind(lib):
     lib.sadmc_sizeof_config.restype = C.c_size_t
     lib.sadmc_sizeof_walker_state.restype = C.c_size_t
     lib.sadmc_sizeof_binning_state.restype = C.c_size_t
+    lib.sadmc_sizeof_replica_state.restype = C.c_size_t
     return lib

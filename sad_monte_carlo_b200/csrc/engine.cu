@@ -20,6 +20,7 @@
 #include "kernel_set.cuh"
 #include "rng.cuh"
 #include "sys_limits.hpp"
+#include "tempering_swap.cuh"
 
 using namespace sadmc;
 
@@ -442,6 +443,7 @@ int sadmc_abi_version(void) { return SADMC_ABI_VERSION; }
 size_t sadmc_sizeof_config(void) { return sizeof(sadmc_config); }
 size_t sadmc_sizeof_walker_state(void) { return sizeof(sadmc_walker_state); }
 size_t sadmc_sizeof_binning_state(void) { return sizeof(sadmc_binning_state); }
+size_t sadmc_sizeof_replica_state(void) { return sizeof(sadmc_replica_state); }
 
 int sadmc_reference_system(const sadmc_config* cfg, double* buf, size_t n, size_t* needed) {
   if (!cfg) return fail(SADMC_ERR_INVALID, "null argument");
@@ -1259,6 +1261,239 @@ int sadmc_fold(sadmc_engine* e, uint64_t* histogram, double* energy_total, doubl
     if (outs[k]) CK(cudaMemcpyAsync(outs[k], d + k * n, n * 8, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   return 0;
+}
+
+// ---- replica exchange: the `tempering` binary (src/mc/tempering.rs; kernels in tempering.cuh) ----
+struct sadmc_tempering {
+  sadmc_engine* e = nullptr; // systems, generators, kernels (its bins are a dummy window; the engine is never started)
+  uint32_t n_sim = 0, n_T = 0;
+  unsigned long long steps = 0, rounds = 0;
+  TemperRec* d_reps = nullptr;
+  unsigned long long* d_mc_rng = nullptr;
+  float last_ms = 0.f;
+  bool settled = false; // every replica's cached energy is what its system says (see temper_settle)
+};
+static unsigned long long min_moves_to_randomize(const sadmc_config& c) {
+  switch (c.system) {
+    case SADMC_SYS_ISING: return (unsigned long long)c.N * c.N;                                              // ising.rs:86-88
+    case SADMC_SYS_FAKE: return c.fake_function == SADMC_FAKE_LINEAR ? 1 : (c.fake_function == SADMC_FAKE_QUADRATIC ? c.N : 3); // fake.rs:113-115
+    default: return c.N; // lj.rs:280-282, optsquare.rs:205-207, wca.rs, erfinv.rs:86-88, two_wells.rs (position.len())
+  }
+}
+static void xoroshiro_jump(Rng& g) { // rand_xoshiro 0.4 Xoroshiro128Plus::jump: 2^64 calls of next_u64
+  static const uint64_t JUMP[2] = {0xdf900294d8f554a5ull, 0x170865df4b3201fcull};
+  uint64_t s0 = 0, s1 = 0;
+  for (int i = 0; i < 2; i++)
+    for (int b = 0; b < 64; b++) {
+      if (JUMP[i] & (1ull << b)) {
+        s0 ^= g.s0;
+        s1 ^= g.s1;
+      }
+      g.next();
+    }
+  g.s0 = s0;
+  g.s1 = s1;
+}
+// A launch with zero moves: load + store of every system.  Host-side constructors that do not know the energy hand over
+// NaN (the fluids sum it when they load, sys_cell_fluid.cuh), and the analytic systems derive theirs from the positions;
+// afterwards images and cached energies are what the reference holds after `system.clone()`.
+static int temper_settle(sadmc_tempering* t) {
+  if (t->settled) return 0;
+  sadmc_engine* e = t->e;
+  CK(cudaSetDevice(e->cfg.device));
+  int grid;
+  launch_cfg(e, &grid);
+  e->ks.temper<<<grid, e->ks.block, e->ks.smem, e->stream>>>(e->P, t->d_reps, 0ull);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  e->launches++;
+  t->settled = true;
+  return 0;
+}
+int sadmc_tempering_create(const sadmc_config* cfg, const double* T, uint32_t n_T, uint64_t canonical_steps, sadmc_tempering** out) {
+  if (!cfg || !T || !out) return fail(SADMC_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (n_T < 1 || cfg->n_walkers < 1) return fail(SADMC_ERR_INVALID, "tempering needs at least one temperature and one simulation");
+  if ((unsigned long long)n_T * cfg->n_walkers > 0x7fffffffull) return fail(SADMC_ERR_INVALID, "too many replicas");
+  if (cfg->init_mode != SADMC_INIT_REFERENCE && cfg->init_mode != SADMC_INIT_EXTERNAL)
+    return fail(SADMC_ERR_INVALID, "tempering starts every replica from the reference constructor's system (tempering.rs:161) or from supplied systems");
+  for (uint32_t r = 0; r < n_T; r++)
+    if (!(T[r] > 0)) return fail(SADMC_ERR_INVALID, "temperature %u is not positive", r);
+  sadmc_config c = *cfg;
+  const uint32_t n_sim = cfg->n_walkers;
+  c.n_walkers = n_sim * n_T;
+  c.method = SADMC_METHOD_CANONICAL; // unused: the bins below are a dummy window
+  c.canonical_T = 1.0;
+  c.energy_bin = 1.0;
+  c.min_allowed_energy = c.max_allowed_energy = NAN;
+  c.bin_window_lo = 0.0;
+  c.bin_window_hi = 1.0;
+  c.flags &= ~(uint32_t)SADMC_FLAG_BINNING;
+  if (c.system == SADMC_SYS_LJ && c.lanes_per_walker == 0) c.lanes_per_walker = 1;
+  if (c.system == SADMC_SYS_WCA && c.lanes_per_walker == 0) c.lanes_per_walker = 32;
+  c.init_mode = SADMC_INIT_EXTERNAL;
+  sadmc_engine* e = nullptr;
+  int rc = sadmc_create(&c, &e);
+  if (rc) return rc;
+  if (!e->ks.temper) {
+    sadmc_destroy(e);
+    return fail(SADMC_ERR_UNSUPPORTED, "no tempering kernel for this system / lanes_per_walker");
+  }
+  sadmc_tempering* t = new sadmc_tempering;
+  t->e = e;
+  t->n_sim = n_sim;
+  t->n_T = n_T;
+  t->steps = min_moves_to_randomize(*cfg) * canonical_steps; // tempering.rs:274
+#define TBAIL(expr)             \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc) {                  \
+      sadmc_tempering_destroy(t); \
+      return _rc;               \
+    }                           \
+  } while (0)
+  if (cfg->init_mode == SADMC_INIT_REFERENCE) { // system.clone() for every replica (tempering.rs:161)
+    std::vector<double> img;
+    e->cfg.init_mode = SADMC_INIT_REFERENCE;
+    rc = reference_image(e, img);
+    e->cfg.init_mode = SADMC_INIT_EXTERNAL;
+    TBAIL(rc);
+    std::vector<double> all((size_t)c.n_walkers * e->sys_len);
+    for (uint32_t w = 0; w < c.n_walkers; w++) memcpy(&all[(size_t)w * e->sys_len], img.data(), e->sys_len * sizeof(double));
+    TBAIL(sadmc_set_systems(e, all.data(), all.size()));
+  }
+  {
+    std::vector<uint64_t> rngs((size_t)c.n_walkers * 2), mc((size_t)n_sim * 2);
+    std::vector<TemperRec> reps(c.n_walkers);
+    for (uint32_t k = 0; k < n_sim; k++) {
+      Rng g;
+      seed_from_u64(cfg->seed + cfg->walker_offset + k, &g.s0, &g.s1); // tempering.rs:153
+      for (uint32_t r = 0; r < n_T; r++) {                             // rng.clone() (161)
+        rngs[2 * ((size_t)k * n_T + r)] = g.s0;
+        rngs[2 * ((size_t)k * n_T + r) + 1] = g.s1;
+        TemperRec& q = reps[(size_t)k * n_T + r];
+        memset(&q, 0, sizeof q);
+        q.T = T[r];
+      }
+      xoroshiro_jump(g); // tempering.rs:164
+      mc[2 * k] = g.s0;
+      mc[2 * k + 1] = g.s1;
+    }
+    TBAIL(sadmc_set_rngs(e, rngs.data()));
+    TBAIL(dev_alloc(e, (void**)&t->d_reps, reps.size() * sizeof(TemperRec), false));
+    TBAIL(dev_alloc(e, (void**)&t->d_mc_rng, mc.size() * 8, false));
+    cudaError_t er = cudaMemcpyAsync(t->d_reps, reps.data(), reps.size() * sizeof(TemperRec), cudaMemcpyHostToDevice, e->stream);
+    if (er == cudaSuccess) er = cudaMemcpyAsync(t->d_mc_rng, mc.data(), mc.size() * 8, cudaMemcpyHostToDevice, e->stream);
+    if (er == cudaSuccess) er = cudaStreamSynchronize(e->stream);
+    if (er != cudaSuccess) {
+      sadmc_tempering_destroy(t);
+      return fail(SADMC_ERR_CUDA, "tempering upload failed: %s", cudaGetErrorString(er));
+    }
+  }
+  if (e->ks.smem > 48 * 1024) {
+    cudaError_t er = cudaFuncSetAttribute((const void*)e->ks.temper, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ks.smem);
+    if (er != cudaSuccess) {
+      sadmc_tempering_destroy(t);
+      return fail(SADMC_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(er));
+    }
+  }
+#undef TBAIL
+  *out = t;
+  return 0;
+}
+void sadmc_tempering_destroy(sadmc_tempering* t) {
+  if (!t) return;
+  if (t->e) sadmc_destroy(t->e); // d_reps / d_mc_rng are among the engine's allocations
+  delete t;
+}
+int sadmc_tempering_run(sadmc_tempering* t, uint64_t n_rounds) {
+  if (!t) return fail(SADMC_ERR_INVALID, "null argument");
+  sadmc_engine* e = t->e;
+  int src = temper_settle(t);
+  if (src) return src;
+  CK(cudaSetDevice(e->cfg.device));
+  int grid;
+  launch_cfg(e, &grid);
+  CK(cudaEventRecord(e->ev0, e->stream));
+  for (uint64_t r = 0; r < n_rounds; r++) {
+    e->ks.temper<<<grid, e->ks.block, e->ks.smem, e->stream>>>(e->P, t->d_reps, t->steps);
+    CK(cudaGetLastError());
+    temper_swap_kernel<<<t->n_sim, 128, 0, e->stream>>>(e->P, t->d_reps, t->d_mc_rng, t->n_T);
+    CK(cudaGetLastError());
+    e->launches += 2;
+  }
+  CK(cudaEventRecord(e->ev1, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaEventElapsedTime(&t->last_ms, e->ev0, e->ev1));
+  t->rounds += n_rounds;
+  return 0;
+}
+int sadmc_tempering_last_run_ms(sadmc_tempering* t, float* ms) {
+  if (!t || !ms) return fail(SADMC_ERR_INVALID, "null argument");
+  *ms = t->last_ms;
+  return 0;
+}
+int sadmc_tempering_num_moves(sadmc_tempering* t, uint64_t* moves) {
+  if (!t || !moves) return fail(SADMC_ERR_INVALID, "null argument");
+  *moves = t->rounds * t->steps * t->n_T; // these_moves = steps per replica, summed (tempering.rs:277-284, 321-323)
+  return 0;
+}
+int sadmc_tempering_steps_per_round(sadmc_tempering* t, uint64_t* steps) {
+  if (!t || !steps) return fail(SADMC_ERR_INVALID, "null argument");
+  *steps = t->steps;
+  return 0;
+}
+int sadmc_tempering_get_replicas(sadmc_tempering* t, uint32_t sim, sadmc_replica_state* out) {
+  if (!t || !out) return fail(SADMC_ERR_INVALID, "null argument");
+  if (sim >= t->n_sim) return fail(SADMC_ERR_INVALID, "simulation %u out of range", sim);
+  sadmc_engine* e = t->e;
+  int src = temper_settle(t);
+  if (src) return src;
+  std::vector<TemperRec> reps(t->n_T);
+  std::vector<WalkerRec> recs(t->n_T);
+  CK(cudaMemcpyAsync(reps.data(), t->d_reps + (size_t)sim * t->n_T, t->n_T * sizeof(TemperRec), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(recs.data(), e->P.walkers + (size_t)sim * t->n_T, t->n_T * sizeof(WalkerRec), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  for (uint32_t r = 0; r < t->n_T; r++) {
+    sadmc_replica_state& o = out[r];
+    o.T = reps[r].T;
+    o.rejected_count = reps[r].rejected;
+    o.accepted_count = reps[r].accepted;
+    o.rejected_swap_count = reps[r].rejected_swap;
+    o.accepted_swap_count = reps[r].accepted_swap;
+    o.ignored_count = reps[r].ignored;
+    o.total_energy = reps[r].total_energy;
+    o.total_energy_squared = reps[r].total_energy_squared;
+    o.translation_scale = 1.0;
+    o.rng_s0 = recs[r].s0;
+    o.rng_s1 = recs[r].s1;
+    o.energy = recs[r].E;
+  }
+  return 0;
+}
+int sadmc_tempering_get_rng(sadmc_tempering* t, uint32_t sim, uint64_t s[2]) {
+  if (!t || !s) return fail(SADMC_ERR_INVALID, "null argument");
+  if (sim >= t->n_sim) return fail(SADMC_ERR_INVALID, "simulation %u out of range", sim);
+  CK(cudaMemcpyAsync(s, t->d_mc_rng + 2 * (size_t)sim, 16, cudaMemcpyDeviceToHost, t->e->stream));
+  CK(cudaStreamSynchronize(t->e->stream));
+  return 0;
+}
+int sadmc_tempering_system_len(sadmc_tempering* t, size_t* n) {
+  if (!t) return fail(SADMC_ERR_INVALID, "null argument");
+  return sadmc_system_len(t->e, n);
+}
+int sadmc_tempering_get_system(sadmc_tempering* t, uint32_t sim, uint32_t replica, double* buf, size_t n) {
+  if (!t) return fail(SADMC_ERR_INVALID, "null argument");
+  if (sim >= t->n_sim || replica >= t->n_T) return fail(SADMC_ERR_INVALID, "replica (%u, %u) out of range", sim, replica);
+  int src = temper_settle(t);
+  if (src) return src;
+  return sadmc_get_system(t->e, sim * t->n_T + replica, buf, n);
+}
+int sadmc_tempering_set_system(sadmc_tempering* t, uint32_t sim, uint32_t replica, const double* buf, size_t n) {
+  if (!t) return fail(SADMC_ERR_INVALID, "null argument");
+  if (sim >= t->n_sim || replica >= t->n_T) return fail(SADMC_ERR_INVALID, "replica (%u, %u) out of range", sim, replica);
+  t->settled = false;
+  return sadmc_set_system(t->e, sim * t->n_T + replica, buf, n);
 }
 
 // ---- trait shims -------------------------------------------------------------

@@ -18,6 +18,14 @@ struct ShimOut {
   int ok;
 };
 
+// one replica slot of a tempering simulation (tempering.cuh; `Replica`, src/mc/tempering.rs:46-73, minus system and generator)
+struct TemperRec {
+  double T;
+  unsigned long long rejected, accepted, rejected_swap, accepted_swap, ignored;
+  double total_energy, total_energy_squared;
+};
+
+typedef void (*temper_fn)(const DevParams, TemperRec*, unsigned long long);
 typedef void (*move_fn)(const DevParams, unsigned long long, unsigned long long);
 typedef void (*init_fn)(const DevParams, unsigned long long, int, long long, int, double, unsigned long long);
 typedef void (*shim_fn)(const DevParams, uint32_t, int, double, ShimOut*, double*);
@@ -25,6 +33,7 @@ typedef void (*shim_fn)(const DevParams, uint32_t, int, double, ShimOut*, double
 struct KernelSet {
   move_fn move[6]; // indexed by sadmc_method_kind (WL and INV_T_WL share)
   move_fn move_binning[6]; // SADMC_FLAG_BINNING: energy_binning.rs bookkeeping (book_binning.cuh); null where not built
+  temper_fn temper; // Replica::run_once x steps (tempering.cuh); null where not built
   init_fn init;
   shim_fn shim;
   int G, block;

@@ -3,10 +3,12 @@
 #include "kernel_set.cuh"
 #include "book_binning.cuh"
 #include "move_kernel.cuh"
+#include "tempering.cuh"
 
 namespace sadmc {
 
-// BINNING: also build the energy_binning.rs move kernels for this system (the `binning` binary's bookkeeping)
+// BINNING: also build the energy_binning.rs move kernels (the `binning` binary's bookkeeping) and the replica-exchange
+// move kernel (the `tempering` binary) for this system
 template <class Sys, bool BINNING = false>
 static KernelSet make_set(const DevParams& P) {
   KernelSet k;
@@ -21,6 +23,7 @@ static KernelSet make_set(const DevParams& P) {
     k.move_binning[SADMC_METHOD_SAMC] = move_kernel_binning<Sys, SADMC_METHOD_SAMC>;
     k.move_binning[SADMC_METHOD_WL] = move_kernel_binning<Sys, SADMC_METHOD_WL>;
     k.move_binning[SADMC_METHOD_INV_T_WL] = move_kernel_binning<Sys, SADMC_METHOD_WL>;
+    k.temper = temper_move_kernel<Sys>;
   }
   k.init = init_kernel<Sys>;
   k.shim = shim_kernel<Sys>;

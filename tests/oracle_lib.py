@@ -5,7 +5,7 @@ import subprocess
 
 import numpy as np
 
-from sad_monte_carlo_b200._abi import BinningState, Config, WalkerState
+from sad_monte_carlo_b200._abi import BinningState, Config, ReplicaState, WalkerState
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _LIB = None
@@ -62,6 +62,18 @@ def load_oracle():
     L.oracle_bench.restype = C.c_double
     L.oracle_bench.argtypes = [C.POINTER(Config), C.c_uint32, C.c_uint64, C.c_uint64]
     L.oracle_set_math_mode.argtypes = [C.c_int]
+    L.oracle_tempering_create.restype = C.c_void_p
+    L.oracle_tempering_create.argtypes = [C.POINTER(Config), C.c_uint32, f64p, C.c_uint32, C.c_uint64, f64p, C.c_size_t, C.c_uint64]
+    L.oracle_tempering_destroy.argtypes = [C.c_void_p]
+    L.oracle_tempering_run.argtypes = [C.c_void_p, C.c_uint64]
+    L.oracle_tempering_num_moves.restype = C.c_uint64
+    L.oracle_tempering_num_moves.argtypes = [C.c_void_p]
+    L.oracle_tempering_get_rng.argtypes = [C.c_void_p, u64p]
+    L.oracle_tempering_get_replicas.argtypes = [C.c_void_p, C.POINTER(ReplicaState)]
+    L.oracle_tempering_system_len.restype = C.c_size_t
+    L.oracle_tempering_system_len.argtypes = [C.c_void_p]
+    L.oracle_tempering_get_system.argtypes = [C.c_void_p, C.c_uint32, f64p, C.c_size_t]
+    L.oracle_rng_jump.argtypes = [u64p]
     L.oracle_binning_create.restype = C.c_void_p
     L.oracle_binning_create.argtypes = [C.POINTER(Config), C.c_uint32, f64p, C.c_size_t, C.c_uint64]
     L.oracle_binning_destroy.argtypes = [C.c_void_p]
@@ -230,4 +242,55 @@ class OracleBinningMC:
         n = self.L.oracle_binning_system_len(self.h)
         buf = np.zeros(n)
         assert self.L.oracle_binning_get_system(self.h, _ptr(buf, f64p), n) == 0
+        return buf
+
+
+class OracleTempering:
+    """One reference `tempering` process: `MC<Any>` of src/mc/tempering.rs, restated on the CPU."""
+
+    def __init__(self, cfg, T, canonical_steps=1, sim=0, system_state=None, attempts_override=0):
+        self.L = load_oracle()
+        self.T = np.ascontiguousarray(T, dtype=np.float64)
+        st, n = None, 0
+        if system_state is not None:
+            st = np.ascontiguousarray(system_state, dtype=np.float64)
+            n = st.size
+        self.h = self.L.oracle_tempering_create(C.byref(cfg), sim, _ptr(self.T, f64p), self.T.size, int(canonical_steps),
+                                                _ptr(st, f64p), n, attempts_override)
+        if not self.h:
+            raise RuntimeError("oracle_tempering_create: " + self.L.oracle_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.oracle_tempering_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_once(self, n_rounds=1):
+        if self.L.oracle_tempering_run(self.h, int(n_rounds)) != 0:
+            raise RuntimeError("oracle_tempering_run: " + self.L.oracle_last_error().decode())
+
+    @property
+    def moves(self):
+        return self.L.oracle_tempering_num_moves(self.h)
+
+    def rng(self):
+        s = np.zeros(2, np.uint64)
+        self.L.oracle_tempering_get_rng(self.h, _ptr(s, u64p))
+        return int(s[0]), int(s[1])
+
+    def replicas(self):
+        out = (ReplicaState * self.T.size)()
+        self.L.oracle_tempering_get_replicas(self.h, out)
+        return list(out)
+
+    def system(self, replica):
+        n = self.L.oracle_tempering_system_len(self.h)
+        buf = np.zeros(n)
+        assert self.L.oracle_tempering_get_system(self.h, replica, _ptr(buf, f64p), n) == 0
         return buf
