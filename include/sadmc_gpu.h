@@ -376,7 +376,7 @@ typedef struct sadmc_replica_state {
   double T;
   uint64_t rejected_count, accepted_count, rejected_swap_count, accepted_swap_count, ignored_count;
   double total_energy, total_energy_squared;
-  double translation_scale; /* always 1.0 (tempering.rs:88) */
+  double translation_scale; /* 1.0 from the constructor (tempering.rs:88) unless sadmc_tempering_set_translation_scales */
   uint64_t rng_s0, rng_s1;
   double energy; /* system.energy() */
 } sadmc_replica_state;
@@ -389,6 +389,10 @@ int sadmc_tempering_num_moves(sadmc_tempering* t, uint64_t* moves);        /* MC
 int sadmc_tempering_steps_per_round(sadmc_tempering* t, uint64_t* steps); /* moves per replica and round (274) */
 int sadmc_tempering_get_replicas(sadmc_tempering* t, uint32_t sim, sadmc_replica_state* out /* [n_T] */);
 int sadmc_tempering_get_rng(sadmc_tempering* t, uint32_t sim, uint64_t s[2]); /* MC::rng */
+/* `Replica::translation_scale` of replica r of every simulation := scale[r] (n_T values).  The reference's constructor
+ * fixes 1.0 and has no flag for it, but the field is part of the serialised state (tempering.rs:71-72), so a resumed
+ * reference run uses whatever the checkpoint holds; clusters and fluids need a step that shrinks with temperature. */
+int sadmc_tempering_set_translation_scales(sadmc_tempering* t, const double* scale /* [n_T] */);
 int sadmc_tempering_system_len(sadmc_tempering* t, size_t* n_doubles);
 int sadmc_tempering_get_system(sadmc_tempering* t, uint32_t sim, uint32_t replica, double* buf, size_t n);
 int sadmc_tempering_set_system(sadmc_tempering* t, uint32_t sim, uint32_t replica, const double* buf, size_t n);

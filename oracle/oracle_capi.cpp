@@ -491,6 +491,9 @@ int oracle_tempering_run(oracle_tmc* o, uint64_t n_rounds) {
   }
 }
 uint64_t oracle_tempering_num_moves(oracle_tmc* o) { return o->mc->moves; }
+void oracle_tempering_set_translation_scales(oracle_tmc* o, const double* scale) {
+  for (size_t r = 0; r < o->mc->replicas.size(); r++) o->mc->replicas[r].translation_scale = scale[r];
+}
 void oracle_tempering_get_rng(oracle_tmc* o, uint64_t* s) {
   s[0] = o->mc->rng.s0;
   s[1] = o->mc->rng.s1;

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "sadmc_tempering_steps_per_round": (C.c_int, [vp, u64p]),
     "sadmc_tempering_get_replicas": (C.c_int, [vp, C.c_uint32, C.POINTER(ReplicaState)]),
     "sadmc_tempering_get_rng": (C.c_int, [vp, C.c_uint32, u64p]),
+    "sadmc_tempering_set_translation_scales": (C.c_int, [vp, f64p]),
     "sadmc_tempering_system_len": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
     "sadmc_tempering_get_system": (C.c_int, [vp, C.c_uint32, C.c_uint32, f64p, C.c_size_t]),
     "sadmc_tempering_set_system": (C.c_int, [vp, C.c_uint32, C.c_uint32, f64p, C.c_size_t]),

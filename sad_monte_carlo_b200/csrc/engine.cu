@@ -1374,6 +1374,7 @@ int sadmc_tempering_create(const sadmc_config* cfg, const double* T, uint32_t n_
         TemperRec& q = reps[(size_t)k * n_T + r];
         memset(&q, 0, sizeof q);
         q.T = T[r];
+        q.tscale = 1.0; // Length::new(1.0), tempering.rs:88
       }
       xoroshiro_jump(g); // tempering.rs:164
       mc[2 * k] = g.s0;
@@ -1464,11 +1465,25 @@ int sadmc_tempering_get_replicas(sadmc_tempering* t, uint32_t sim, sadmc_replica
     o.ignored_count = reps[r].ignored;
     o.total_energy = reps[r].total_energy;
     o.total_energy_squared = reps[r].total_energy_squared;
-    o.translation_scale = 1.0;
+    o.translation_scale = reps[r].tscale;
     o.rng_s0 = recs[r].s0;
     o.rng_s1 = recs[r].s1;
     o.energy = recs[r].E;
   }
+  return 0;
+}
+int sadmc_tempering_set_translation_scales(sadmc_tempering* t, const double* scale) {
+  if (!t || !scale) return fail(SADMC_ERR_INVALID, "null argument");
+  sadmc_engine* e = t->e;
+  const size_t n = (size_t)t->n_sim * t->n_T;
+  std::vector<TemperRec> reps(n);
+  CK(cudaMemcpyAsync(reps.data(), t->d_reps, n * sizeof(TemperRec), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  for (uint32_t r = 0; r < t->n_T; r++)
+    if (!(scale[r] > 0)) return fail(SADMC_ERR_INVALID, "translation scale %u is not positive", r);
+  for (size_t k = 0; k < n; k++) reps[k].tscale = scale[k % t->n_T];
+  CK(cudaMemcpyAsync(t->d_reps, reps.data(), n * sizeof(TemperRec), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
   return 0;
 }
 int sadmc_tempering_get_rng(sadmc_tempering* t, uint32_t sim, uint64_t s[2]) {

@@ -23,6 +23,7 @@ struct TemperRec {
   double T;
   unsigned long long rejected, accepted, rejected_swap, accepted_swap, ignored;
   double total_energy, total_energy_squared;
+  double tscale; // Replica::translation_scale: 1.0 from the constructor (tempering.rs:88), a serialised field otherwise
 };
 
 typedef void (*temper_fn)(const DevParams, TemperRec*, unsigned long long);

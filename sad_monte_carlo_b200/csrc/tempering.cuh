@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) temper_move_kerne
     double e = 0.0;
     bool some = false;
     if (!ghost) {
-      some = sys.plan_move(rng, 1.0, zx, zf, e); // translation_scale: Length::new(1.0), tempering.rs:88
+      some = sys.plan_move(rng, r.tscale, zx, zf, e); // translation_scale: Length::new(1.0) unless set (tempering.rs:88)
       if (some) {
         const double beta_delta_e = (e - sys.energy()) / r.T;
         // beta_delta_e < 0.0 || rng.gen::<f64>() < (-beta_delta_e).exp()  (tempering.rs:99): the uniform is drawn for

@@ -90,6 +90,23 @@ class TemperingMC:
         buf = np.ascontiguousarray(buf, dtype=np.float64)
         self._check(self.L.sadmc_tempering_set_system(self.h, sim, replica, buf.ctypes.data_as(f64p), buf.size))
 
+    def set_translation_scales(self, scales):
+        """`Replica::translation_scale` per temperature (the reference's constructor fixes 1.0, tempering.rs:88)."""
+        a = np.ascontiguousarray(scales, dtype=np.float64)
+        assert a.size == self.n_T
+        self._check(self.L.sadmc_tempering_set_translation_scales(self.h, a.ctypes.data_as(f64p)))
+
+    def all_replicas(self):
+        """Counters and moments of every replica as arrays [n_sim, n_T] (one device read per simulation)."""
+        keys = ["accepted_count", "rejected_count", "accepted_swap_count", "rejected_swap_count", "ignored_count",
+                "total_energy", "total_energy_squared", "energy"]
+        out = {k: np.zeros((self.n_sim, self.n_T)) for k in keys}
+        for s in range(self.n_sim):
+            for r, q in enumerate(self.replicas(s)):
+                for k in keys:
+                    out[k][s, r] = getattr(q, k)
+        return out
+
     def mean_energy(self, sim=0):
         """plotting/parse-tempering.py:57-73: <E> and <E^2> per temperature from the accumulated moments (the number of
         samples is moves + swap attempts - ignored, as there)."""

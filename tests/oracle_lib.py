@@ -74,6 +74,7 @@ def load_oracle():
     L.oracle_tempering_system_len.argtypes = [C.c_void_p]
     L.oracle_tempering_get_system.argtypes = [C.c_void_p, C.c_uint32, f64p, C.c_size_t]
     L.oracle_rng_jump.argtypes = [u64p]
+    L.oracle_tempering_set_translation_scales.argtypes = [C.c_void_p, f64p]
     L.oracle_binning_create.restype = C.c_void_p
     L.oracle_binning_create.argtypes = [C.POINTER(Config), C.c_uint32, f64p, C.c_size_t, C.c_uint64]
     L.oracle_binning_destroy.argtypes = [C.c_void_p]
@@ -278,6 +279,10 @@ class OracleTempering:
     @property
     def moves(self):
         return self.L.oracle_tempering_num_moves(self.h)
+
+    def set_translation_scales(self, scales):
+        a = np.ascontiguousarray(scales, dtype=np.float64)
+        self.L.oracle_tempering_set_translation_scales(self.h, _ptr(a, f64p))
 
     def rng(self):
         s = np.zeros(2, np.uint64)

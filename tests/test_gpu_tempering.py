@@ -87,6 +87,28 @@ def test_lj13_reference_order_arithmetic():
     _check(cfg, geometric_spacing(0.05, 0.5, 6), 3, [1, 150], sims=(0, 7), state=state)
 
 
+def test_lj13_with_per_temperature_translation_scales():
+    # Replica::translation_scale is serialised state (tempering.rs:71-72); the constructor's 1.0 accepts next to nothing
+    # for a cluster, a step that shrinks with temperature does
+    state = _lj_state(13, 2.0)
+    cfg = make_config("lj", N=13, lj_radius=2.0, n_walkers=8, seed=9, lanes_per_walker=1, init_mode=_abi.INIT_EXTERNAL)
+    T = geometric_spacing(0.05, 0.5, 6)
+    scales = [0.1 * np.sqrt(t) for t in T]
+    mc = TemperingMC(cfg, T, 3)
+    mc.set_translation_scales(scales)
+    for k in range(mc.n_sim):
+        for r in range(mc.n_T):
+            mc.set_system(k, r, state)
+    o = OracleTempering(cfg, T, 3, sim=5, system_state=state)
+    o.set_translation_scales(scales)
+    mc.run_once(200)
+    o.run_once(200)
+    assert_sim_equal(mc, 5, o, "scaled")
+    reps = mc.replicas(5)
+    assert all(r.accepted_count > 0.1 * (r.accepted_count + r.rejected_count) for r in reps)
+    assert [r.translation_scale for r in reps] == scales
+
+
 def test_lj31_fast_math_tier():
     state = _lj_state(31, 2.5)
     cfg = make_config("lj", N=31, lj_radius=2.5, n_walkers=40, seed=9, lanes_per_walker=1, init_mode=_abi.INIT_EXTERNAL,
