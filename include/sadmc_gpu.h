@@ -396,6 +396,8 @@ int sadmc_tempering_set_translation_scales(sadmc_tempering* t, const double* sca
 int sadmc_tempering_system_len(sadmc_tempering* t, size_t* n_doubles);
 int sadmc_tempering_get_system(sadmc_tempering* t, uint32_t sim, uint32_t replica, double* buf, size_t n);
 int sadmc_tempering_set_system(sadmc_tempering* t, uint32_t sim, uint32_t replica, const double* buf, size_t n);
+/* sadmc_cell_box for the periodic fluids (what a checkpoint's `cell` records). */
+int sadmc_tempering_cell_box(sadmc_tempering* t, double box_diagonal[3], double* r_cutoff);
 /* Device time of the last sadmc_tempering_run (move and swap kernels), CUDA events. */
 int sadmc_tempering_last_run_ms(sadmc_tempering* t, float* ms);
 

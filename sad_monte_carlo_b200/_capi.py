@@ -67,6 +67,7 @@ PROTOTYPES = {
     "sadmc_tempering_system_len": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
     "sadmc_tempering_get_system": (C.c_int, [vp, C.c_uint32, C.c_uint32, f64p, C.c_size_t]),
     "sadmc_tempering_set_system": (C.c_int, [vp, C.c_uint32, C.c_uint32, f64p, C.c_size_t]),
+    "sadmc_tempering_cell_box": (C.c_int, [vp, f64p, f64p]),
     "sadmc_tempering_last_run_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "sadmc_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, f64p]),
     "sadmc_selftest_exp_cmp": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, u64p, u64p]),

@@ -1,0 +1,182 @@
+"""The reference's `binning` command line on the GPU engine (src/bin/binning.rs: `EnergyMC<Any>` of
+src/mc/energy_binning.rs over `binning::Bins`).
+
+    python -m sad_monte_carlo_b200.binning --fake-linear --histogram-bin 0.01 --translation-scale 0.05 \\
+        --sad-min-T 0.001 --max-iter 1e9 --save-as sad-linear-0.01.yaml            (fake/run-fake.py:25-36)
+
+Flags are the `histogram` command line's (histogram.py) with `BinningParams` in place of `--energy-bin`
+(binning.rs:50-69): `--histogram-bin <de>` (default 1.0); `--linear-bin` and `--high-resolution-de` are parsed and refused
+(no device kernel).  Checkpoints are written in the reference's serde schema for this Monte Carlo -- one document per
+walker, `bins: {Histogram: {min, min_e, max_e, width, lnw: BinCounts, extra: {name: BinCounts}}}` (histogram.rs:12-32,
+99-111) -- so `plotting/parse-binning.py` reads them.  Resuming such a checkpoint is not built: `--save-as` on an
+existing file and `--resume-from` are refused.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+from . import _abi
+from . import histogram as H
+
+BINNING_FLAGS = {"histogram-bin": H.F64, "linear-bin": H.F64, "high-resolution-de": H.F64}
+H.ALL_FLAGS.update(BINNING_FLAGS)
+
+
+def _bincounts(total, count, max_count=None, max_total=None, centres=None):
+    """`BinCounts` (histogram.rs:12-32).  The aggregates the sampler never reads are reported as what a full rescan of
+    the vectors gives (the reference maintains them lazily, histogram.rs:60-80); max_count / max_total, which the
+    sampler does read, are the engine's exact running values where given."""
+    total = np.asarray(total, float)
+    count = np.asarray(count)
+    n = len(total)
+    i_t = int(np.argmax(total)) if n else 0
+    i_c = int(np.argmax(count)) if n else 0
+    return {"total": [float(x) for x in total], "min_total": float(total.min()) if n else 0.0,
+            "max_total": float(max_total if max_total is not None else (total.max() if n else 0.0)),
+            "e_max_total": float(centres[i_t]) if n and centres is not None else float("-inf"),
+            "count": [int(x) for x in count], "min_count": int(count.min()) if n else 0,
+            "max_count": int(max_count if max_count is not None else (count.max() if n else 0)),
+            "e_max_count": float(centres[i_c]) if n and centres is not None else float("-inf"),
+            "total_count": int(count.sum())}
+
+
+def walker_document(engine, w, save_as="resume.yaml", report=None, movies=None, save=None):
+    """The serde document of walker `w`: energy_binning.rs:92-126 (`EnergyMC`), 128-148 (`Method`), binning.rs:71-78 (`Bins`)."""
+    from .checkpoint import EXTRA_LABEL, _opt, _system_document
+    cfg = engine.cfg
+    st = engine.binning_walker(w)
+    if st.status != 0:
+        raise RuntimeError("walker %d is halted (status %d)" % (w, st.status))
+    b = engine.binning_bins(w)
+    n = st.bins_len
+    centres = st.bins_min + (np.arange(n) + 0.5) * st.bins_width
+    extra = {}
+    if n:
+        extra["energy"] = _bincounts(b["energy_total"], b["energy_count"], centres=centres)
+        if b["t_found_count"].any():
+            extra["t_found"] = _bincounts(b["t_found_total"], b["t_found_count"], max_total=st.t_found_max_total, centres=centres)
+        if st.method in (_abi.METHOD_WL, _abi.METHOD_INV_T_WL) or b["hist_count"].any():
+            extra["hist"] = _bincounts(np.zeros(n), b["hist_count"], centres=centres)
+        if cfg.system in EXTRA_LABEL and b["extra_count"].any():
+            extra[EXTRA_LABEL[cfg.system]] = _bincounts(b["extra_total"], b["extra_count"], centres=centres)
+    m = st.method
+    if m == _abi.METHOD_SAD:
+        method = {"Sad": {"num_states": int(st.num_states), "min_T": cfg.sad_min_T, "too_lo": st.too_lo, "too_hi": st.too_hi, "tL": int(st.tL),
+                          "tF": st.tF, "latest_parameter": st.latest_parameter}}
+    elif m == _abi.METHOD_SAMC:
+        method = {"Samc": {"t0": st.samc_t0}}
+    else:
+        method = {"WL": {"gamma": st.wl_gamma, "inv_t": bool(st.wl_inv_t), "min_gamma": _opt(cfg.wl_min_gamma)}}
+    lnw = _bincounts(b["lnw_total"], b["lnw_count"], max_count=st.lnw_max_count, centres=centres)
+    lnw["total_count"] = int(st.lnw_total_count)
+    move_plan = ({"TranslationScale": cfg.move_value} if cfg.move_plan == _abi.MOVE_TRANSLATION_SCALE else {"AcceptanceRate": cfg.move_value})
+    return {
+        "system": _system_document(cfg, engine.system(w), engine.cell_box() if cfg.system in (_abi.SYS_WCA, _abi.SYS_SW) else None),
+        "method": method, "moves": int(st.moves), "time_L": 0, "accepted_moves": int(st.accepted_moves),
+        "min_allowed_energy": _opt(cfg.min_allowed_energy), "max_allowed_energy": _opt(cfg.max_allowed_energy),
+        "move_plan": move_plan, "translation_scale": st.translation_scale, "acceptance_rate": st.acceptance_rate,
+        "rng": {"s0": int(st.rng_s0), "s1": int(st.rng_s1)}, "save_as": str(save_as),
+        "report": report if report is not None else {"max_iter": "Never", "max_independent_samples": None, "quiet": True},
+        "save": save if save is not None else {"save_time_seconds": 3600.0},
+        "movies": movies if movies is not None else {"movie_time": None, "which_frame": 0, "period": "Never"},
+        "manager": {},
+        "bins": {"Histogram": {"min": st.bins_min, "min_e": st.bins_min_e, "max_e": st.bins_max_e, "width": st.bins_width, "lnw": lnw,
+                               "extra": extra}},
+        "high_resolution": None,
+    }
+
+
+def save(engine, save_as, walkers=None, **plugin_docs):
+    """MonteCarlo::checkpoint for a binning engine: one file per walker, all or nothing (as checkpoint.save)."""
+    from . import checkpoint as ck
+    ext = os.path.splitext(str(save_as))[1].lstrip(".")
+    walkers = list(range(engine.n_walkers) if walkers is None else walkers)
+    left, failed = engine.num_halted()
+    if left or failed:
+        raise RuntimeError("no checkpoint written: %d walker(s) left the bin window and %d failed verify_energy" % (left, failed))
+    staged = []
+    try:
+        for w in walkers:
+            p = ck.walker_path(save_as, w, engine.n_walkers)
+            staged.append((ck.stage(p, ck.dumps(walker_document(engine, w, save_as=p, **plugin_docs), ext)), p))
+        for tmp, p in staged:
+            os.replace(tmp, p)
+    except BaseException:
+        for tmp, _ in staged:
+            if os.path.exists(tmp):
+                os.unlink(tmp)
+        raise
+    return [p for _, p in staged]
+
+
+def config_from_flags(flags):
+    """`AnyParams` + energy_binning.rs `EnergyMCParams` (52-69) -> sadmc_config with SADMC_FLAG_BINNING."""
+    if "linear-bin" in flags:
+        raise H.UsageError("--linear-bin: binning::linear (interpolated ln w, src/mc/binning/linear.rs) has no device kernel")
+    if "high-resolution-de" in flags:
+        raise H.UsageError("--high-resolution-de: the second, finer histogram (energy_binning.rs:62-63, 328-330) is not built")
+    if "energy-bin" in flags:
+        raise H.UsageError("--energy-bin belongs to `histogram`; `binning` takes --histogram-bin (binning.rs:50-69)")
+    if "T" in flags or "canonical-T" in flags:
+        raise H.UsageError("energy_binning.rs has no canonical method (MethodParams, energy_binning.rs:22-40)")
+    f = dict(flags)
+    f["energy-bin"] = f.pop("histogram-bin", 1.0)  # BinningParams::default: Histogram { bin: 1.0 }
+    cfg = H.config_from_flags(f)
+    cfg.flags |= _abi.FLAG_BINNING
+    return cfg
+
+
+def main(argv=None, out=print):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    flags = H.parse_flags(argv)
+    if flags.get("help"):
+        out(__doc__)
+        return 0
+    if "resume-from" in flags:
+        raise H.UsageError("--resume-from: resuming a `binning` checkpoint is not built")
+    pp = H.plugin_params(flags)
+    cfg = config_from_flags(flags)
+    save_as = flags.get("save-as", "resume.yaml")
+    if os.path.splitext(save_as)[1].lstrip(".") not in ("yaml", "json", "cbor"):
+        raise H.UsageError("I don't know how to create file %r" % save_as)
+    from . import checkpoint as ck
+    if "save-as" in flags and os.path.exists(ck.walker_path(save_as, 0, cfg.n_walkers)):
+        raise H.UsageError("%s exists: resuming a `binning` checkpoint is not built (remove the file to start over)" % save_as)
+    if flags.get("dry-run"):
+        out(json.dumps({"config": H.config_summary(cfg), "binning": {"Histogram": {"bin": cfg.energy_bin}}, "plugins": pp, "save_as": save_as}))
+        return 0
+    from . import plugins
+    from .engine import WalkerEngine
+    engine = WalkerEngine(cfg)
+
+    class BinningMC(plugins.EngineMC):
+        def checkpoint(self):
+            return save(self.engine, self.save_as, walkers=self.checkpoint_walkers, **self._docs())
+
+        def save_movie_frame(self, moves):
+            d = os.path.splitext(self.save_as)[0]
+            return save(self.engine, os.path.join(d, "%014d.cbor" % moves), walkers=self.checkpoint_walkers, **self._docs())
+
+    report = plugins.Report(pp["max_iter"], pp["max_independent_samples"], pp["quiet"], out=out)
+    saver = plugins.Save(pp["save_time"])
+    movies = plugins.Movie(pp["movie_time"])
+    kw = flags.get("checkpoint-walkers")
+    mc = BinningMC(engine, save_as, list(range(kw)) if kw is not None else None, report, saver, movies)
+    manager = plugins.PluginManager()
+    launches = 0
+    while True:
+        n = manager.moves_until_next_action()
+        if "max-launch" in flags:
+            n = min(n, flags["max-launch"])
+        engine.run(n)
+        launches += 1
+        if manager.run(mc, [report, saver, movies], moves_made=n) == plugins.Action.EXIT:
+            break
+    engine.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

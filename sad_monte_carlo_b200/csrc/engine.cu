@@ -1429,6 +1429,10 @@ int sadmc_tempering_run(sadmc_tempering* t, uint64_t n_rounds) {
   t->rounds += n_rounds;
   return 0;
 }
+int sadmc_tempering_cell_box(sadmc_tempering* t, double box_diagonal[3], double* r_cutoff) {
+  if (!t) return fail(SADMC_ERR_INVALID, "null argument");
+  return sadmc_cell_box(t->e, box_diagonal, r_cutoff);
+}
 int sadmc_tempering_last_run_ms(sadmc_tempering* t, float* ms) {
   if (!t || !ms) return fail(SADMC_ERR_INVALID, "null argument");
   *ms = t->last_ms;
