@@ -285,8 +285,11 @@ def run_ours(args):
                     "what": "sadmc_set_systems + sadmc_set_rngs (pinned host) -> sadmc_run -> sadmc_fold + sadmc_get_energies (host)"},
             "roofline": {"bound": "fp64", "achieved": per_gpu_moves_s * FLOPS_PER_MOVE / 1e12, "peak": fp64.value,
                          "unit": "TFLOP/s", "frac": (per_gpu_moves_s * FLOPS_PER_MOVE / 1e12) / fp64.value if fp64.value else None,
-                         "traffic": None, "per_unit": "900 FP64 flop per move (30 per pair x 30 pairs), divide = 1 flop; "
-                                                      "`achieved` = 900 x moves per launch / average launch duration",
+                         "traffic": traffic["dram_bytes_per_move"] * W * args.moves_per_step if traffic else None,
+                         "traffic_unit": "DRAM bytes per launch (measured bytes per move of the committed ncu capture x moves per launch; "
+                                         "algorithmic: 80 B per move)",
+                         "per_unit": "900 FP64 flop per move (30 per pair x 30 pairs), divide = 1 flop; "
+                                     "`achieved` = 900 x moves per launch / average launch duration",
                          "peak_source": "DFMA microkernel in this library, measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "kernel": "move_kernel<LjThreadSys<%s, 31, %d>, SAD>" % ("exact" if args.exact else "fast", args.lanes), "ms_per_launch": ms_max / args.steps},
             "roofline_hbm": {"bound": "hbm", "achieved": per_gpu_moves_s * BYTES_PER_MOVE / 1e9, "peak": peaks.get("hbm_gbs"),

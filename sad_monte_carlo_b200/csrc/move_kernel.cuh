@@ -402,7 +402,11 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const
       }
     }
     // ... and what does not depend on it is computed while it is in flight: next move's sqrt(1/moves),
+#ifdef SADMC_EXP_RSQRT /* experiment: tolerance tier only (acceptance_rate is a diagnostic unless the move plan is AcceptanceRate) */
+    recent_next = Sys::FAST_BOOK ? rsqrt_newton((double)(moves + 1)) : sqrt(1.0 / (double)(moves + 1));
+#else
     recent_next = sqrt(1.0 / (double)(moves + 1));
+#endif
     // the previous move's bookkeeping (DEFER),
     if constexpr (DEFER) {
       if (pend) {
