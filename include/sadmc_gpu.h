@@ -278,6 +278,13 @@ int sadmc_get_binning_walker(sadmc_engine* e, uint32_t w, sadmc_binning_state* o
 int sadmc_get_binning_bins(sadmc_engine* e, uint32_t w, uint32_t cap, double* lnw_total, uint64_t* lnw_count,
                            double* energy_total, uint64_t* energy_count, double* t_found_total, uint64_t* t_found_count,
                            uint64_t* hist_count, double* extra_total, uint64_t* extra_count);
+/* Resume of a SADMC_FLAG_BINNING engine (created with SADMC_INIT_EXTERNAL): sadmc_set_system(s), then this for every
+ * walker -- the inverse of the two getters above, same field meanings (t_found_*, hist_count, extra_* may be NULL) -- then
+ * sadmc_resume(e, moves).  The resumed engine continues bit for bit like the one that was checkpointed. */
+int sadmc_set_binning_walker(sadmc_engine* e, uint32_t w, const sadmc_binning_state* s, const double* lnw_total,
+                             const uint64_t* lnw_count, const double* energy_total, const uint64_t* energy_count,
+                             const double* t_found_total, const uint64_t* t_found_count, const uint64_t* hist_count,
+                             const double* extra_total, const uint64_t* extra_count);
 /* System configuration of walker w as f64s.  Layout: LJ/WCA/SW: x0,y0,z0,x1,..
  * (3N), then E, then error (WCA/LJ; 0 for SW).  Fake/ErfInv/TwoWells:
  * position[dim] (+ d_squared for two-wells).  Ising: N*N spins as +-1.0, then E. */
@@ -389,6 +396,12 @@ int sadmc_tempering_num_moves(sadmc_tempering* t, uint64_t* moves);        /* MC
 int sadmc_tempering_steps_per_round(sadmc_tempering* t, uint64_t* steps); /* moves per replica and round (274) */
 int sadmc_tempering_get_replicas(sadmc_tempering* t, uint32_t sim, sadmc_replica_state* out /* [n_T] */);
 int sadmc_tempering_get_rng(sadmc_tempering* t, uint32_t sim, uint64_t s[2]); /* MC::rng */
+/* Resume (tempering.rs:196-213 deserialises the whole MC): counters, moments, translation scales and generators of the
+ * replicas of one simulation, the simulation's own generator, and MC::moves (a multiple of steps x replicas); systems go
+ * back with sadmc_tempering_set_system. */
+int sadmc_tempering_set_replicas(sadmc_tempering* t, uint32_t sim, const sadmc_replica_state* in /* [n_T] */);
+int sadmc_tempering_set_rng(sadmc_tempering* t, uint32_t sim, const uint64_t s[2]);
+int sadmc_tempering_set_num_moves(sadmc_tempering* t, uint64_t moves);
 /* `Replica::translation_scale` of replica r of every simulation := scale[r] (n_T values).  The reference's constructor
  * fixes 1.0 and has no flag for it, but the field is part of the serialised state (tempering.rs:71-72), so a resumed
  * reference run uses whatever the checkpoint holds; clusters and fluids need a step that shrinks with temperature. */

@@ -32,6 +32,7 @@ PROTOTYPES = {
     "sadmc_get_bins": (C.c_int, [vp, C.c_uint32, C.c_uint32, u64p, u64p, f64p, f64p, f64p, u64p, u8p, u64p, f64p, u64p]),
     "sadmc_get_binning_walker": (C.c_int, [vp, C.c_uint32, C.POINTER(BinningState)]),
     "sadmc_get_binning_bins": (C.c_int, [vp, C.c_uint32, C.c_uint32, f64p, u64p, f64p, u64p, f64p, u64p, u64p, f64p, u64p]),
+    "sadmc_set_binning_walker": (C.c_int, [vp, C.c_uint32, C.POINTER(BinningState), f64p, u64p, f64p, u64p, f64p, u64p, u64p, f64p, u64p]),
     "sadmc_system_len": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
     "sadmc_get_system": (C.c_int, [vp, C.c_uint32, f64p, C.c_size_t]),
     "sadmc_set_system": (C.c_int, [vp, C.c_uint32, f64p, C.c_size_t]),
@@ -63,6 +64,9 @@ PROTOTYPES = {
     "sadmc_tempering_steps_per_round": (C.c_int, [vp, u64p]),
     "sadmc_tempering_get_replicas": (C.c_int, [vp, C.c_uint32, C.POINTER(ReplicaState)]),
     "sadmc_tempering_get_rng": (C.c_int, [vp, C.c_uint32, u64p]),
+    "sadmc_tempering_set_replicas": (C.c_int, [vp, C.c_uint32, C.POINTER(ReplicaState)]),
+    "sadmc_tempering_set_rng": (C.c_int, [vp, C.c_uint32, u64p]),
+    "sadmc_tempering_set_num_moves": (C.c_int, [vp, C.c_uint64]),
     "sadmc_tempering_set_translation_scales": (C.c_int, [vp, f64p]),
     "sadmc_tempering_system_len": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
     "sadmc_tempering_get_system": (C.c_int, [vp, C.c_uint32, C.c_uint32, f64p, C.c_size_t]),

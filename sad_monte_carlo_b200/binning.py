@@ -8,8 +8,8 @@ Flags are the `histogram` command line's (histogram.py) with `BinningParams` in 
 (binning.rs:50-69): `--histogram-bin <de>` (default 1.0); `--linear-bin` and `--high-resolution-de` are parsed and refused
 (no device kernel).  Checkpoints are written in the reference's serde schema for this Monte Carlo -- one document per
 walker, `bins: {Histogram: {min, min_e, max_e, width, lnw: BinCounts, extra: {name: BinCounts}}}` (histogram.rs:12-32,
-99-111) -- so `plotting/parse-binning.py` reads them.  Resuming such a checkpoint is not built: `--save-as` on an
-existing file and `--resume-from` are refused.
+99-111) -- so `plotting/parse-binning.py` reads them.  `--save-as` on an existing checkpoint set resumes it
+(mc/mod.rs:66-84: state from the file, report / save parameters from the flags) and continues bit for bit.
 """
 import json
 import os
@@ -88,6 +88,73 @@ def walker_document(engine, w, save_as="resume.yaml", report=None, movies=None, 
     }
 
 
+def restore_walker(engine, w, doc):
+    """Feed a `binning` document back into walker `w` of an engine created with INIT_EXTERNAL + FLAG_BINNING (then
+    engine.resume(moves)): what `MonteCarlo::from_args` does with an existing --save-as file (mc/mod.rs:70-84)."""
+    from .checkpoint import _system_image
+    cfg = engine.cfg
+    engine.set_system(w, _system_image(cfg, doc["system"], engine.system_len))
+    st = _abi.BinningState()
+    st.moves, st.accepted_moves = doc["moves"], doc["accepted_moves"]
+    st.acceptance_rate, st.translation_scale = doc["acceptance_rate"], doc["translation_scale"]
+    st.rng_s0, st.rng_s1 = doc["rng"]["s0"], doc["rng"]["s1"]
+    kind, h = next(iter(doc["bins"].items()))
+    if kind != "Histogram":
+        raise NotImplementedError("bins variant %r has no device kernel" % kind)
+    n = len(h["lnw"]["total"])
+    st.bins_min, st.bins_width, st.bins_len = h["min"], h["width"], n
+    st.bins_min_e, st.bins_max_e = h["min_e"], h["max_e"]
+    st.lnw_max_count, st.lnw_total_count = h["lnw"]["max_count"], h["lnw"]["total_count"]
+    mtag, m = next(iter(doc["method"].items()))
+    if mtag == "Sad":
+        st.method = _abi.METHOD_SAD
+        st.too_lo, st.too_hi, st.latest_parameter, st.tF = m["too_lo"], m["too_hi"], m["latest_parameter"], m["tF"]
+        st.tL, st.num_states = m["tL"], m["num_states"]
+    elif mtag == "Samc":
+        st.method, st.samc_t0 = _abi.METHOD_SAMC, m["t0"]
+    else:
+        st.method = _abi.METHOD_INV_T_WL if m["inv_t"] else _abi.METHOD_WL
+        st.wl_gamma, st.wl_inv_t = m["gamma"], int(m["inv_t"])
+    ex = h.get("extra", {})
+    arrays = {"lnw_total": h["lnw"]["total"], "lnw_count": h["lnw"]["count"]}
+    zero_f, zero_u = np.zeros(n), np.zeros(n, np.uint64)
+    arrays["energy_total"] = ex["energy"]["total"] if "energy" in ex else zero_f
+    arrays["energy_count"] = ex["energy"]["count"] if "energy" in ex else zero_u
+    if "t_found" in ex:
+        arrays["t_found_total"], arrays["t_found_count"] = ex["t_found"]["total"], ex["t_found"]["count"]
+        st.t_found_max_total = ex["t_found"]["max_total"]
+    if "hist" in ex:
+        arrays["hist_count"] = ex["hist"]["count"]
+        st.hist_min_count, st.hist_total_count = ex["hist"]["min_count"], ex["hist"]["total_count"]
+    for label, bc in ex.items():
+        if label not in ("energy", "t_found", "hist"):
+            arrays["extra_total"], arrays["extra_count"] = bc["total"], bc["count"]
+    tag, body = next(iter(doc["system"].items()))
+    st.energy = body["E"] if "E" in body else engine.compute_energy(w)  # the analytic systems keep no cached energy
+    engine.set_binning_walker(w, st, arrays)
+
+
+def resume(cfg, save_as):
+    """An engine continued from the per-walker documents written by save()."""
+    from . import checkpoint as ck
+    from .engine import WalkerEngine
+    docs = [ck.load(ck.walker_path(save_as, w, cfg.n_walkers)) for w in range(cfg.n_walkers)]
+    moves = {d["moves"] for d in docs}
+    if len(moves) != 1:
+        raise ValueError("walker checkpoints disagree on moves: %s" % sorted(moves)[:4])
+    for d in docs:
+        if "Histogram" not in d.get("bins", {}):
+            raise ValueError("%s is not a `binning` checkpoint (bins: {Histogram: ...})" % save_as)
+        if d["bins"]["Histogram"]["width"] != cfg.energy_bin:
+            raise ValueError("checkpoint bin width %r differs from --histogram-bin %r" % (d["bins"]["Histogram"]["width"], cfg.energy_bin))
+    cfg.init_mode = _abi.INIT_EXTERNAL
+    engine = WalkerEngine(cfg)
+    for w, d in enumerate(docs):
+        restore_walker(engine, w, d)
+    engine.resume(moves.pop())
+    return engine
+
+
 def save(engine, save_as, walkers=None, **plugin_docs):
     """MonteCarlo::checkpoint for a binning engine: one file per walker, all or nothing (as checkpoint.save)."""
     from . import checkpoint as ck
@@ -135,21 +202,30 @@ def main(argv=None, out=print):
         out(__doc__)
         return 0
     if "resume-from" in flags:
-        raise H.UsageError("--resume-from: resuming a `binning` checkpoint is not built")
+        raise H.UsageError("--resume-from: give the system flags and --save-as <the checkpoint> instead (the configuration is not rebuilt from a `binning` document)")
     pp = H.plugin_params(flags)
     cfg = config_from_flags(flags)
     save_as = flags.get("save-as", "resume.yaml")
     if os.path.splitext(save_as)[1].lstrip(".") not in ("yaml", "json", "cbor"):
         raise H.UsageError("I don't know how to create file %r" % save_as)
     from . import checkpoint as ck
-    if "save-as" in flags and os.path.exists(ck.walker_path(save_as, 0, cfg.n_walkers)):
-        raise H.UsageError("%s exists: resuming a `binning` checkpoint is not built (remove the file to start over)" % save_as)
+    resuming = "save-as" in flags and os.path.exists(ck.walker_path(save_as, 0, cfg.n_walkers))  # mc/mod.rs:66-84
     if flags.get("dry-run"):
-        out(json.dumps({"config": H.config_summary(cfg), "binning": {"Histogram": {"bin": cfg.energy_bin}}, "plugins": pp, "save_as": save_as}))
+        out(json.dumps({"config": H.config_summary(cfg), "binning": {"Histogram": {"bin": cfg.energy_bin}}, "plugins": pp, "save_as": save_as,
+                        "resuming": resuming}))
         return 0
     from . import plugins
     from .engine import WalkerEngine
-    engine = WalkerEngine(cfg)
+    movie_state = None
+    if resuming:
+        try:
+            engine = resume(cfg, save_as)
+        except (ValueError, OSError) as ex:
+            raise H.UsageError(str(ex))
+        out("Resuming from file %r" % save_as)
+        movie_state = ck.load(ck.walker_path(save_as, 0, cfg.n_walkers)).get("movies")
+    else:
+        engine = WalkerEngine(cfg)
 
     class BinningMC(plugins.EngineMC):
         def checkpoint(self):
@@ -159,9 +235,11 @@ def main(argv=None, out=print):
             d = os.path.splitext(self.save_as)[0]
             return save(self.engine, os.path.join(d, "%014d.cbor" % moves), walkers=self.checkpoint_walkers, **self._docs())
 
-    report = plugins.Report(pp["max_iter"], pp["max_independent_samples"], pp["quiet"], out=out)
-    saver = plugins.Save(pp["save_time"])
+    report = plugins.Report(pp["max_iter"], pp["max_independent_samples"], pp["quiet"], out=out, resumed=resuming)
+    saver = plugins.Save(pp["save_time"], resumed=resuming)
     movies = plugins.Movie(pp["movie_time"])
+    if movie_state is not None:
+        movies.restore(movie_state)
     kw = flags.get("checkpoint-walkers")
     mc = BinningMC(engine, save_as, list(range(kw)) if kw is not None else None, report, saver, movies)
     manager = plugins.PluginManager()

@@ -903,6 +903,108 @@ int sadmc_get_binning_bins(sadmc_engine* e, uint32_t w, uint32_t cap, double* ln
   return 0;
 }
 
+// resume for SADMC_FLAG_BINNING engines: the inverse of sadmc_get_binning_walker / sadmc_get_binning_bins
+int sadmc_set_binning_walker(sadmc_engine* e, uint32_t w, const sadmc_binning_state* s, const double* lnw_total, const uint64_t* lnw_count,
+                             const double* energy_total, const uint64_t* energy_count, const double* t_found_total, const uint64_t* t_found_count,
+                             const uint64_t* hist_count, const double* extra_total, const uint64_t* extra_count) {
+  int rc = need_binning(e);
+  if (rc) return rc;
+  if (!s || !lnw_total || !lnw_count || !energy_total || !energy_count)
+    return fail(SADMC_ERR_INVALID, "null argument (lnw_total, lnw_count, energy_total, energy_count are required)");
+  if (w >= e->P.n_walkers) return fail(SADMC_ERR_INVALID, "walker %u out of range", w);
+  if (e->cfg.init_mode != SADMC_INIT_EXTERNAL) return fail(SADMC_ERR_INVALID, "resume needs an engine created with SADMC_INIT_EXTERNAL");
+  const DevParams& P = e->P;
+  if (s->bins_width != P.width) return fail(SADMC_ERR_INVALID, "checkpoint bin width %g differs from the engine's %g", s->bins_width, P.width);
+  const size_t n = s->bins_len;
+  if (n == 0) return fail(SADMC_ERR_INVALID, "a checkpoint without bins (moves == 0) is a fresh start: create the engine without SADMC_INIT_EXTERNAL");
+  // window bin j covers [(k_base + j) width, (k_base + j + 1) width); bins_min sits on such an edge up to the rounding of
+  // the repeated `min -= width` (histogram.rs:159)
+  const long long lo = (long long)std::floor(s->bins_min / P.width + 0.5) - e->k_base;
+  if (lo < 0 || lo + (long long)n > (long long)P.cap)
+    return fail(SADMC_ERR_WINDOW, "checkpointed bins [%g, %g) do not fit the device window", s->bins_min, s->bins_min + n * P.width);
+  WalkerRec old;
+  rc = fetch_walker(e, w, &old);
+  if (rc) return rc;
+  WalkerRec r;
+  memset(&r, 0, sizeof r);
+  r.err = old.err; // the system-side fields that sadmc_set_system(s) already placed in the record
+  r.d_squared = old.d_squared;
+  r.s0 = s->rng_s0;
+  r.s1 = s->rng_s1;
+  r.accepted = s->accepted_moves;
+  r.acc_rate = s->acceptance_rate;
+  r.tscale = s->translation_scale;
+  r.E = s->energy;
+  r.bmin = s->bins_min;
+  r.lo = (int)lo;
+  r.len = (int)n;
+  r.method = s->method == SADMC_METHOD_INV_T_WL ? SADMC_METHOD_WL : s->method;
+  r.too_lo = s->too_lo;
+  r.too_hi = s->too_hi;
+  r.latest_parameter = s->latest_parameter;
+  r.b_tF = s->tF;
+  r.tL = s->tL;
+  r.num_states = s->num_states;
+  r.samc_t0 = s->samc_t0;
+  r.wl_gamma = s->wl_gamma;
+  r.highest_hist = s->lnw_max_count;
+  r.b_tf_max = s->t_found_max_total;
+  r.b_min_e = s->bins_min_e;
+  r.b_max_e = s->bins_max_e;
+  r.b_hist_total = s->hist_total_count;
+  // derived device fields
+  auto widx = [&](double energy) { // histogram.rs:135-146 shifted into the window (book_binning.cuh widx)
+    if (energy < s->bins_min) return (int)lo;
+    const double fi = (energy - s->bins_min) / P.width;
+    if (fi == (double)n || !(fi < (double)n)) return (int)(lo + (long long)n - 1);
+    return (int)(lo + (long long)fi);
+  };
+  r.ilo = widx(s->too_lo);
+  r.ihi = widx(s->too_hi);
+  unsigned long long hmin = ~0ull;
+  long long nmin = 0;
+  double mx = 0.0;
+  for (size_t j = 0; j < n; j++) {
+    const unsigned long long h = hist_count ? hist_count[j] : 0;
+    if (h < hmin) {
+      hmin = h;
+      nmin = 1;
+    } else if (h == hmin) {
+      nmin++;
+    }
+    if (lnw_total[j] > mx) mx = lnw_total[j];
+  }
+  r.b_hist_min = hmin; // == s->hist_min_count: the reference's min_count is the true minimum at all times (histogram.rs:241-245)
+  r.b_hist_nmin = nmin;
+  r.max_S = mx;
+  std::vector<BinRec> recs(n);
+  for (size_t j = 0; j < n; j++) { // record layout: book_binning.cuh
+    BinRec& b = recs[j];
+    b.lo.lnw = lnw_total[j];
+    b.lo.hist = lnw_count[j];
+    b.lo.etot = energy_total[j];
+    memcpy(&b.lo.e2tot, &energy_count[j], 8);
+    const double tft = t_found_total ? t_found_total[j] : 0.0;
+    memcpy(&b.hi.t_found, &tft, 8);
+    b.hi.rt_stamp = t_found_count ? t_found_count[j] : 0;
+    b.hi.round_trips = 0;
+    b.hi.wl_hist = hist_count ? hist_count[j] : 0;
+  }
+  CK(cudaSetDevice(e->cfg.device));
+  const size_t base = (size_t)w * P.cap;
+  CK(cudaMemsetAsync(P.rec + base, 0, (size_t)P.cap * sizeof(BinRec), e->stream));
+  CK(cudaMemcpyAsync(P.rec + base + lo, recs.data(), n * sizeof(BinRec), cudaMemcpyHostToDevice, e->stream));
+  if (P.extra_total) {
+    CK(cudaMemsetAsync(P.extra_total + base, 0, (size_t)P.cap * 8, e->stream));
+    CK(cudaMemsetAsync(P.extra_count + base, 0, (size_t)P.cap * 8, e->stream));
+    if (extra_total) CK(cudaMemcpyAsync(P.extra_total + base + lo, extra_total, n * 8, cudaMemcpyHostToDevice, e->stream));
+    if (extra_count) CK(cudaMemcpyAsync(P.extra_count + base + lo, extra_count, n * 8, cudaMemcpyHostToDevice, e->stream));
+  }
+  CK(cudaMemcpyAsync(P.walkers + w, &r, sizeof r, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
 // ---- resume: the inverse of sadmc_get_walker / sadmc_get_bins (mc/mod.rs:70-84 deserialises a whole EnergyMC) ----
 int sadmc_set_walker_bins(sadmc_engine* e, uint32_t w, const sadmc_walker_state* s, const uint64_t* histogram, const uint64_t* t_found,
                           const double* lnw, const double* energy_total, const double* energy_squared_total, const uint64_t* round_trips,
@@ -1010,7 +1112,6 @@ int sadmc_resume(sadmc_engine* e, uint64_t moves) {
   if (!e) return fail(SADMC_ERR_INVALID, "null engine");
   if (e->started) return fail(SADMC_ERR_INVALID, "engine already started");
   if (e->cfg.init_mode != SADMC_INIT_EXTERNAL) return fail(SADMC_ERR_INVALID, "resume needs an engine created with SADMC_INIT_EXTERNAL");
-  if (refuse_binning(e, "sadmc_resume")) return SADMC_ERR_INVALID;
   e->started = true;
   e->moves = moves;
   return 0;
@@ -1488,6 +1589,50 @@ int sadmc_tempering_set_translation_scales(sadmc_tempering* t, const double* sca
   for (size_t k = 0; k < n; k++) reps[k].tscale = scale[k % t->n_T];
   CK(cudaMemcpyAsync(t->d_reps, reps.data(), n * sizeof(TemperRec), cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+// resume (tempering.rs:196-213: the whole MC is deserialised): the inverse of sadmc_tempering_get_replicas / _get_rng / _num_moves;
+// systems go back with sadmc_tempering_set_system
+int sadmc_tempering_set_replicas(sadmc_tempering* t, uint32_t sim, const sadmc_replica_state* in) {
+  if (!t || !in) return fail(SADMC_ERR_INVALID, "null argument");
+  if (sim >= t->n_sim) return fail(SADMC_ERR_INVALID, "simulation %u out of range", sim);
+  sadmc_engine* e = t->e;
+  std::vector<TemperRec> reps(t->n_T);
+  std::vector<WalkerRec> recs(t->n_T);
+  CK(cudaMemcpyAsync(recs.data(), e->P.walkers + (size_t)sim * t->n_T, t->n_T * sizeof(WalkerRec), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  for (uint32_t r = 0; r < t->n_T; r++) {
+    if (!(in[r].T > 0) || !(in[r].translation_scale > 0)) return fail(SADMC_ERR_INVALID, "replica %u: temperature and translation scale must be positive", r);
+    TemperRec& q = reps[r];
+    q.T = in[r].T;
+    q.rejected = in[r].rejected_count;
+    q.accepted = in[r].accepted_count;
+    q.rejected_swap = in[r].rejected_swap_count;
+    q.accepted_swap = in[r].accepted_swap_count;
+    q.ignored = in[r].ignored_count;
+    q.total_energy = in[r].total_energy;
+    q.total_energy_squared = in[r].total_energy_squared;
+    q.tscale = in[r].translation_scale;
+    recs[r].s0 = in[r].rng_s0;
+    recs[r].s1 = in[r].rng_s1;
+  }
+  CK(cudaMemcpyAsync(t->d_reps + (size_t)sim * t->n_T, reps.data(), t->n_T * sizeof(TemperRec), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->P.walkers + (size_t)sim * t->n_T, recs.data(), t->n_T * sizeof(WalkerRec), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int sadmc_tempering_set_rng(sadmc_tempering* t, uint32_t sim, const uint64_t s[2]) {
+  if (!t || !s) return fail(SADMC_ERR_INVALID, "null argument");
+  if (sim >= t->n_sim) return fail(SADMC_ERR_INVALID, "simulation %u out of range", sim);
+  CK(cudaMemcpyAsync(t->d_mc_rng + 2 * (size_t)sim, s, 16, cudaMemcpyHostToDevice, t->e->stream));
+  CK(cudaStreamSynchronize(t->e->stream));
+  return 0;
+}
+int sadmc_tempering_set_num_moves(sadmc_tempering* t, uint64_t moves) {
+  if (!t) return fail(SADMC_ERR_INVALID, "null argument");
+  const unsigned long long per_round = t->steps * t->n_T;
+  if (per_round == 0 || moves % per_round) return fail(SADMC_ERR_INVALID, "MC::moves of a checkpoint is a multiple of %llu (steps x replicas)", per_round);
+  t->rounds = moves / per_round;
   return 0;
 }
 int sadmc_tempering_get_rng(sadmc_tempering* t, uint32_t sim, uint64_t s[2]) {

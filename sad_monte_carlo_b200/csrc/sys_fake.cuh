@@ -17,6 +17,11 @@
 #include "sys_limits.hpp"
 #include "rng.cuh"
 
+// resident CTAs per SM the one-thread-per-walker kernels of the small systems are compiled for (register cap = 65536 / (128 * this))
+#ifndef SADMC_SMALL_MIN_BLOCKS
+#define SADMC_SMALL_MIN_BLOCKS 4
+#endif
+
 namespace sadmc {
 
 
@@ -24,7 +29,7 @@ struct FakeSys {
   static constexpr int G = 1;
   static constexpr bool FAST_BOOK = false;
   static constexpr int BLOCK = 128;
-  static constexpr int MIN_BLOCKS = 4;
+  static constexpr int MIN_BLOCKS = SADMC_SMALL_MIN_BLOCKS;
   static constexpr bool COOP = false;
   __device__ __forceinline__ void set_cooperative(bool) {}
   __device__ __forceinline__ void finish_move() {}
@@ -111,7 +116,7 @@ struct TwoWellsSys {
   static constexpr int G = 1;
   static constexpr bool FAST_BOOK = false;
   static constexpr int BLOCK = 128;
-  static constexpr int MIN_BLOCKS = 4;
+  static constexpr int MIN_BLOCKS = SADMC_SMALL_MIN_BLOCKS;
   static constexpr bool COOP = false;
   static constexpr bool HAS_EXTRA = true; // `which` well, two_wells.rs:408-418
   __device__ __forceinline__ void set_cooperative(bool) {}
@@ -266,7 +271,7 @@ struct ErfInvSys {
   static constexpr int G = 1;
   static constexpr bool FAST_BOOK = false;
   static constexpr int BLOCK = 128;
-  static constexpr int MIN_BLOCKS = 4;
+  static constexpr int MIN_BLOCKS = SADMC_SMALL_MIN_BLOCKS;
   static constexpr bool COOP = false;
   __device__ __forceinline__ void set_cooperative(bool) {}
   __device__ __forceinline__ void finish_move() {}

@@ -11,13 +11,18 @@
 #include "book.cuh"
 #include "rng.cuh"
 
+// resident CTAs per SM the one-thread-per-walker kernels of the small systems are compiled for (register cap = 65536 / (128 * this))
+#ifndef SADMC_SMALL_MIN_BLOCKS
+#define SADMC_SMALL_MIN_BLOCKS 4
+#endif
+
 namespace sadmc {
 
 struct IsingSys {
   static constexpr int G = 1;
   static constexpr bool FAST_BOOK = false;
   static constexpr int BLOCK = 128;
-  static constexpr int MIN_BLOCKS = 4;
+  static constexpr int MIN_BLOCKS = SADMC_SMALL_MIN_BLOCKS;
   static constexpr bool COOP = false;
   __device__ __forceinline__ void set_cooperative(bool) {}
   __device__ __forceinline__ void finish_move() {}

@@ -194,6 +194,17 @@ class WalkerEngine:
         types = [u64p, u64p, f64p, f64p, f64p, u64p, u8p, u64p, f64p, u64p]
         self._check(self.L.sadmc_set_walker_bins(self.h, w, C.byref(state), *[_p(a, t) for a, t in zip(keep, types)]))
 
+    def set_binning_walker(self, w, state: BinningState, bins):
+        """FLAG_BINNING engines: inverse of binning_walker(w) + binning_bins(w) on an engine created with INIT_EXTERNAL."""
+        def arr(k, dt):
+            a = bins.get(k)
+            return None if a is None else np.ascontiguousarray(a, dtype=dt)
+        keys = [("lnw_total", np.float64, f64p), ("lnw_count", np.uint64, u64p), ("energy_total", np.float64, f64p),
+                ("energy_count", np.uint64, u64p), ("t_found_total", np.float64, f64p), ("t_found_count", np.uint64, u64p),
+                ("hist_count", np.uint64, u64p), ("extra_total", np.float64, f64p), ("extra_count", np.uint64, u64p)]
+        keep = [arr(k, dt) for k, dt, _ in keys]
+        self._check(self.L.sadmc_set_binning_walker(self.h, w, C.byref(state), *[_p(a, t) for a, (_, _, t) in zip(keep, keys)]))
+
     def resume(self, moves):
         """Instead of start(): continue from restored walkers at move count `moves`."""
         self._check(self.L.sadmc_resume(self.h, int(moves)))

@@ -90,6 +90,28 @@ class TemperingMC:
         buf = np.ascontiguousarray(buf, dtype=np.float64)
         self._check(self.L.sadmc_tempering_set_system(self.h, sim, replica, buf.ctypes.data_as(f64p), buf.size))
 
+    def restore(self, sim, doc):
+        """Put a simulation's `MC` document (simulation_document) back: tempering.rs:196-213 deserialises the whole MC."""
+        from .checkpoint import _system_image
+        if [float(t) for t in doc["T"]] != [float(t) for t in self.T] or doc["canonical_steps"] != self.canonical_steps:
+            raise ValueError("checkpoint ladder / canonical_steps differ from this simulation's")
+        reps = (ReplicaState * self.n_T)()
+        n = C.c_size_t()
+        self._check(self.L.sadmc_tempering_system_len(self.h, C.byref(n)))
+        for r, q in enumerate(doc["replicas"]):
+            self.set_system(sim, r, _system_image(self.cfg, q["system"], n.value))
+            reps[r].T = q["T"]
+            for k in ("rejected_count", "accepted_count", "rejected_swap_count", "accepted_swap_count", "ignored_count",
+                      "total_energy", "total_energy_squared", "translation_scale"):
+                setattr(reps[r], k, q[k])
+            reps[r].rng_s0, reps[r].rng_s1 = q["rng"]["s0"], q["rng"]["s1"]
+        self._check(self.L.sadmc_tempering_set_replicas(self.h, sim, reps))
+        s = np.array([doc["rng"]["s0"], doc["rng"]["s1"]], np.uint64)
+        self._check(self.L.sadmc_tempering_set_rng(self.h, sim, s.ctypes.data_as(u64p)))
+
+    def set_moves(self, moves):
+        self._check(self.L.sadmc_tempering_set_num_moves(self.h, int(moves)))
+
     def set_translation_scales(self, scales):
         """`Replica::translation_scale` per temperature (the reference's constructor fixes 1.0, tempering.rs:88)."""
         a = np.ascontiguousarray(scales, dtype=np.float64)
@@ -130,7 +152,7 @@ HELP = """python -m sad_monte_carlo_b200.tempering <system flags> --T t0 --T t1 
 The reference's `tempering` binary (MCParams, src/mc/tempering.rs:14-41; two-wells/run-two-wells.py:45-61) for
 `--num-walkers` independent simulations on one GPU (simulation k = `--seed seed + k`).  Checkpoints: one document per
 simulation in the reference's serde schema (`MC`: T, rng, save_as, moves, replicas[], canonical_steps, save, movie, report;
-tempering.rs:123-145), which plotting/parse-tempering.py reads.  Resuming is not built."""
+tempering.rs:123-145), which plotting/parse-tempering.py reads; `--save-as` on an existing set resumes it (195-213)."""
 
 
 def simulation_document(mc, sim, save_as, report=None, movie=None, save=None):
@@ -205,18 +227,35 @@ def main(argv=None, out=print):
     if os.path.splitext(save_as)[1].lstrip(".") not in ("yaml", "json", "cbor"):
         raise H.UsageError("I don't know how to create file %r" % save_as)
     from . import checkpoint as ck
-    if "save-as" in flags and os.path.exists(ck.walker_path(save_as, 0, cfg.n_walkers)):
-        raise H.UsageError("%s exists: resuming a `tempering` checkpoint is not built (remove the file to start over)" % save_as)
+    resuming = "save-as" in flags and os.path.exists(ck.walker_path(save_as, 0, cfg.n_walkers))  # tempering.rs:195-213
     pp = H.plugin_params(flags)
     steps = flags.get("canonical-steps", 1)
+    docs0 = None
+    if resuming:  # the whole MC comes from the file (T, canonical_steps included); report and save parameters from the flags
+        docs0 = [ck.load(ck.walker_path(save_as, k, cfg.n_walkers)) for k in range(cfg.n_walkers)]
+        T, steps = [float(t) for t in docs0[0]["T"]], int(docs0[0]["canonical_steps"])
+        if len({d["moves"] for d in docs0}) != 1:
+            raise H.UsageError("the simulations' checkpoints disagree on moves")
     if flags.get("dry-run"):
-        out(json.dumps({"config": H.config_summary(cfg), "T": T, "canonical_steps": steps, "plugins": pp, "save_as": save_as}))
+        out(json.dumps({"config": H.config_summary(cfg), "T": T, "canonical_steps": steps, "plugins": pp, "save_as": save_as, "resuming": resuming}))
         return 0
     from . import plugins
+    if resuming:
+        cfg.init_mode = _abi.INIT_EXTERNAL
     mc = TemperingMC(cfg, T, steps)
-    report = plugins.Report(pp["max_iter"], pp["max_independent_samples"], pp["quiet"], out=out)
-    saver = plugins.Save(pp["save_time"])
+    if resuming:
+        try:
+            for k, d in enumerate(docs0):
+                mc.restore(k, d)
+            mc.set_moves(docs0[0]["moves"])
+        except ValueError as ex:
+            raise H.UsageError(str(ex))
+        out("Resuming from file %r" % save_as)
+    report = plugins.Report(pp["max_iter"], pp["max_independent_samples"], pp["quiet"], out=out, resumed=resuming)
+    saver = plugins.Save(pp["save_time"], resumed=resuming)
     movie = plugins.Movie(pp["movie_time"])
+    if resuming and docs0[0].get("movie"):
+        movie.restore(docs0[0]["movie"])
     docs = lambda: dict(report=report.document(), save=saver.document(), movie=movie.document())  # noqa: E731
     per_round = mc.steps_per_round * mc.n_T
     # MC::run_once ticks movie / report / save once per move of the round, AFTER the round (tempering.rs:321-341): a frame

@@ -40,8 +40,25 @@ def test_binning_run_writes_the_reference_schema_and_matches_the_oracle(tmp_path
     assert doc["method"]["Sad"]["too_lo"] == s.too_lo and doc["method"]["Sad"]["tF"] == s.tF and doc["method"]["Sad"]["num_states"] == s.num_states
     assert np.array_equal(np.array(h["lnw"]["total"]), b["lnw_total"]) and h["lnw"]["count"] == [int(x) for x in b["lnw_count"]]
     assert h["lnw"]["max_count"] == s.lnw_max_count and h["extra"]["t_found"]["max_total"] == s.t_found_max_total
-    with pytest.raises(SystemExit):  # resuming is not built: the same --save-as refuses instead of overwriting
-        _run(binning, args, tmp_path)
+
+
+@pytest.mark.parametrize("sysargs,method", [
+    ("--fake-quadratic-dimensions 3 --histogram-bin 0.01 --translation-scale 0.05", "--sad-min-T 0.001"),
+    ("--ising-N 16 --histogram-bin 4", "--wl --min-allowed-energy -400 --max-allowed-energy 0"),
+    ("--two-wells-N 12 --two-wells-h2-to-h1 1.1 --two-wells-barrier-over-h1 0.1 --two-wells-r2 0.5 --histogram-bin 0.001 --translation-scale 0.01", "--samc-t0 1e4"),
+])
+def test_binning_resume_continues_bit_for_bit(tmp_path, sysargs, method):
+    """tests/resume-sad.rs for the `binning` binary: 2e4 moves + resume to 5e4 == 5e4 moves in one go (only save_as differs)."""
+    base = (sysargs + " " + method + " --seed 7 --num-walkers 3 --quiet").split()
+    _run(binning, base + ["--max-iter", "2e4", "--save-as", "a.yaml"], tmp_path)
+    lines = _run(binning, base + ["--max-iter", "5e4", "--save-as", "a.yaml"], tmp_path)
+    assert any("Resuming" in x for x in lines)
+    _run(binning, base + ["--max-iter", "5e4", "--save-as", "b.yaml"], tmp_path)
+    for w in range(3):
+        a = open(tmp_path / ("a-w%06d.yaml" % w)).read().splitlines()
+        b = open(tmp_path / ("b-w%06d.yaml" % w)).read().splitlines()
+        diff = [(x, y) for x, y in zip(a, b) if x != y]
+        assert len(a) == len(b) and all(x.startswith("save_as") for x, _ in diff), diff[:3]
 
 
 def test_tempering_run_writes_one_document_per_simulation(tmp_path):
@@ -68,3 +85,20 @@ def test_tempering_run_writes_one_document_per_simulation(tmp_path):
         assert set(r["system"]) == {"TwoWells"}
     frames = sorted(os.listdir(tmp_path / "tem"))
     assert frames and all(f.endswith(".cbor") for f in frames)  # movie frames at 10^k, labelled with the tick's move number
+
+
+def test_tempering_resume_continues_bit_for_bit(tmp_path):
+    T = tempering.geometric_spacing(0.01, 1.0, 5)
+    base = ("--two-wells-N 12 --two-wells-h2-to-h1 1.1 --two-wells-barrier-over-h1 0.1 --two-wells-r2 0.5 --canonical-steps 4 --seed 5 "
+            "--num-walkers 2 --quiet").split()
+    for t in T:
+        base += ["--T", repr(t)]
+    _run(tempering, base + ["--max-iter", "48000", "--save-as", "a.json"], tmp_path)
+    lines = _run(tempering, base + ["--max-iter", "120000", "--save-as", "a.json"], tmp_path)
+    assert any("Resuming" in x for x in lines)
+    _run(tempering, base + ["--max-iter", "120000", "--save-as", "b.json"], tmp_path)
+    for k in range(2):
+        a = checkpoint.load(str(tmp_path / ("a-w%06d.json" % k)))
+        b = checkpoint.load(str(tmp_path / ("b-w%06d.json" % k)))
+        a.pop("save_as"), b.pop("save_as")
+        assert a == b
