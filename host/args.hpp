@@ -292,6 +292,7 @@ inline sadmc_config default_config() { // EnergyMCParams::default (energy.rs:99-
   c.abi_version = SADMC_ABI_VERSION;
   c.sad_min_T = 0.2;
   c.wl_min_gamma = c.energy_bin = c.min_allowed_energy = c.max_allowed_energy = c.bin_window_lo = c.bin_window_hi = NAN;
+  c.high_resolution_de = NAN; // energy_binning.rs only (SADMC_FLAG_BINNING); `histogram` has no such parameter
   c.move_plan = SADMC_MOVE_TRANSLATION_SCALE;
   c.move_value = 0.05;
   c.n_walkers = 1;

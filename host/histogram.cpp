@@ -41,6 +41,7 @@ static Value config_summary(const sadmc_config& c) {
   v.set("n_walkers", Value::uinteger(c.n_walkers)).set("walker_offset", Value::uinteger(c.walker_offset)).set("device", Value::integer(c.device));
   v.set("init_mode", Value::integer(c.init_mode)).set("bin_window_lo", opt(c.bin_window_lo)).set("bin_window_hi", opt(c.bin_window_hi));
   v.set("lanes_per_walker", Value::integer(c.lanes_per_walker)).set("flags", Value::uinteger(c.flags));
+  v.set("high_resolution_de", opt(c.high_resolution_de));
   return v;
 }
 static Value plugin_summary(const PluginParams& p) {

@@ -107,7 +107,7 @@ typedef enum {
  * Methods: SAD, SAMC, WL, 1/t-WL.  State out: sadmc_get_binning_walker / sadmc_get_binning_bins (sadmc_get_bins,
  * sadmc_set_walker_bins, sadmc_resume and sadmc_set_lnw are for the energy.rs layout and refuse such an engine).
  * Built for the one-thread-per-walker systems (Ising, fake, two-wells, erfinv, LJ with lanes_per_walker = 1) and the
- * warp-per-walker fluids (square well, WCA with lanes_per_walker = 32).  Not built: `binning::linear`, `high_resolution_de`. */
+ * warp-per-walker fluids (square well, WCA with lanes_per_walker = 32).  Not built: `binning::linear`. */
 #define SADMC_FLAG_BINNING 16u
 
 typedef struct sadmc_config {
@@ -158,6 +158,9 @@ typedef struct sadmc_config {
                                WCA: 0 = auto (8 with SADMC_FLAG_FAST_MATH, else 32); 4/8/16 = lanes sharing a walker's cell-list
                                lookups; 32 = a warp per walker */
   uint32_t flags;
+  /* SADMC_FLAG_BINNING only: `high_resolution_de` (energy_binning.rs:62-63, 124-125, 328-330): a second, finer histogram of
+   * the visited energies that rides along with the weights' bins (counts only).  NaN or <= 0 = None. */
+  double high_resolution_de;
 } sadmc_config;
 
 /* Per-walker scalars: the non-vector fields of `EnergyMC` (energy.rs:167-210)
@@ -278,6 +281,10 @@ int sadmc_get_binning_walker(sadmc_engine* e, uint32_t w, sadmc_binning_state* o
 int sadmc_get_binning_bins(sadmc_engine* e, uint32_t w, uint32_t cap, double* lnw_total, uint64_t* lnw_count,
                            double* energy_total, uint64_t* energy_count, double* t_found_total, uint64_t* t_found_count,
                            uint64_t* hist_count, double* extra_total, uint64_t* extra_count);
+/* The `high_resolution` histogram (cfg->high_resolution_de) of walker w: `histogram::Bins::min`, the counts in reference
+ * index order (the `lnw.count` of that Bins; its totals are all 0), their number in *len.  cap = capacity of `count`. */
+int sadmc_get_high_resolution(sadmc_engine* e, uint32_t w, uint32_t cap, double* bins_min, uint32_t* len, uint64_t* count);
+int sadmc_set_high_resolution(sadmc_engine* e, uint32_t w, double bins_min, uint32_t len, const uint64_t* count); /* resume */
 /* Resume of a SADMC_FLAG_BINNING engine (created with SADMC_INIT_EXTERNAL): sadmc_set_system(s), then this for every
  * walker -- the inverse of the two getters above, same field meanings (t_found_*, hist_count, extra_* may be NULL) -- then
  * sadmc_resume(e, moves).  The resumed engine continues bit for bit like the one that was checkpointed. */

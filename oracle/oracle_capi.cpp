@@ -333,7 +333,7 @@ oracle_bmc* oracle_binning_create(const sadmc_config* cfg, uint32_t walker, cons
     MCParams p = mc_params(*cfg, walker);
     if (system_state) p.randomize_first = false;
     oracle_bmc* o = new oracle_bmc;
-    o->mc.reset(new binning::EnergyMC(p, std::move(sys)));
+    o->mc.reset(new binning::EnergyMC(p, std::move(sys), cfg->high_resolution_de > 0 ? cfg->high_resolution_de : NAN));
     return o;
   } catch (const std::exception& ex) {
     g_err = ex.what();
@@ -430,6 +430,18 @@ int oracle_binning_get_aggregates(oracle_bmc* o, const char* name, double* out) 
   out[4] = (double)c->max_count;
   out[5] = c->e_max_count;
   out[6] = (double)c->total_count;
+  return 0;
+}
+// the optional high-resolution histogram (energy_binning.rs:124-125): min, number of bins, counts
+int oracle_binning_get_high_resolution(oracle_bmc* o, uint32_t cap, double* bins_min, uint32_t* len, uint64_t* count) {
+  if (!o->mc->has_high_resolution) return -1;
+  const binning::Bins& b = o->mc->high_resolution;
+  *bins_min = b.min;
+  *len = (uint32_t)b.lnw.count.size();
+  if (count) {
+    if (cap < *len) return -2;
+    for (size_t i = 0; i < b.lnw.count.size(); i++) count[i] = b.lnw.count[i];
+  }
   return 0;
 }
 size_t oracle_binning_system_len(oracle_bmc* o) { return o->mc->system->get_state().size(); }

@@ -52,6 +52,7 @@ class Config(C.Structure):
         ("n_walkers", C.c_uint32), ("walker_offset", C.c_uint32), ("device", C.c_int32), ("init_mode", C.c_int32),
         ("bin_window_lo", C.c_double), ("bin_window_hi", C.c_double),
         ("lanes_per_walker", C.c_int32), ("flags", C.c_uint32),
+        ("high_resolution_de", C.c_double),
     ]
 
 
@@ -131,6 +132,7 @@ def make_config(system, method="sad", **kw):
     c.bin_window_lo = NAN
     c.bin_window_hi = NAN
     c.init_mode = INIT_REFERENCE
+    c.high_resolution_de = NAN
     # per-system defaults of the reference
     c.reduced_density = 1.0      # WcaNParams::default, wca.rs:380-388
     c.filling_fraction = 0.3     # SquareWellNParams::default, optsquare.rs:347-355

@@ -32,6 +32,8 @@ PROTOTYPES = {
     "sadmc_get_bins": (C.c_int, [vp, C.c_uint32, C.c_uint32, u64p, u64p, f64p, f64p, f64p, u64p, u8p, u64p, f64p, u64p]),
     "sadmc_get_binning_walker": (C.c_int, [vp, C.c_uint32, C.POINTER(BinningState)]),
     "sadmc_get_binning_bins": (C.c_int, [vp, C.c_uint32, C.c_uint32, f64p, u64p, f64p, u64p, f64p, u64p, u64p, f64p, u64p]),
+    "sadmc_get_high_resolution": (C.c_int, [vp, C.c_uint32, C.c_uint32, f64p, C.POINTER(C.c_uint32), u64p]),
+    "sadmc_set_high_resolution": (C.c_int, [vp, C.c_uint32, C.c_double, C.c_uint32, u64p]),
     "sadmc_set_binning_walker": (C.c_int, [vp, C.c_uint32, C.POINTER(BinningState), f64p, u64p, f64p, u64p, f64p, u64p, u64p, f64p, u64p]),
     "sadmc_system_len": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
     "sadmc_get_system": (C.c_int, [vp, C.c_uint32, f64p, C.c_size_t]),

@@ -5,8 +5,8 @@ src/mc/energy_binning.rs over `binning::Bins`).
         --sad-min-T 0.001 --max-iter 1e9 --save-as sad-linear-0.01.yaml            (fake/run-fake.py:25-36)
 
 Flags are the `histogram` command line's (histogram.py) with `BinningParams` in place of `--energy-bin`
-(binning.rs:50-69): `--histogram-bin <de>` (default 1.0); `--linear-bin` and `--high-resolution-de` are parsed and refused
-(no device kernel).  Checkpoints are written in the reference's serde schema for this Monte Carlo -- one document per
+(binning.rs:50-69): `--histogram-bin <de>` (default 1.0), `--high-resolution-de <de>` (energy_binning.rs:62-63); `--linear-bin` is
+parsed and refused (no device kernel).  Checkpoints are written in the reference's serde schema for this Monte Carlo -- one document per
 walker, `bins: {Histogram: {min, min_e, max_e, width, lnw: BinCounts, extra: {name: BinCounts}}}` (histogram.rs:12-32,
 99-111) -- so `plotting/parse-binning.py` reads them.  `--save-as` on an existing checkpoint set resumes it
 (mc/mod.rs:66-84: state from the file, report / save parameters from the flags) and continues bit for bit.
@@ -40,6 +40,17 @@ def _bincounts(total, count, max_count=None, max_total=None, centres=None):
             "max_count": int(max_count if max_count is not None else (count.max() if n else 0)),
             "e_max_count": float(centres[i_c]) if n and centres is not None else float("-inf"),
             "total_count": int(count.sum())}
+
+
+def _high_resolution_document(engine, w, st):
+    """`high_resolution: Option<histogram::Bins>` (energy_binning.rs:124-125): counts only, no extras."""
+    de = engine.cfg.high_resolution_de
+    if not de > 0:
+        return None
+    mn, cnt = engine.high_resolution(w)
+    centres = mn + (np.arange(len(cnt)) + 0.5) * de
+    return {"min": mn, "min_e": st.bins_min_e, "max_e": st.bins_max_e, "width": de, "lnw": _bincounts(np.zeros(len(cnt)), cnt, centres=centres),
+            "extra": {}}
 
 
 def walker_document(engine, w, save_as="resume.yaml", report=None, movies=None, save=None):
@@ -84,7 +95,7 @@ def walker_document(engine, w, save_as="resume.yaml", report=None, movies=None, 
         "manager": {},
         "bins": {"Histogram": {"min": st.bins_min, "min_e": st.bins_min_e, "max_e": st.bins_max_e, "width": st.bins_width, "lnw": lnw,
                                "extra": extra}},
-        "high_resolution": None,
+        "high_resolution": _high_resolution_document(engine, w, st),
     }
 
 
@@ -131,6 +142,13 @@ def restore_walker(engine, w, doc):
             arrays["extra_total"], arrays["extra_count"] = bc["total"], bc["count"]
     tag, body = next(iter(doc["system"].items()))
     st.energy = body["E"] if "E" in body else engine.compute_energy(w)  # the analytic systems keep no cached energy
+    hr = doc.get("high_resolution")
+    if cfg.high_resolution_de > 0:
+        if hr is None or hr["width"] != cfg.high_resolution_de:
+            raise ValueError("the checkpoint's high_resolution histogram does not match --high-resolution-de %r" % cfg.high_resolution_de)
+        engine.set_high_resolution(w, hr["min"], hr["lnw"]["count"])
+    elif hr is not None:
+        raise ValueError("the checkpoint carries a high_resolution histogram: give --high-resolution-de %r" % hr["width"])
     engine.set_binning_walker(w, st, arrays)
 
 
@@ -182,16 +200,19 @@ def config_from_flags(flags):
     """`AnyParams` + energy_binning.rs `EnergyMCParams` (52-69) -> sadmc_config with SADMC_FLAG_BINNING."""
     if "linear-bin" in flags:
         raise H.UsageError("--linear-bin: binning::linear (interpolated ln w, src/mc/binning/linear.rs) has no device kernel")
-    if "high-resolution-de" in flags:
-        raise H.UsageError("--high-resolution-de: the second, finer histogram (energy_binning.rs:62-63, 328-330) is not built")
     if "energy-bin" in flags:
         raise H.UsageError("--energy-bin belongs to `histogram`; `binning` takes --histogram-bin (binning.rs:50-69)")
     if "T" in flags or "canonical-T" in flags:
         raise H.UsageError("energy_binning.rs has no canonical method (MethodParams, energy_binning.rs:22-40)")
     f = dict(flags)
     f["energy-bin"] = f.pop("histogram-bin", 1.0)  # BinningParams::default: Histogram { bin: 1.0 }
+    hr = f.pop("high-resolution-de", None)
     cfg = H.config_from_flags(f)
     cfg.flags |= _abi.FLAG_BINNING
+    if hr is not None:
+        if not hr > 0:
+            raise H.UsageError("--high-resolution-de must be positive (histogram.rs:148)")
+        cfg.high_resolution_de = hr
     return cfg
 
 

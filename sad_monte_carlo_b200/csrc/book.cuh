@@ -111,6 +111,9 @@ struct __align__(16) WalkerRec {
   double b_tF, b_tf_max, b_min_e, b_max_e;
   unsigned long long b_hist_min, b_hist_total;
   long long b_hist_nmin;
+  // the optional high-resolution histogram (energy_binning.rs:124-125): its Bins::min and the part of its window in use
+  double hr_min;
+  int hr_lo, hr_len;
 };
 
 struct DevParams {
@@ -122,6 +125,10 @@ struct DevParams {
   uint32_t* sys_words; // Ising: [n_walkers][ising_words] packed spins
   const double* zig;   // X[257] then F[257]
   unsigned int* halted; // [0] walkers that left the bin window, [1] walkers whose verify_energy failed (since creation)
+  unsigned long long* hr_count; // [n_walkers][hr_cap] counts of the high-resolution histogram, null when there is none
+  double hr_width;
+  long long hr_kbase; // its window bin j covers [(hr_kbase + j) hr_width, (hr_kbase + j + 1) hr_width)
+  uint32_t hr_cap;
   uint32_t n_walkers, cap, sys_stride, ising_words;
   double width;
   int has_min, has_max;

@@ -101,6 +101,8 @@ struct BookB {
   long long hist_nmin;            // how many bins hold it
   unsigned long long hist_total;  // "hist".total_count
   double max_S;                   // running maximum of ln w (alignment constant of the reporting fold)
+  double hr_min;                  // high-resolution histogram: Bins::min and the extent of its vectors in the window
+  int hr_lo, hr_len;
   // SAD: window indices of the bins that hold too_lo / too_hi and their ln w as it sits in HBM
   int ilo, ihi;
   double b_lnw_lo, b_lnw_hi;
@@ -145,6 +147,9 @@ struct BookB {
     hist_nmin = r.b_hist_nmin;
     hist_total = r.b_hist_total;
     max_S = r.max_S;
+    hr_min = r.hr_min;
+    hr_lo = r.hr_lo;
+    hr_len = r.hr_len;
     ilo = r.ilo;
     ihi = r.ihi;
     b_lnw_lo = 0.0;
@@ -185,6 +190,9 @@ struct BookB {
     r.b_hist_nmin = hist_nmin;
     r.b_hist_total = hist_total;
     r.max_S = max_S;
+    r.hr_min = hr_min;
+    r.hr_lo = hr_lo;
+    r.hr_len = hr_len;
     r.ilo = ilo;
     r.ihi = ihi;
   }
@@ -288,6 +296,33 @@ struct BookB {
   }
   __device__ __forceinline__ double lnw_lo() const { return ci == ilo ? c.lnw : b_lnw_lo; } // get_lnw(too_lo)
   __device__ __forceinline__ double lnw_hi() const { return ci == ihi ? c.lnw : b_lnw_hi; } // get_lnw(too_hi)
+
+  // `high_resolution.increment_count(energy, 0.)` (energy_binning.rs:328-330; histogram.rs:181-191 with its own min / width):
+  // counts only, never read by the sampler -- one fire-and-forget reduction per move.  false: its window cannot hold e.
+  __device__ __forceinline__ bool high_resolution_count(double e) {
+    const double hw = P.hr_width;
+    if (hr_len == 0) { // prep_for_e on empty vectors: min = floor(e / width) width (histogram.rs:149-151)
+      const double k0 = floor(e / hw);
+      hr_min = k0 * hw;
+      const long long l0 = (long long)k0 - P.hr_kbase;
+      if (l0 < 0 || l0 >= (long long)P.hr_cap) return false;
+      hr_lo = (int)l0;
+    }
+    while (e < hr_min) {
+      if (hr_lo == 0) return false;
+      hr_lo -= 1;
+      hr_len += 1;
+      hr_min -= hw;
+    }
+    while (e >= hr_min + hw * (double)hr_len) {
+      if (hr_lo + hr_len >= (int)P.hr_cap) return false;
+      hr_len += 1;
+    }
+    const double fi = (e - hr_min) / hw;
+    const int idx = fi == (double)hr_len ? hr_len - 1 : (int)fi;
+    if (writer) atomicAdd(P.hr_count + (size_t)w * P.hr_cap + (size_t)(hr_lo + idx), 1ull);
+    return true;
+  }
 
   // ---- gamma (energy_binning.rs:507-533) -------------------------------------
   __device__ __forceinline__ double gamma(unsigned long long moves) const {
@@ -526,6 +561,9 @@ __device__ inline void first_bin_binning(const DevParams& P, uint32_t w, WalkerR
   r.max_S_index = 0;
   r.verify_fail = 0;
   r.t_range = 0;
+  r.hr_min = (round(e0 / P.hr_width) - 0.5) * P.hr_width; // Bins::new (histogram.rs:170-180); replaced by the first count
+  r.hr_lo = 0;
+  r.hr_len = 0;
 }
 
 // n_moves x `move_once` of energy_binning.rs:592-633 for every walker, in one launch.
@@ -668,6 +706,10 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel_binni
         bk.c.count += 1;
         if (bk.c.count > bk.max_count) bk.max_count = bk.c.count;
         if (bk.c.lnw > bk.max_S) bk.max_S = bk.c.lnw;
+        if (P.hr_count && !bk.high_resolution_count(energy)) { // energy_binning.rs:328-330, before the method's part
+          bk.status = SADMC_ERR_WINDOW;
+          halted = true;
+        }
         bk.after_increment(energy, moves, old_highest, old_here);
       }
     }

@@ -279,6 +279,18 @@ static int setup_params(sadmc_engine* e) {
   const long long cap = k_top - e->k_base + 1;
   if (cap > (1ll << 28)) return fail(SADMC_ERR_INVALID, "bin window needs %lld bins per walker", cap);
   P.cap = (uint32_t)cap;
+  P.hr_count = nullptr;
+  P.hr_cap = 0;
+  P.hr_width = 1.0;
+  P.hr_kbase = 0;
+  if (!is_none(c.high_resolution_de) && c.high_resolution_de > 0) { // energy_binning.rs:62-63
+    if (!binning) return fail(SADMC_ERR_INVALID, "high_resolution_de belongs to the `binning` Monte Carlo: set SADMC_FLAG_BINNING");
+    P.hr_width = c.high_resolution_de;
+    P.hr_kbase = (long long)std::floor(wlo / P.hr_width) - 1;
+    const long long hcap = (long long)std::ceil(whi / P.hr_width) + 2 - P.hr_kbase;
+    if (hcap > (1ll << 28)) return fail(SADMC_ERR_INVALID, "the high-resolution histogram needs %lld bins per walker", hcap);
+    P.hr_cap = (uint32_t)hcap;
+  }
   return 0;
 }
 
@@ -523,7 +535,7 @@ int sadmc_create(const sadmc_config* cfg, sadmc_engine** out) {
   CKB(cudaEventCreate(&e->ev1));
   DevParams& P = e->P;
   const size_t nb = (size_t)P.n_walkers * P.cap;
-  size_t need = nb * (sizeof(BinRec) + (e->has_extra ? 16 : 0)) + (size_t)P.n_walkers * (sizeof(WalkerRec) + e->sys_len * 8 + P.ising_words * 4);
+  size_t need = (size_t)P.n_walkers * P.hr_cap * 8 + nb * (sizeof(BinRec) + (e->has_extra ? 16 : 0)) + (size_t)P.n_walkers * (sizeof(WalkerRec) + e->sys_len * 8 + P.ising_words * 4);
   size_t free_b = 0, total_b = 0;
   CKB(cudaMemGetInfo(&free_b, &total_b));
   if (need > free_b) {
@@ -537,6 +549,7 @@ int sadmc_create(const sadmc_config* cfg, sadmc_engine** out) {
     BAIL(dev_alloc(e, (void**)&P.extra_total, nb * 8, true));
     BAIL(dev_alloc(e, (void**)&P.extra_count, nb * 8, true));
   }
+  if (P.hr_cap) BAIL(dev_alloc(e, (void**)&P.hr_count, (size_t)P.n_walkers * P.hr_cap * 8, true));
   BAIL(dev_alloc(e, (void**)&P.walkers, (size_t)P.n_walkers * sizeof(WalkerRec), true));
   BAIL(dev_alloc(e, (void**)&P.sys, (size_t)P.n_walkers * (P.sys_stride ? P.sys_stride : 1) * 8, true));
   BAIL(dev_alloc(e, (void**)&P.sys_words, (size_t)P.n_walkers * (P.ising_words ? P.ising_words : 1) * 4, true));
@@ -903,6 +916,47 @@ int sadmc_get_binning_bins(sadmc_engine* e, uint32_t w, uint32_t cap, double* ln
   return 0;
 }
 
+int sadmc_get_high_resolution(sadmc_engine* e, uint32_t w, uint32_t cap, double* bins_min, uint32_t* len, uint64_t* count) {
+  int rc = need_binning(e);
+  if (rc) return rc;
+  if (!e->P.hr_count) return fail(SADMC_ERR_INVALID, "engine was created without high_resolution_de");
+  WalkerRec r;
+  rc = fetch_walker(e, w, &r);
+  if (rc) return rc;
+  if (bins_min) *bins_min = r.hr_min;
+  if (len) *len = (uint32_t)r.hr_len;
+  if (count) {
+    if (cap < (uint32_t)r.hr_len) return fail(SADMC_ERR_INVALID, "capacity %u < %d high-resolution bins", cap, r.hr_len);
+    if (r.hr_len) {
+      CK(cudaMemcpyAsync(count, e->P.hr_count + (size_t)w * e->P.hr_cap + (size_t)r.hr_lo, (size_t)r.hr_len * 8, cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+    }
+  }
+  return 0;
+}
+int sadmc_set_high_resolution(sadmc_engine* e, uint32_t w, double bins_min, uint32_t len, const uint64_t* count) {
+  int rc = need_binning(e);
+  if (rc) return rc;
+  if (!e->P.hr_count) return fail(SADMC_ERR_INVALID, "engine was created without high_resolution_de");
+  if (w >= e->P.n_walkers) return fail(SADMC_ERR_INVALID, "walker %u out of range", w);
+  if (len && !count) return fail(SADMC_ERR_INVALID, "null argument");
+  const DevParams& P = e->P;
+  const long long lo = len ? (long long)std::floor(bins_min / P.hr_width + 0.5) - P.hr_kbase : 0;
+  if (lo < 0 || lo + (long long)len > (long long)P.hr_cap) return fail(SADMC_ERR_WINDOW, "the checkpointed high-resolution histogram does not fit its device window");
+  WalkerRec r;
+  rc = fetch_walker(e, w, &r);
+  if (rc) return rc;
+  r.hr_min = bins_min;
+  r.hr_lo = (int)lo;
+  r.hr_len = (int)len;
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaMemsetAsync(P.hr_count + (size_t)w * P.hr_cap, 0, (size_t)P.hr_cap * 8, e->stream));
+  if (len) CK(cudaMemcpyAsync(P.hr_count + (size_t)w * P.hr_cap + lo, count, (size_t)len * 8, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(P.walkers + w, &r, sizeof r, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
 // resume for SADMC_FLAG_BINNING engines: the inverse of sadmc_get_binning_walker / sadmc_get_binning_bins
 int sadmc_set_binning_walker(sadmc_engine* e, uint32_t w, const sadmc_binning_state* s, const double* lnw_total, const uint64_t* lnw_count,
                              const double* energy_total, const uint64_t* energy_count, const double* t_found_total, const uint64_t* t_found_count,
@@ -929,6 +983,9 @@ int sadmc_set_binning_walker(sadmc_engine* e, uint32_t w, const sadmc_binning_st
   memset(&r, 0, sizeof r);
   r.err = old.err; // the system-side fields that sadmc_set_system(s) already placed in the record
   r.d_squared = old.d_squared;
+  r.hr_min = old.hr_min; // ... and sadmc_set_high_resolution
+  r.hr_lo = old.hr_lo;
+  r.hr_len = old.hr_len;
   r.s0 = s->rng_s0;
   r.s1 = s->rng_s1;
   r.accepted = s->accepted_moves;

@@ -194,6 +194,18 @@ class WalkerEngine:
         types = [u64p, u64p, f64p, f64p, f64p, u64p, u8p, u64p, f64p, u64p]
         self._check(self.L.sadmc_set_walker_bins(self.h, w, C.byref(state), *[_p(a, t) for a, t in zip(keep, types)]))
 
+    def high_resolution(self, w=0):
+        """FLAG_BINNING engines created with high_resolution_de: (Bins::min, counts) of the finer histogram of walker w."""
+        mn, n = C.c_double(), C.c_uint32()
+        self._check(self.L.sadmc_get_high_resolution(self.h, w, 0, C.byref(mn), C.byref(n), None))
+        cnt = np.zeros(n.value, np.uint64)
+        self._check(self.L.sadmc_get_high_resolution(self.h, w, n.value, C.byref(mn), C.byref(n), _p(cnt, u64p)))
+        return mn.value, cnt
+
+    def set_high_resolution(self, w, bins_min, counts):
+        cnt = np.ascontiguousarray(counts, dtype=np.uint64)
+        self._check(self.L.sadmc_set_high_resolution(self.h, w, float(bins_min), cnt.size, _p(cnt, u64p) if cnt.size else None))
+
     def set_binning_walker(self, w, state: BinningState, bins):
         """FLAG_BINNING engines: inverse of binning_walker(w) + binning_bins(w) on an engine created with INIT_EXTERNAL."""
         def arr(k, dt):

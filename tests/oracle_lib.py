@@ -82,6 +82,7 @@ def load_oracle():
     L.oracle_binning_get_walker.argtypes = [C.c_void_p, C.POINTER(BinningState)]
     L.oracle_binning_get_bins.argtypes = [C.c_void_p, C.c_uint32, f64p, u64p, f64p, u64p, f64p, u64p, u64p, f64p, u64p]
     L.oracle_binning_get_aggregates.argtypes = [C.c_void_p, C.c_char_p, f64p]
+    L.oracle_binning_get_high_resolution.argtypes = [C.c_void_p, C.c_uint32, f64p, C.POINTER(C.c_uint32), u64p]
     L.oracle_binning_system_len.restype = C.c_size_t
     L.oracle_binning_system_len.argtypes = [C.c_void_p]
     L.oracle_binning_get_system.argtypes = [C.c_void_p, f64p, C.c_size_t]
@@ -231,6 +232,13 @@ class OracleBinningMC:
             _ptr(out["hist_count"], u64p), _ptr(out["extra_total"], f64p), _ptr(out["extra_count"], u64p))
         assert rc == 0
         return out
+
+    def high_resolution(self):
+        mn, n = C.c_double(), C.c_uint32()
+        assert self.L.oracle_binning_get_high_resolution(self.h, 0, C.byref(mn), C.byref(n), None) == 0
+        cnt = np.zeros(n.value, np.uint64)
+        assert self.L.oracle_binning_get_high_resolution(self.h, n.value, C.byref(mn), C.byref(n), _ptr(cnt, u64p)) == 0
+        return mn.value, cnt
 
     def aggregates(self, name=""):
         """(min_total, max_total, e_max_total, min_count, max_count, e_max_count, total_count) of bins.lnw ("") or an extra."""

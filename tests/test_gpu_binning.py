@@ -177,6 +177,21 @@ def test_wca_with_the_pressure_accumulator():
     assert np.allclose(gb["energy_total"], ob["energy_total"], rtol=1e-11, atol=1e-12)
 
 
+@pytest.mark.parametrize("system,kw", [
+    ("fake", dict(fake_function=_abi.FAKE_QUADRATIC, N=3, sad_min_T=0.001, energy_bin=0.01, high_resolution_de=0.0013)),
+    ("ising", dict(N=16, sad_min_T=1.0, energy_bin=8.0, high_resolution_de=4.0)),
+])
+def test_high_resolution_histogram_rides_along(system, kw):
+    # energy_binning.rs:124-125, 328-330: a second histogram::Bins with its own width, counts only
+    cfg = make_config(system, "sad", n_walkers=40, seed=6, **kw)
+    eng = _check(cfg, [1, 30000], walkers=(0, 39))
+    for w in (0, 39):
+        o = OracleBinningMC(cfg, walker=w)
+        o.run(30001)
+        (gm, gc), (om, oc) = eng.high_resolution(w), o.high_resolution()
+        assert gm == om and np.array_equal(gc, oc) and int(gc.sum()) == 30001
+
+
 def test_energy_layout_calls_refuse_a_binning_engine_and_canonical_is_rejected():
     cfg = make_config("fake", "sad", fake_function=_abi.FAKE_LINEAR, sad_min_T=0.001, energy_bin=0.01, n_walkers=4,
                       flags=_abi.FLAG_BINNING)

@@ -45,6 +45,7 @@ def test_binning_run_writes_the_reference_schema_and_matches_the_oracle(tmp_path
 @pytest.mark.parametrize("sysargs,method", [
     ("--fake-quadratic-dimensions 3 --histogram-bin 0.01 --translation-scale 0.05", "--sad-min-T 0.001"),
     ("--ising-N 16 --histogram-bin 4", "--wl --min-allowed-energy -400 --max-allowed-energy 0"),
+    ("--fake-linear --histogram-bin 0.01 --high-resolution-de 0.0007 --translation-scale 0.05", "--sad-min-T 0.001"),
     ("--two-wells-N 12 --two-wells-h2-to-h1 1.1 --two-wells-barrier-over-h1 0.1 --two-wells-r2 0.5 --histogram-bin 0.001 --translation-scale 0.01", "--samc-t0 1e4"),
 ])
 def test_binning_resume_continues_bit_for_bit(tmp_path, sysargs, method):

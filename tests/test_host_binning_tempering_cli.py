@@ -36,7 +36,6 @@ def test_binning_wca_line():
 
 @pytest.mark.parametrize("argv,msg", [
     ("--fake-linear --linear-bin 0.01 --sad-min-T 0.001", "binning::linear"),
-    ("--fake-linear --histogram-bin 0.01 --high-resolution-de 0.001 --sad-min-T 0.001", "high-resolution"),
     ("--fake-linear --energy-bin 0.01 --sad-min-T 0.001", "--histogram-bin"),
     ("--fake-linear --histogram-bin 0.01 --T 0.5", "no canonical method"),
 ])
@@ -44,6 +43,13 @@ def test_binning_refuses_what_is_not_built(argv, msg):
     with pytest.raises(SystemExit) as ei:
         binning.main(argv.split() + ["--dry-run"], out=lambda s: None)
     assert msg in str(ei.value)
+
+
+def test_binning_high_resolution_flag():
+    cfg = binning.config_from_flags({"fake-linear": True, "histogram-bin": 0.01, "high-resolution-de": 0.001, "sad-min-T": 0.1})
+    assert cfg.high_resolution_de == 0.001
+    cfg = binning.config_from_flags({"fake-linear": True, "histogram-bin": 0.01, "sad-min-T": 0.1})
+    assert cfg.high_resolution_de != cfg.high_resolution_de  # None
 
 
 def test_binning_config_carries_the_flag():
