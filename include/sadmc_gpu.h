@@ -109,6 +109,12 @@ typedef enum {
  * Built for the one-thread-per-walker systems (Ising, fake, two-wells, erfinv, LJ with lanes_per_walker = 1) and the
  * warp-per-walker fluids (square well, WCA with lanes_per_walker = 32).  Not built: `binning::linear`. */
 #define SADMC_FLAG_BINNING 16u
+/* With SADMC_FLAG_BINNING: `BinningParams::Linear { bin }` (binning.rs:57-60, src/mc/binning/linear.rs) instead of the histogram:
+ * ln w, the counts (f64 there) and every accumulator are spread over the two neighbouring bin points in proportion to the
+ * distance and read back by linear interpolation.  One-thread-per-walker systems only; state out: sadmc_get_binning_walker
+ * (lnw_max_count_f64 / hist_min_count_f64) and sadmc_get_binning_bins_f64.  A correctness path: every access goes to HBM
+ * uncached (no job script of the reference uses --linear-bin). */
+#define SADMC_FLAG_BINNING_LINEAR 32u
 
 typedef struct sadmc_config {
   uint32_t abi_version; /* = SADMC_ABI_VERSION */
@@ -213,6 +219,9 @@ typedef struct sadmc_binning_state {
   uint64_t lnw_max_count, lnw_total_count;  /* bins.lnw.max_count (SAD's old_highest_hist), bins.lnw.total_count */
   double t_found_max_total;                 /* bins.extra["t_found"].max_total (SAD's tF source) */
   uint64_t hist_min_count, hist_total_count; /* bins.extra["hist"] (WL flatness) */
+  /* the same two aggregates as f64: what binning::linear keeps (its counts are f64, linear.rs:22-28); for the histogram
+   * variant the integer values converted */
+  double lnw_max_count_f64, hist_min_count_f64;
 } sadmc_binning_state;
 
 typedef struct sadmc_engine sadmc_engine;
@@ -281,6 +290,11 @@ int sadmc_get_binning_walker(sadmc_engine* e, uint32_t w, sadmc_binning_state* o
 int sadmc_get_binning_bins(sadmc_engine* e, uint32_t w, uint32_t cap, double* lnw_total, uint64_t* lnw_count,
                            double* energy_total, uint64_t* energy_count, double* t_found_total, uint64_t* t_found_count,
                            uint64_t* hist_count, double* extra_total, uint64_t* extra_count);
+/* The same with every count as f64: required for SADMC_FLAG_BINNING_LINEAR engines (their counts are fractional), exact
+ * for histogram engines below 2^53. */
+int sadmc_get_binning_bins_f64(sadmc_engine* e, uint32_t w, uint32_t cap, double* lnw_total, double* lnw_count,
+                               double* energy_total, double* energy_count, double* t_found_total, double* t_found_count,
+                               double* hist_count, double* extra_total, double* extra_count);
 /* The `high_resolution` histogram (cfg->high_resolution_de) of walker w: `histogram::Bins::min`, the counts in reference
  * index order (the `lnw.count` of that Bins; its totals are all 0), their number in *len.  cap = capacity of `count`. */
 int sadmc_get_high_resolution(sadmc_engine* e, uint32_t w, uint32_t cap, double* bins_min, uint32_t* len, uint64_t* count);

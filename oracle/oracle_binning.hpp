@@ -190,6 +190,215 @@ struct Bins { // histogram.rs:99-111
   }
 };
 
+
+// ---- binning::linear (src/mc/binning/linear.rs): ln w and every accumulator interpolated linearly between bin points ----
+struct LBinCounts { // linear.rs:12-32: counts are f64
+  std::vector<double> total;
+  double min_total = 0, max_total = 0, e_max_total = -INFINITY;
+  std::vector<double> count;
+  double min_count = 0, max_count = 0, e_max_count = -INFINITY;
+  uint64_t total_count = 0;
+
+  explicit LBinCounts(size_t sz = 0) : total(sz, 0.0), count(sz, 0.0) {} // linear.rs:60-72
+  void insert_zero() {                                                   // linear.rs:73-78
+    total.insert(total.begin(), 0.0);
+    count.insert(count.begin(), 0.0);
+    min_total = 0;
+    min_count = 0;
+  }
+  void push_zero() { // linear.rs:79-84
+    total.push_back(0.0);
+    count.push_back(0.0);
+    min_total = 0;
+    min_count = 0;
+  }
+  // interpret_float_index (linear.rs:85-98) + the Idx iterator (40-57): sum of v[i] f over the one or two points
+  double interpolate(const std::vector<double>& v, double fidx) const {
+    const double len = (double)total.size();
+    double acc = 0.0;
+    if (fidx < -1.0) return acc;                                     // Idx::None
+    if (fidx < 0.0) return acc + v[0] * (1.0 - (-fidx));             // Idx::One(0, -fidx)
+    if (fidx < len - 1.0) {                                          // Idx::Two(i, fidx - i): (i + 1, o) first, then (i, 1 - o)
+      const size_t i = f64_as_usize(fidx);
+      const double o = fidx - (double)i;
+      acc += v[i + 1] * o;
+      acc += v[i] * (1.0 - o);
+      return acc;
+    }
+    if (fidx < len) return acc + v[total.size() - 1] * (1.0 - (fidx - (len - 1.0))); // Idx::One(len - 1, fidx - (len - 1))
+    return acc;
+  }
+  void increment_count(double elo, double ehi, double fidx, double value) { // linear.rs:99-134
+    const size_t idx = f64_as_usize(fidx);
+    const double offset = fidx - (double)idx;
+    total_count += 1;
+    const double old_count = count[idx], old_plus_count = count[idx + 1];
+    count[idx] += 1.0 - offset;
+    count[idx + 1] += offset;
+    const double old_total = total[idx], old_plus_total = total[idx + 1];
+    total[idx] += value * (1.0 - offset);
+    total[idx + 1] += value * offset;
+    if (total[idx] > max_total && max_of(total) == total[idx]) {
+      max_total = total[idx];
+      e_max_total = elo;
+    }
+    if (total[idx + 1] > max_total && max_of(total) == total[idx + 1]) {
+      max_total = total[idx + 1];
+      e_max_total = ehi;
+    }
+    if (old_total == min_total || old_plus_total == min_total) min_total = min_of(total);
+    if (old_count == min_count || old_plus_count == min_count) min_count = min_of(count);
+    if (count[idx] > max_count) {
+      max_count = count[idx];
+      e_max_count = elo;
+    }
+    if (count[idx + 1] > max_count) {
+      max_count = count[idx + 1];
+      e_max_count = ehi;
+    }
+  }
+  double get_total(double fidx) const { return interpolate(total, fidx); } // linear.rs:136-142
+  double get_count(double fidx) const { return interpolate(count, fidx); } // linear.rs:143-149
+};
+
+struct LinearBins { // linear.rs:153-165
+  double min = INFINITY, min_e = INFINITY, max_e = -INFINITY, width = 1.0;
+  LBinCounts lnw;
+  std::map<std::string, LBinCounts> extra;
+
+  LinearBins() {}
+  LinearBins(double e, double w) : min((std::round(e / w) - 0.5) * w), min_e(e), max_e(e), width(w) {} // linear.rs:230-240
+
+  double index_to_energy(size_t i) const { return min + ((double)i + 0.5) * width; } // linear.rs:200-202
+  double energy_to_index(double e) const { return (e - min) / width; }               // linear.rs:203-205
+  void prep_for_e(double e) {                                                        // linear.rs:206-226
+    if (lnw.count.empty()) min = std::floor(e / width) * width;
+    while (e < min) {
+      lnw.insert_zero();
+      for (auto& kv : extra) kv.second.insert_zero();
+      min -= width;
+    }
+    while (e >= min + width * ((double)lnw.count.size() - 1.0)) {
+      lnw.push_zero();
+      for (auto& kv : extra) kv.second.push_zero();
+    }
+  }
+  void increment_count(double e, double gamma) { // linear.rs:241-258
+    if (e > max_e) max_e = e;
+    if (e < min_e) min_e = e;
+    prep_for_e(e);
+    const double idx = energy_to_index(e);
+    const size_t int_idx = f64_as_usize(idx);
+    const double rescaled_gamma = gamma * 1.0 / width;
+    lnw.increment_count(index_to_energy(int_idx), index_to_energy(int_idx + 1), idx, rescaled_gamma);
+  }
+  double get_lnw(double e) const { return lnw.get_total(energy_to_index(e)); }           // linear.rs:283-285
+  double get_count(double e) const { return lnw.get_count(energy_to_index(e)) / width; } // linear.rs:286-289
+  template <class F>
+  void set_lnw(F f) { // linear.rs:259-267
+    for (size_t i = 0; i < lnw.count.size(); i++) {
+      const double e = index_to_energy(i);
+      double v;
+      if (f(e, get_count(e), &v)) {
+        lnw.total[i] = v;
+        lnw.count[i] = 0.0;
+      }
+    }
+  }
+  template <class F>
+  size_t count_states(F f) const { // linear.rs:268-277
+    size_t n = 0;
+    for (size_t i = 0; i < lnw.count.size(); i++) {
+      const double e = index_to_energy(i);
+      if (f(e, get_count(e))) n++;
+    }
+    return n;
+  }
+  size_t num_states() const { return lnw.count.size(); }      // linear.rs:279-281
+  double max_count() const { return lnw.max_count / width; } // linear.rs:296-298
+
+  void accumulate_extra(const std::string& name, double e, double value) { // linear.rs:303-345
+    prep_for_e(e);
+    const double idx = energy_to_index(e);
+    auto it = extra.find(name);
+    if (it == extra.end()) it = extra.emplace(name, LBinCounts(lnw.total.size())).first;
+    LBinCounts& d = it->second;
+    const size_t int_idx = f64_as_usize(idx);
+    const double offset = idx - (double)int_idx;
+    d.total_count += 1;
+    const double old_count = d.count[int_idx], old_plus_count = d.count[int_idx + 1];
+    d.count[int_idx] += 1.0 - offset;
+    d.count[int_idx + 1] += offset;
+    if (old_count == d.min_count || old_plus_count == d.min_count) d.min_count = min_of(d.count);
+    if (d.count[int_idx] > d.max_count) d.max_count = d.count[int_idx];
+    if (d.count[int_idx + 1] > d.max_count) d.max_count = d.count[int_idx + 1];
+    const double old_total = d.total[int_idx], old_plus_total = d.total[int_idx + 1];
+    d.total[int_idx] = old_total + value * (1.0 - offset);
+    d.total[int_idx + 1] = old_plus_total + value * offset;
+    if (d.total[int_idx] > d.max_total) d.max_total = d.total[int_idx];
+    if (d.total[int_idx + 1] > d.max_total) d.max_total = d.total[int_idx + 1];
+    if (old_total == d.min_total || old_plus_total == d.min_total) d.min_total = min_of(d.total);
+  }
+  void zero_out_extra(const std::string& name) { // linear.rs:346-360
+    auto it = extra.find(name);
+    if (it == extra.end()) return;
+    LBinCounts& d = it->second;
+    for (auto& v : d.count) v = 0.0;
+    for (auto& v : d.total) v = 0.0;
+    d.min_total = 0.0;
+    d.max_total = -INFINITY;
+    d.min_count = 0.0;
+    d.max_count = 0.0;
+    d.total_count = 0;
+  }
+  double mean_extra(const std::string& name, double e) const { // linear.rs:361-373
+    auto it = extra.find(name);
+    if (it == extra.end()) return 0.0;
+    const double idx = energy_to_index(e);
+    return it->second.get_count(idx) > 0.0 ? it->second.get_total(idx) / it->second.get_count(idx) : 0.0;
+  }
+  double total_extra(const std::string& name, double e) const { // linear.rs:374-381
+    auto it = extra.find(name);
+    return it == extra.end() ? 0.0 : it->second.get_total(energy_to_index(e));
+  }
+  double max_total_extra(const std::string& name) const { // linear.rs:382-388
+    auto it = extra.find(name);
+    return it == extra.end() ? 0.0 : it->second.max_total;
+  }
+  double mean_count_extra(const std::string& name) const { // linear.rs:415-421
+    auto it = extra.find(name);
+    return it == extra.end() ? 0.0 : (double)it->second.total_count / (width * (double)num_states());
+  }
+  double min_count_extra(const std::string& name) const { // linear.rs:422-428
+    auto it = extra.find(name);
+    return it == extra.end() ? 0.0 : it->second.min_count / width;
+  }
+};
+
+// `test_linear` (linear.rs:167-186) on this restatement; 0 = passes
+inline int reference_test_linear() {
+  {
+    LinearBins b; // test_binning::<linear::Bins> first (binning.rs:336-364)
+    const double eps = 1.0;
+    if (b.get_count(eps) != 0.0 / eps) return 1;
+    b.increment_count(eps, 1.0);
+    if (!(b.get_count(eps) > 0.0 / eps)) return 2;
+    b.accumulate_extra("datum", eps, 7.0);
+    if (b.mean_extra("datum", eps) != 7.0) return 3;
+    if (b.total_extra("datum", eps) != 7.0) return 4;
+    if (b.max_total_extra("datum") != 7.0) return 5;
+  }
+  LinearBins bins;
+  bins.increment_count(1.9, 1.0);
+  if (!(bins.get_lnw(1.95) > bins.get_lnw(1.85))) return 6;
+  if (!(bins.get_lnw(1.0) > 0.0)) return 7;
+  if (!(bins.get_lnw(0.51) > 0.0)) return 8;
+  if (!(bins.get_lnw(2.49) > 0.0)) return 9;
+  if (bins.get_lnw(3.01) != 0.0) return 10;
+  if (bins.get_lnw(-0.01) != 0.0) return 11;
+  return 0;
+}
+
 // `test_binning::<histogram::Bins>` (binning.rs:336-364, histogram.rs:113-116) on this restatement; 0 = passes,
 // otherwise the number of the assertion that failed
 inline int reference_test_binning() {
@@ -222,7 +431,8 @@ struct Method { // energy_binning.rs:128-148
   double min_gamma = 0;
 };
 
-struct EnergyMC { // energy_binning.rs:92-126
+template <class BinsT>
+struct EnergyMCT { // energy_binning.rs:92-126 (BinsT: the variant of binning::Bins, binning.rs:71-78)
   std::unique_ptr<System> system;
   Method method;
   uint64_t moves = 0, accepted_moves = 0;
@@ -232,13 +442,13 @@ struct EnergyMC { // energy_binning.rs:92-126
   double move_plan_value = 0;
   double translation_scale = 0.05, acceptance_rate = 0.5;
   Rng rng;
-  Bins bins;
+  BinsT bins;
   bool has_high_resolution = false;
   Bins high_resolution;
   uint64_t verify_failures = 0;
 
   // from_params, energy_binning.rs:539-586 (+ Method::new 150-174)
-  EnergyMC(const MCParams& p, std::unique_ptr<System> sys, double high_resolution_de = NAN) : system(std::move(sys)) {
+  EnergyMCT(const MCParams& p, std::unique_ptr<System> sys, double high_resolution_de = NAN) : system(std::move(sys)) {
     rng = Rng::seed_from_u64(p.seed);
     if (p.randomize_first) system->randomize(rng); // SADMC_INIT_RANDOMIZE (engine-side start, not the reference's)
     has_min = !std::isnan(p.min_allowed_energy);
@@ -280,7 +490,7 @@ struct EnergyMC { // energy_binning.rs:92-126
     }
     // BinningParams::Histogram { bin } (binning.rs:50-69, default bin 1.0)
     const double width = !std::isnan(p.energy_bin) ? p.energy_bin : 1.0;
-    bins = Bins(e0, width);
+    bins = BinsT(e0, width);
     if (!std::isnan(high_resolution_de)) {
       has_high_resolution = true;
       high_resolution = Bins(e0, high_resolution_de);
@@ -426,6 +636,9 @@ struct EnergyMC { // energy_binning.rs:92-126
     update_weights(system->energy());
   }
 };
+
+using EnergyMC = EnergyMCT<Bins>;             // BinningParams::Histogram
+using EnergyMCLinear = EnergyMCT<LinearBins>; // BinningParams::Linear
 
 } // namespace binning
 } // namespace oracle

@@ -321,9 +321,10 @@ double oracle_sw_compute_energy_slowly(oracle_mc* o) {
   return s ? s->compute_energy_slowly() : NAN;
 }
 
-// ---- the `binning` binary: energy_binning.rs over binning::histogram (oracle_binning.hpp) ----
+// ---- the `binning` binary: energy_binning.rs over binning::histogram / binning::linear (oracle_binning.hpp) ----
 struct oracle_bmc {
-  std::unique_ptr<binning::EnergyMC> mc;
+  std::unique_ptr<binning::EnergyMC> mc;        // BinningParams::Histogram
+  std::unique_ptr<binning::EnergyMCLinear> mcl; // BinningParams::Linear (cfg->flags & SADMC_FLAG_BINNING_LINEAR)
 };
 oracle_bmc* oracle_binning_create(const sadmc_config* cfg, uint32_t walker, const double* system_state, size_t n_state,
                                   uint64_t attempts_override) {
@@ -333,7 +334,11 @@ oracle_bmc* oracle_binning_create(const sadmc_config* cfg, uint32_t walker, cons
     MCParams p = mc_params(*cfg, walker);
     if (system_state) p.randomize_first = false;
     oracle_bmc* o = new oracle_bmc;
-    o->mc.reset(new binning::EnergyMC(p, std::move(sys), cfg->high_resolution_de > 0 ? cfg->high_resolution_de : NAN));
+    const double hr = cfg->high_resolution_de > 0 ? cfg->high_resolution_de : NAN;
+    if (cfg->flags & SADMC_FLAG_BINNING_LINEAR)
+      o->mcl.reset(new binning::EnergyMCLinear(p, std::move(sys), hr));
+    else
+      o->mc.reset(new binning::EnergyMC(p, std::move(sys), hr));
     return o;
   } catch (const std::exception& ex) {
     g_err = ex.what();
@@ -342,21 +347,29 @@ oracle_bmc* oracle_binning_create(const sadmc_config* cfg, uint32_t walker, cons
 }
 void oracle_binning_destroy(oracle_bmc* o) { delete o; }
 int oracle_binning_reference_test(void) { return binning::reference_test_binning(); }
+int oracle_binning_reference_test_linear(void) { return binning::reference_test_linear(); }
 int oracle_binning_run(oracle_bmc* o, uint64_t n) {
   try {
-    for (uint64_t k = 0; k < n; k++) o->mc->move_once();
+    if (o->mcl)
+      for (uint64_t k = 0; k < n; k++) o->mcl->move_once();
+    else
+      for (uint64_t k = 0; k < n; k++) o->mc->move_once();
     return 0;
   } catch (const std::exception& ex) {
     g_err = ex.what();
     return -1;
   }
 }
-static const binning::BinCounts* find_extra(const binning::Bins& b, const char* name) {
+extern "C++" {
+template <class B>
+static const auto* find_extra(const B& b, const char* name) {
   auto it = b.extra.find(name);
   return it == b.extra.end() ? nullptr : &it->second;
 }
-int oracle_binning_get_walker(oracle_bmc* o, sadmc_binning_state* s) {
-  const binning::EnergyMC& m = *o->mc;
+}
+extern "C++" {
+template <class MC>
+static void fill_binning_state(const MC& m, sadmc_binning_state* s) {
   std::memset(s, 0, sizeof(*s));
   s->moves = m.moves;
   s->accepted_moves = m.accepted_moves;
@@ -382,46 +395,88 @@ int oracle_binning_get_walker(oracle_bmc* o, sadmc_binning_state* s) {
   s->samc_t0 = me.t0;
   s->wl_gamma = me.gamma;
   s->wl_inv_t = me.inv_t;
-  s->lnw_max_count = m.bins.lnw.max_count;
+  s->lnw_max_count = (uint64_t)m.bins.lnw.max_count;
+  s->lnw_max_count_f64 = (double)m.bins.lnw.max_count;
   s->lnw_total_count = m.bins.lnw.total_count;
-  if (const binning::BinCounts* t = find_extra(m.bins, "t_found")) s->t_found_max_total = t->max_total;
-  if (const binning::BinCounts* h = find_extra(m.bins, "hist")) {
-    s->hist_min_count = h->min_count;
+  if (const auto* t = find_extra(m.bins, "t_found")) s->t_found_max_total = t->max_total;
+  if (const auto* h = find_extra(m.bins, "hist")) {
+    s->hist_min_count = (uint64_t)h->min_count;
+    s->hist_min_count_f64 = (double)h->min_count;
     s->hist_total_count = h->total_count;
   }
+}
+}
+int oracle_binning_get_walker(oracle_bmc* o, sadmc_binning_state* s) {
+  if (o->mcl)
+    fill_binning_state(*o->mcl, s);
+  else
+    fill_binning_state(*o->mc, s);
   return 0;
 }
-int oracle_binning_get_bins(oracle_bmc* o, uint32_t cap, double* lnw_total, uint64_t* lnw_count, double* energy_total, uint64_t* energy_count,
-                            double* t_found_total, uint64_t* t_found_count, uint64_t* hist_count, double* extra_total, uint64_t* extra_count) {
-  const binning::Bins& b = o->mc->bins;
+// counts as f64 (exact for the histogram variant below 2^53; the linear variant's counts ARE f64, linear.rs:22)
+extern "C++" {
+template <class B>
+static int fill_binning_bins(const B& b, uint32_t cap, double* lnw_total, double* lnw_count, double* energy_total, double* energy_count,
+                             double* t_found_total, double* t_found_count, double* hist_count, double* extra_total, double* extra_count) {
   const size_t n = b.lnw.total.size();
   if (cap < n) {
     g_err = "capacity too small";
     return -1;
   }
-  const binning::BinCounts* en = find_extra(b, "energy");
-  const binning::BinCounts* tf = find_extra(b, "t_found");
-  const binning::BinCounts* hi = find_extra(b, "hist");
-  const binning::BinCounts* sx = nullptr; // the system's own data_to_collect key
+  const auto* en = find_extra(b, "energy");
+  const auto* tf = find_extra(b, "t_found");
+  const auto* hi = find_extra(b, "hist");
+  decltype(en) sx = nullptr; // the system's own data_to_collect key
   for (const auto& kv : b.extra)
     if (kv.first != "energy" && kv.first != "t_found" && kv.first != "hist") sx = &kv.second;
   for (size_t i = 0; i < n; i++) {
     if (lnw_total) lnw_total[i] = b.lnw.total[i];
-    if (lnw_count) lnw_count[i] = b.lnw.count[i];
+    if (lnw_count) lnw_count[i] = (double)b.lnw.count[i];
     if (energy_total) energy_total[i] = en ? en->total[i] : 0.0;
-    if (energy_count) energy_count[i] = en ? en->count[i] : 0;
+    if (energy_count) energy_count[i] = en ? (double)en->count[i] : 0.0;
     if (t_found_total) t_found_total[i] = tf ? tf->total[i] : 0.0;
-    if (t_found_count) t_found_count[i] = tf ? tf->count[i] : 0;
-    if (hist_count) hist_count[i] = hi ? hi->count[i] : 0;
+    if (t_found_count) t_found_count[i] = tf ? (double)tf->count[i] : 0.0;
+    if (hist_count) hist_count[i] = hi ? (double)hi->count[i] : 0.0;
     if (extra_total) extra_total[i] = sx ? sx->total[i] : 0.0;
-    if (extra_count) extra_count[i] = sx ? sx->count[i] : 0;
+    if (extra_count) extra_count[i] = sx ? (double)sx->count[i] : 0.0;
+  }
+  return 0;
+}
+}
+int oracle_binning_get_bins_f64(oracle_bmc* o, uint32_t cap, double* lnw_total, double* lnw_count, double* energy_total, double* energy_count,
+                                double* t_found_total, double* t_found_count, double* hist_count, double* extra_total, double* extra_count) {
+  if (o->mcl)
+    return fill_binning_bins(o->mcl->bins, cap, lnw_total, lnw_count, energy_total, energy_count, t_found_total, t_found_count, hist_count, extra_total,
+                             extra_count);
+  return fill_binning_bins(o->mc->bins, cap, lnw_total, lnw_count, energy_total, energy_count, t_found_total, t_found_count, hist_count, extra_total,
+                           extra_count);
+}
+int oracle_binning_get_bins(oracle_bmc* o, uint32_t cap, double* lnw_total, uint64_t* lnw_count, double* energy_total, uint64_t* energy_count,
+                            double* t_found_total, uint64_t* t_found_count, uint64_t* hist_count, double* extra_total, uint64_t* extra_count) {
+  if (o->mcl) {
+    g_err = "the linear variant's counts are f64: use oracle_binning_get_bins_f64";
+    return -1;
+  }
+  const binning::Bins& b = o->mc->bins;
+  const size_t n = b.lnw.total.size();
+  std::vector<double> c0(n), c1(n), c2(n), c3(n), c4(n);
+  const int rc = fill_binning_bins(b, cap, lnw_total, c0.data(), energy_total, c1.data(), t_found_total, c2.data(), c3.data(), extra_total, c4.data());
+  if (rc) return rc;
+  for (size_t i = 0; i < n; i++) {
+    if (lnw_count) lnw_count[i] = (uint64_t)c0[i];
+    if (energy_count) energy_count[i] = (uint64_t)c1[i];
+    if (t_found_count) t_found_count[i] = (uint64_t)c2[i];
+    if (hist_count) hist_count[i] = (uint64_t)c3[i];
+    if (extra_count) extra_count[i] = (uint64_t)c4[i];
   }
   return 0;
 }
 // the lazily maintained aggregates of one BinCounts (histogram.rs:12-32); name "" = bins.lnw.  out: min_total, max_total,
 // e_max_total, min_count, max_count, e_max_count, total_count (counts as doubles)
-int oracle_binning_get_aggregates(oracle_bmc* o, const char* name, double* out) {
-  const binning::BinCounts* c = name[0] ? find_extra(o->mc->bins, name) : &o->mc->bins.lnw;
+extern "C++" {
+template <class B>
+static int fill_aggregates(const B& bins, const char* name, double* out) {
+  const auto* c = name[0] ? find_extra(bins, name) : &bins.lnw;
   if (!c) return -1;
   out[0] = c->min_total;
   out[1] = c->max_total;
@@ -432,10 +487,15 @@ int oracle_binning_get_aggregates(oracle_bmc* o, const char* name, double* out) 
   out[6] = (double)c->total_count;
   return 0;
 }
+}
+int oracle_binning_get_aggregates(oracle_bmc* o, const char* name, double* out) {
+  return o->mcl ? fill_aggregates(o->mcl->bins, name, out) : fill_aggregates(o->mc->bins, name, out);
+}
 // the optional high-resolution histogram (energy_binning.rs:124-125): min, number of bins, counts
 int oracle_binning_get_high_resolution(oracle_bmc* o, uint32_t cap, double* bins_min, uint32_t* len, uint64_t* count) {
-  if (!o->mc->has_high_resolution) return -1;
-  const binning::Bins& b = o->mc->high_resolution;
+  const bool has = o->mcl ? o->mcl->has_high_resolution : o->mc->has_high_resolution;
+  if (!has) return -1;
+  const binning::Bins& b = o->mcl ? o->mcl->high_resolution : o->mc->high_resolution;
   *bins_min = b.min;
   *len = (uint32_t)b.lnw.count.size();
   if (count) {
@@ -444,9 +504,10 @@ int oracle_binning_get_high_resolution(oracle_bmc* o, uint32_t cap, double* bins
   }
   return 0;
 }
-size_t oracle_binning_system_len(oracle_bmc* o) { return o->mc->system->get_state().size(); }
+static System* binning_system(oracle_bmc* o) { return o->mcl ? o->mcl->system.get() : o->mc->system.get(); }
+size_t oracle_binning_system_len(oracle_bmc* o) { return binning_system(o)->get_state().size(); }
 int oracle_binning_get_system(oracle_bmc* o, double* buf, size_t n) {
-  const std::vector<double> s = o->mc->system->get_state();
+  const std::vector<double> s = binning_system(o)->get_state();
   if (n < s.size()) return -1;
   std::memcpy(buf, s.data(), s.size() * sizeof(double));
   return 0;

@@ -24,6 +24,7 @@ FLAG_NO_ROUND_TRIPS = 1
 FLAG_SUM_TREE = 2
 FLAG_FAST_MATH = 4
 FLAG_BINNING = 16  # energy_binning.rs bookkeeping over binning::histogram (the `binning` binary)
+FLAG_BINNING_LINEAR = 32  # with FLAG_BINNING: binning::linear (interpolated ln w, f64 counts)
 FLAG_HELPER_WARPS = 8  # experiment: helper warps for the LJ pair loop (with FLAG_FAST_MATH, lanes_per_walker = 1)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WINDOW, ERR_UNSUPPORTED, ERR_VERIFY = 0, -1, -2, -3, -4, -5
@@ -95,6 +96,7 @@ class BinningState(C.Structure):
         ("lnw_max_count", C.c_uint64), ("lnw_total_count", C.c_uint64),
         ("t_found_max_total", C.c_double),
         ("hist_min_count", C.c_uint64), ("hist_total_count", C.c_uint64),
+        ("lnw_max_count_f64", C.c_double), ("hist_min_count_f64", C.c_double),
     ]
 
     def as_dict(self):

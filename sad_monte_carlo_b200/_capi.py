@@ -32,6 +32,7 @@ PROTOTYPES = {
     "sadmc_get_bins": (C.c_int, [vp, C.c_uint32, C.c_uint32, u64p, u64p, f64p, f64p, f64p, u64p, u8p, u64p, f64p, u64p]),
     "sadmc_get_binning_walker": (C.c_int, [vp, C.c_uint32, C.POINTER(BinningState)]),
     "sadmc_get_binning_bins": (C.c_int, [vp, C.c_uint32, C.c_uint32, f64p, u64p, f64p, u64p, f64p, u64p, u64p, f64p, u64p]),
+    "sadmc_get_binning_bins_f64": (C.c_int, [vp, C.c_uint32, C.c_uint32, f64p, f64p, f64p, f64p, f64p, f64p, f64p, f64p, f64p]),
     "sadmc_get_high_resolution": (C.c_int, [vp, C.c_uint32, C.c_uint32, f64p, C.POINTER(C.c_uint32), u64p]),
     "sadmc_set_high_resolution": (C.c_int, [vp, C.c_uint32, C.c_double, C.c_uint32, u64p]),
     "sadmc_set_binning_walker": (C.c_int, [vp, C.c_uint32, C.POINTER(BinningState), f64p, u64p, f64p, u64p, f64p, u64p, u64p, f64p, u64p]),

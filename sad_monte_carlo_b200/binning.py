@@ -5,8 +5,8 @@ src/mc/energy_binning.rs over `binning::Bins`).
         --sad-min-T 0.001 --max-iter 1e9 --save-as sad-linear-0.01.yaml            (fake/run-fake.py:25-36)
 
 Flags are the `histogram` command line's (histogram.py) with `BinningParams` in place of `--energy-bin`
-(binning.rs:50-69): `--histogram-bin <de>` (default 1.0), `--high-resolution-de <de>` (energy_binning.rs:62-63); `--linear-bin` is
-parsed and refused (no device kernel).  Checkpoints are written in the reference's serde schema for this Monte Carlo -- one document per
+(binning.rs:50-69): `--histogram-bin <de>` (default 1.0) or `--linear-bin <de>` (binning::linear: a correctness path on the device; its
+checkpoints are written, resuming them is not built), and `--high-resolution-de <de>` (energy_binning.rs:62-63).  Checkpoints are written in the reference's serde schema for this Monte Carlo -- one document per
 walker, `bins: {Histogram: {min, min_e, max_e, width, lnw: BinCounts, extra: {name: BinCounts}}}` (histogram.rs:12-32,
 99-111) -- so `plotting/parse-binning.py` reads them.  `--save-as` on an existing checkpoint set resumes it
 (mc/mod.rs:66-84: state from the file, report / save parameters from the flags) and continues bit for bit.
@@ -53,13 +53,43 @@ def _high_resolution_document(engine, w, st):
             "extra": {}}
 
 
+def _common_document(engine, w, st, save_as, report, movies, save):
+    """Everything of energy_binning.rs's `EnergyMC` (92-126) except `bins`."""
+    from .checkpoint import _opt, _system_document
+    cfg = engine.cfg
+    m = st.method
+    if m == _abi.METHOD_SAD:
+        method = {"Sad": {"num_states": int(st.num_states), "min_T": cfg.sad_min_T, "too_lo": st.too_lo, "too_hi": st.too_hi, "tL": int(st.tL),
+                          "tF": st.tF, "latest_parameter": st.latest_parameter}}
+    elif m == _abi.METHOD_SAMC:
+        method = {"Samc": {"t0": st.samc_t0}}
+    else:
+        method = {"WL": {"gamma": st.wl_gamma, "inv_t": bool(st.wl_inv_t), "min_gamma": _opt(cfg.wl_min_gamma)}}
+    move_plan = ({"TranslationScale": cfg.move_value} if cfg.move_plan == _abi.MOVE_TRANSLATION_SCALE else {"AcceptanceRate": cfg.move_value})
+    return {
+        "system": _system_document(cfg, engine.system(w), engine.cell_box() if cfg.system in (_abi.SYS_WCA, _abi.SYS_SW) else None),
+        "method": method, "moves": int(st.moves), "time_L": 0, "accepted_moves": int(st.accepted_moves),
+        "min_allowed_energy": _opt(cfg.min_allowed_energy), "max_allowed_energy": _opt(cfg.max_allowed_energy),
+        "move_plan": move_plan, "translation_scale": st.translation_scale, "acceptance_rate": st.acceptance_rate,
+        "rng": {"s0": int(st.rng_s0), "s1": int(st.rng_s1)}, "save_as": str(save_as),
+        "report": report if report is not None else {"max_iter": "Never", "max_independent_samples": None, "quiet": True},
+        "save": save if save is not None else {"save_time_seconds": 3600.0},
+        "movies": movies if movies is not None else {"movie_time": None, "which_frame": 0, "period": "Never"},
+        "manager": {},
+        "bins": None,
+        "high_resolution": _high_resolution_document(engine, w, st),
+    }
+
+
 def walker_document(engine, w, save_as="resume.yaml", report=None, movies=None, save=None):
     """The serde document of walker `w`: energy_binning.rs:92-126 (`EnergyMC`), 128-148 (`Method`), binning.rs:71-78 (`Bins`)."""
-    from .checkpoint import EXTRA_LABEL, _opt, _system_document
+    from .checkpoint import EXTRA_LABEL
     cfg = engine.cfg
     st = engine.binning_walker(w)
     if st.status != 0:
         raise RuntimeError("walker %d is halted (status %d)" % (w, st.status))
+    if cfg.flags & _abi.FLAG_BINNING_LINEAR:
+        return _linear_walker_document(engine, w, st, save_as, report, movies, save)
     b = engine.binning_bins(w)
     n = st.bins_len
     centres = st.bins_min + (np.arange(n) + 0.5) * st.bins_width
@@ -72,31 +102,12 @@ def walker_document(engine, w, save_as="resume.yaml", report=None, movies=None, 
             extra["hist"] = _bincounts(np.zeros(n), b["hist_count"], centres=centres)
         if cfg.system in EXTRA_LABEL and b["extra_count"].any():
             extra[EXTRA_LABEL[cfg.system]] = _bincounts(b["extra_total"], b["extra_count"], centres=centres)
-    m = st.method
-    if m == _abi.METHOD_SAD:
-        method = {"Sad": {"num_states": int(st.num_states), "min_T": cfg.sad_min_T, "too_lo": st.too_lo, "too_hi": st.too_hi, "tL": int(st.tL),
-                          "tF": st.tF, "latest_parameter": st.latest_parameter}}
-    elif m == _abi.METHOD_SAMC:
-        method = {"Samc": {"t0": st.samc_t0}}
-    else:
-        method = {"WL": {"gamma": st.wl_gamma, "inv_t": bool(st.wl_inv_t), "min_gamma": _opt(cfg.wl_min_gamma)}}
     lnw = _bincounts(b["lnw_total"], b["lnw_count"], max_count=st.lnw_max_count, centres=centres)
     lnw["total_count"] = int(st.lnw_total_count)
-    move_plan = ({"TranslationScale": cfg.move_value} if cfg.move_plan == _abi.MOVE_TRANSLATION_SCALE else {"AcceptanceRate": cfg.move_value})
-    return {
-        "system": _system_document(cfg, engine.system(w), engine.cell_box() if cfg.system in (_abi.SYS_WCA, _abi.SYS_SW) else None),
-        "method": method, "moves": int(st.moves), "time_L": 0, "accepted_moves": int(st.accepted_moves),
-        "min_allowed_energy": _opt(cfg.min_allowed_energy), "max_allowed_energy": _opt(cfg.max_allowed_energy),
-        "move_plan": move_plan, "translation_scale": st.translation_scale, "acceptance_rate": st.acceptance_rate,
-        "rng": {"s0": int(st.rng_s0), "s1": int(st.rng_s1)}, "save_as": str(save_as),
-        "report": report if report is not None else {"max_iter": "Never", "max_independent_samples": None, "quiet": True},
-        "save": save if save is not None else {"save_time_seconds": 3600.0},
-        "movies": movies if movies is not None else {"movie_time": None, "which_frame": 0, "period": "Never"},
-        "manager": {},
-        "bins": {"Histogram": {"min": st.bins_min, "min_e": st.bins_min_e, "max_e": st.bins_max_e, "width": st.bins_width, "lnw": lnw,
-                               "extra": extra}},
-        "high_resolution": _high_resolution_document(engine, w, st),
-    }
+    doc = _common_document(engine, w, st, save_as, report, movies, save)
+    doc["bins"] = {"Histogram": {"min": st.bins_min, "min_e": st.bins_min_e, "max_e": st.bins_max_e, "width": st.bins_width, "lnw": lnw,
+                                 "extra": extra}}
+    return doc
 
 
 def restore_walker(engine, w, doc):
@@ -161,6 +172,8 @@ def resume(cfg, save_as):
     if len(moves) != 1:
         raise ValueError("walker checkpoints disagree on moves: %s" % sorted(moves)[:4])
     for d in docs:
+        if "Linear" in d.get("bins", {}):
+            raise ValueError("%s holds binning::linear bins: resuming them is not built" % save_as)
         if "Histogram" not in d.get("bins", {}):
             raise ValueError("%s is not a `binning` checkpoint (bins: {Histogram: ...})" % save_as)
         if d["bins"]["Histogram"]["width"] != cfg.energy_bin:
@@ -171,6 +184,42 @@ def resume(cfg, save_as):
         restore_walker(engine, w, d)
     engine.resume(moves.pop())
     return engine
+
+
+def _linear_walker_document(engine, w, st, save_as, report, movies, save):
+    """The same document with `bins: {Linear: ...}`: linear.rs:153-165, its BinCounts (12-32) keep f64 counts."""
+    from .checkpoint import EXTRA_LABEL
+    cfg = engine.cfg
+    b = engine.binning_bins_f64(w)
+    n = st.bins_len
+    centres = st.bins_min + (np.arange(n) + 0.5) * st.bins_width
+
+    def bc(total, count, max_count=None, max_total=None):
+        d = _bincounts(total, np.zeros(len(total), np.uint64), max_total=max_total, centres=centres)
+        count = np.asarray(count, float)
+        d["count"] = [float(x) for x in count]
+        d["min_count"] = float(count.min()) if n else 0.0
+        d["max_count"] = float(max_count if max_count is not None else (count.max() if n else 0.0))
+        d["e_max_count"] = float(centres[int(np.argmax(count))]) if n else float("-inf")
+        return d
+    extra = {}
+    if n:
+        extra["energy"] = bc(b["energy_total"], b["energy_count"])
+        extra["energy"]["total_count"] = int(st.moves)
+        if b["t_found_count"].any():
+            extra["t_found"] = bc(b["t_found_total"], b["t_found_count"], max_total=st.t_found_max_total)
+            extra["t_found"]["total_count"] = int(round(b["t_found_count"].sum()))
+        if st.method in (_abi.METHOD_WL, _abi.METHOD_INV_T_WL) or b["hist_count"].any():
+            extra["hist"] = bc(np.zeros(n), b["hist_count"])
+            extra["hist"]["total_count"] = int(st.hist_total_count)
+        if cfg.system in EXTRA_LABEL and b["extra_count"].any():
+            extra[EXTRA_LABEL[cfg.system]] = bc(b["extra_total"], b["extra_count"])
+            extra[EXTRA_LABEL[cfg.system]]["total_count"] = int(round(b["extra_count"].sum()))
+    lnw = bc(b["lnw_total"], b["lnw_count"], max_count=st.lnw_max_count_f64)
+    lnw["total_count"] = int(st.lnw_total_count)
+    doc = _common_document(engine, w, st, save_as, report, movies, save)
+    doc["bins"] = {"Linear": {"min": st.bins_min, "min_e": st.bins_min_e, "max_e": st.bins_max_e, "width": st.bins_width, "lnw": lnw, "extra": extra}}
+    return doc
 
 
 def save(engine, save_as, walkers=None, **plugin_docs):
@@ -198,17 +247,18 @@ def save(engine, save_as, walkers=None, **plugin_docs):
 
 def config_from_flags(flags):
     """`AnyParams` + energy_binning.rs `EnergyMCParams` (52-69) -> sadmc_config with SADMC_FLAG_BINNING."""
-    if "linear-bin" in flags:
-        raise H.UsageError("--linear-bin: binning::linear (interpolated ln w, src/mc/binning/linear.rs) has no device kernel")
+    if "linear-bin" in flags and "histogram-bin" in flags:
+        raise H.UsageError("more than one binning given: --histogram-bin, --linear-bin (BinningParams, binning.rs:50-61)")
     if "energy-bin" in flags:
         raise H.UsageError("--energy-bin belongs to `histogram`; `binning` takes --histogram-bin (binning.rs:50-69)")
     if "T" in flags or "canonical-T" in flags:
         raise H.UsageError("energy_binning.rs has no canonical method (MethodParams, energy_binning.rs:22-40)")
     f = dict(flags)
-    f["energy-bin"] = f.pop("histogram-bin", 1.0)  # BinningParams::default: Histogram { bin: 1.0 }
+    linear = "linear-bin" in f
+    f["energy-bin"] = f.pop("linear-bin") if linear else f.pop("histogram-bin", 1.0)  # BinningParams::default: Histogram { bin: 1.0 }
     hr = f.pop("high-resolution-de", None)
     cfg = H.config_from_flags(f)
-    cfg.flags |= _abi.FLAG_BINNING
+    cfg.flags |= _abi.FLAG_BINNING | (_abi.FLAG_BINNING_LINEAR if linear else 0)
     if hr is not None:
         if not hr > 0:
             raise H.UsageError("--high-resolution-de must be positive (histogram.rs:148)")

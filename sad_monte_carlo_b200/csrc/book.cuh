@@ -114,6 +114,8 @@ struct __align__(16) WalkerRec {
   // the optional high-resolution histogram (energy_binning.rs:124-125): its Bins::min and the part of its window in use
   double hr_min;
   int hr_lo, hr_len;
+  // SADMC_FLAG_BINNING_LINEAR (book_linear.cuh): lnw.max_count and "hist".min_count are f64 there
+  double l_max_count, l_hist_min;
 };
 
 struct DevParams {

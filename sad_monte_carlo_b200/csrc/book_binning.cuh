@@ -78,6 +78,33 @@ __device__ __forceinline__ void store_brec(BinRec* p, const BLo& l, const BHi& h
   p->hi = b;
 }
 
+// `high_resolution.increment_count(energy, 0.)` (energy_binning.rs:328-330; histogram.rs:181-191 with its own min / width):
+// counts only, never read by the sampler -- one fire-and-forget reduction per move.  false: its window cannot hold e.
+__device__ __forceinline__ bool high_resolution_increment(const DevParams& P, uint32_t w, bool writer, double& hr_min, int& hr_lo, int& hr_len, double e) {
+  const double hw = P.hr_width;
+  if (hr_len == 0) { // prep_for_e on empty vectors: min = floor(e / width) width (histogram.rs:149-151)
+    const double k0 = floor(e / hw);
+    hr_min = k0 * hw;
+    const long long l0 = (long long)k0 - P.hr_kbase;
+    if (l0 < 0 || l0 >= (long long)P.hr_cap) return false;
+    hr_lo = (int)l0;
+  }
+  while (e < hr_min) {
+    if (hr_lo == 0) return false;
+    hr_lo -= 1;
+    hr_len += 1;
+    hr_min -= hw;
+  }
+  while (e >= hr_min + hw * (double)hr_len) {
+    if (hr_lo + hr_len >= (int)P.hr_cap) return false;
+    hr_len += 1;
+  }
+  const double fi = (e - hr_min) / hw;
+  const int idx = fi == (double)hr_len ? hr_len - 1 : (int)fi;
+  if (writer) atomicAdd(P.hr_count + (size_t)w * P.hr_cap + (size_t)(hr_lo + idx), 1ull);
+  return true;
+}
+
 template <int METHOD, int G>
 struct BookB {
   const DevParams& P;
@@ -297,32 +324,7 @@ struct BookB {
   __device__ __forceinline__ double lnw_lo() const { return ci == ilo ? c.lnw : b_lnw_lo; } // get_lnw(too_lo)
   __device__ __forceinline__ double lnw_hi() const { return ci == ihi ? c.lnw : b_lnw_hi; } // get_lnw(too_hi)
 
-  // `high_resolution.increment_count(energy, 0.)` (energy_binning.rs:328-330; histogram.rs:181-191 with its own min / width):
-  // counts only, never read by the sampler -- one fire-and-forget reduction per move.  false: its window cannot hold e.
-  __device__ __forceinline__ bool high_resolution_count(double e) {
-    const double hw = P.hr_width;
-    if (hr_len == 0) { // prep_for_e on empty vectors: min = floor(e / width) width (histogram.rs:149-151)
-      const double k0 = floor(e / hw);
-      hr_min = k0 * hw;
-      const long long l0 = (long long)k0 - P.hr_kbase;
-      if (l0 < 0 || l0 >= (long long)P.hr_cap) return false;
-      hr_lo = (int)l0;
-    }
-    while (e < hr_min) {
-      if (hr_lo == 0) return false;
-      hr_lo -= 1;
-      hr_len += 1;
-      hr_min -= hw;
-    }
-    while (e >= hr_min + hw * (double)hr_len) {
-      if (hr_lo + hr_len >= (int)P.hr_cap) return false;
-      hr_len += 1;
-    }
-    const double fi = (e - hr_min) / hw;
-    const int idx = fi == (double)hr_len ? hr_len - 1 : (int)fi;
-    if (writer) atomicAdd(P.hr_count + (size_t)w * P.hr_cap + (size_t)(hr_lo + idx), 1ull);
-    return true;
-  }
+  __device__ __forceinline__ bool high_resolution_count(double e) { return high_resolution_increment(P, w, writer, hr_min, hr_lo, hr_len, e); }
 
   // ---- gamma (energy_binning.rs:507-533) -------------------------------------
   __device__ __forceinline__ double gamma(unsigned long long moves) const {

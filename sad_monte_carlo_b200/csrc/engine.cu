@@ -505,6 +505,10 @@ int sadmc_create(const sadmc_config* cfg, sadmc_engine** out) {
     return rc;
   }
   rc = pick_kernels(e);
+  if (!rc && (e->cfg.flags & SADMC_FLAG_BINNING_LINEAR) && !(e->cfg.flags & SADMC_FLAG_BINNING))
+    rc = fail(SADMC_ERR_INVALID, "SADMC_FLAG_BINNING_LINEAR selects the bins of the `binning` Monte Carlo: set SADMC_FLAG_BINNING as well");
+  if (!rc && (e->cfg.flags & SADMC_FLAG_BINNING_LINEAR) && !e->ks.move_linear[e->cfg.method])
+    rc = fail(SADMC_ERR_UNSUPPORTED, "SADMC_FLAG_BINNING_LINEAR: binning::linear is built for the one-thread-per-walker systems only (method %d)", e->cfg.method);
   if (!rc && (e->cfg.flags & SADMC_FLAG_BINNING) && !e->ks.move_binning[e->cfg.method])
     rc = fail(SADMC_ERR_UNSUPPORTED, "SADMC_FLAG_BINNING: no energy_binning.rs kernel for this system / lanes_per_walker / method %d", e->cfg.method);
   if (rc) {
@@ -575,6 +579,9 @@ int sadmc_create(const sadmc_config* cfg, sadmc_engine** out) {
     for (int m = 1; m <= 5; m++)
       if (e->ks.move_binning[m])
         CKB(cudaFuncSetAttribute((const void*)e->ks.move_binning[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ks.smem));
+    for (int m = 1; m <= 5; m++)
+      if (e->ks.move_linear[m])
+        CKB(cudaFuncSetAttribute((const void*)e->ks.move_linear[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ks.smem));
     CKB(cudaFuncSetAttribute((const void*)e->ks.init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ks.smem));
     CKB(cudaFuncSetAttribute((const void*)e->ks.shim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ks.smem));
   }
@@ -628,7 +635,9 @@ int sadmc_run_async(sadmc_engine* e, uint64_t n_moves) {
     const long long threads = (long long)e->cfg.n_walkers * e->ks.move_threads_per_walker;
     grid = (int)((threads + block - 1) / block);
   }
-  move_fn f = (e->cfg.flags & SADMC_FLAG_BINNING) ? e->ks.move_binning[e->cfg.method] : e->ks.move[e->cfg.method];
+  move_fn f = (e->cfg.flags & SADMC_FLAG_BINNING_LINEAR) ? e->ks.move_linear[e->cfg.method]
+              : (e->cfg.flags & SADMC_FLAG_BINNING)      ? e->ks.move_binning[e->cfg.method]
+                                                         : e->ks.move[e->cfg.method];
   if (!f) return fail(SADMC_ERR_UNSUPPORTED, "no move kernel for method %d with these flags", e->cfg.method);
   CK(cudaEventRecord(e->ev0, e->stream));
   f<<<grid, block, smem, e->stream>>>(e->P, e->moves, n_moves);
@@ -867,10 +876,13 @@ int sadmc_get_binning_walker(sadmc_engine* e, uint32_t w, sadmc_binning_state* s
   s->samc_t0 = r.samc_t0;
   s->wl_gamma = r.wl_gamma;
   s->wl_inv_t = e->P.inv_t;
-  s->lnw_max_count = r.highest_hist;
+  const bool linear = (e->cfg.flags & SADMC_FLAG_BINNING_LINEAR) != 0;
+  s->lnw_max_count = linear ? (uint64_t)r.l_max_count : r.highest_hist;
+  s->lnw_max_count_f64 = linear ? r.l_max_count : (double)r.highest_hist;
   s->lnw_total_count = e->moves;
   s->t_found_max_total = r.b_tf_max;
-  s->hist_min_count = r.b_hist_min;
+  s->hist_min_count = linear ? (uint64_t)r.l_hist_min : r.b_hist_min;
+  s->hist_min_count_f64 = linear ? r.l_hist_min : (double)r.b_hist_min;
   s->hist_total_count = r.b_hist_total;
   return 0;
 }
@@ -879,6 +891,7 @@ int sadmc_get_binning_bins(sadmc_engine* e, uint32_t w, uint32_t cap, double* ln
                            uint64_t* extra_count) {
   int rc = need_binning(e);
   if (rc) return rc;
+  if (e->cfg.flags & SADMC_FLAG_BINNING_LINEAR) return fail(SADMC_ERR_INVALID, "binning::linear keeps f64 counts: use sadmc_get_binning_bins_f64");
   WalkerRec r;
   rc = fetch_walker(e, w, &r);
   if (rc) return rc;
@@ -916,6 +929,50 @@ int sadmc_get_binning_bins(sadmc_engine* e, uint32_t w, uint32_t cap, double* ln
   return 0;
 }
 
+int sadmc_get_binning_bins_f64(sadmc_engine* e, uint32_t w, uint32_t cap, double* lnw_total, double* lnw_count, double* energy_total,
+                               double* energy_count, double* t_found_total, double* t_found_count, double* hist_count, double* extra_total,
+                               double* extra_count) {
+  int rc = need_binning(e);
+  if (rc) return rc;
+  const bool linear = (e->cfg.flags & SADMC_FLAG_BINNING_LINEAR) != 0;
+  WalkerRec r;
+  rc = fetch_walker(e, w, &r);
+  if (rc) return rc;
+  const size_t n = e->moves == 0 ? 0 : (size_t)r.len;
+  if (cap < n) return fail(SADMC_ERR_INVALID, "capacity %u < bins_len %zu", cap, n);
+  if (n == 0) return 0;
+  const size_t base = (size_t)w * e->P.cap + (size_t)r.lo;
+  std::vector<BinRec> recs(n);
+  CK(cudaMemcpyAsync(recs.data(), e->P.rec + base, n * sizeof(BinRec), cudaMemcpyDeviceToHost, e->stream));
+  std::vector<uint64_t> xc(n, 0);
+  if (e->P.extra_count) CK(cudaMemcpyAsync(xc.data(), e->P.extra_count + base, n * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (extra_total) {
+    if (e->P.extra_total)
+      CK(cudaMemcpyAsync(extra_total, e->P.extra_total + base, n * 8, cudaMemcpyDeviceToHost, e->stream));
+    else
+      for (size_t i = 0; i < n; i++) extra_total[i] = 0;
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  auto word = [&](const void* p) { // a count word of the record: f64 for linear engines (book_linear.cuh), u64 otherwise
+    double d;
+    uint64_t u;
+    memcpy(&d, p, 8);
+    memcpy(&u, p, 8);
+    return linear ? d : (double)u;
+  };
+  for (size_t i = 0; i < n; i++) {
+    const BinRec& b = recs[i];
+    if (lnw_total) lnw_total[i] = b.lo.lnw;
+    if (lnw_count) lnw_count[i] = word(&b.lo.hist);
+    if (energy_total) energy_total[i] = b.lo.etot;
+    if (energy_count) energy_count[i] = word(&b.lo.e2tot);
+    if (t_found_total) memcpy(&t_found_total[i], &b.hi.t_found, 8);
+    if (t_found_count) t_found_count[i] = word(&b.hi.rt_stamp);
+    if (hist_count) hist_count[i] = word(&b.hi.wl_hist);
+    if (extra_count) extra_count[i] = word(&xc[i]);
+  }
+  return 0;
+}
 int sadmc_get_high_resolution(sadmc_engine* e, uint32_t w, uint32_t cap, double* bins_min, uint32_t* len, uint64_t* count) {
   int rc = need_binning(e);
   if (rc) return rc;
@@ -965,6 +1022,7 @@ int sadmc_set_binning_walker(sadmc_engine* e, uint32_t w, const sadmc_binning_st
   if (rc) return rc;
   if (!s || !lnw_total || !lnw_count || !energy_total || !energy_count)
     return fail(SADMC_ERR_INVALID, "null argument (lnw_total, lnw_count, energy_total, energy_count are required)");
+  if (e->cfg.flags & SADMC_FLAG_BINNING_LINEAR) return fail(SADMC_ERR_UNSUPPORTED, "resuming a binning::linear engine is not built");
   if (w >= e->P.n_walkers) return fail(SADMC_ERR_INVALID, "walker %u out of range", w);
   if (e->cfg.init_mode != SADMC_INIT_EXTERNAL) return fail(SADMC_ERR_INVALID, "resume needs an engine created with SADMC_INIT_EXTERNAL");
   const DevParams& P = e->P;
@@ -1356,6 +1414,7 @@ static int fold_launch(sadmc_engine* e, void* d_histogram, void* d_energy_total,
                        void* d_lnw_sq_sum, void* d_lnw_count, double* d_packed) {
   if (!e) return fail(SADMC_ERR_INVALID, "null engine");
   CK(cudaSetDevice(e->cfg.device));
+  if (e->cfg.flags & SADMC_FLAG_BINNING_LINEAR) return fail(SADMC_ERR_UNSUPPORTED, "the reporting fold is not built for binning::linear engines (f64 counts)");
   FoldSel sel = e->fold_sel;
   sel.binning = (e->cfg.flags & SADMC_FLAG_BINNING) ? 1 : 0;
   uint32_t n_sel = sel.first < e->P.n_walkers ? (e->P.n_walkers - sel.first + sel.stride - 1) / sel.stride : 0;

@@ -34,6 +34,7 @@ typedef void (*shim_fn)(const DevParams, uint32_t, int, double, ShimOut*, double
 struct KernelSet {
   move_fn move[6]; // indexed by sadmc_method_kind (WL and INV_T_WL share)
   move_fn move_binning[6]; // SADMC_FLAG_BINNING: energy_binning.rs bookkeeping (book_binning.cuh); null where not built
+  move_fn move_linear[6];  // ... | SADMC_FLAG_BINNING_LINEAR: the same over binning::linear (book_linear.cuh)
   temper_fn temper; // Replica::run_once x steps (tempering.cuh); null where not built
   init_fn init;
   shim_fn shim;

@@ -2,6 +2,7 @@
 #pragma once
 #include "kernel_set.cuh"
 #include "book_binning.cuh"
+#include "book_linear.cuh"
 #include "move_kernel.cuh"
 #include "tempering.cuh"
 
@@ -24,6 +25,12 @@ static KernelSet make_set(const DevParams& P) {
     k.move_binning[SADMC_METHOD_WL] = move_kernel_binning<Sys, SADMC_METHOD_WL>;
     k.move_binning[SADMC_METHOD_INV_T_WL] = move_kernel_binning<Sys, SADMC_METHOD_WL>;
     k.temper = temper_move_kernel<Sys>;
+    if constexpr (Sys::G == 1) {
+      k.move_linear[SADMC_METHOD_SAD] = move_kernel_linear<Sys, SADMC_METHOD_SAD>;
+      k.move_linear[SADMC_METHOD_SAMC] = move_kernel_linear<Sys, SADMC_METHOD_SAMC>;
+      k.move_linear[SADMC_METHOD_WL] = move_kernel_linear<Sys, SADMC_METHOD_WL>;
+      k.move_linear[SADMC_METHOD_INV_T_WL] = move_kernel_linear<Sys, SADMC_METHOD_WL>;
+    }
   }
   k.init = init_kernel<Sys>;
   k.shim = shim_kernel<Sys>;

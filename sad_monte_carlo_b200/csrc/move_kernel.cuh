@@ -158,6 +158,7 @@ __device__ void first_bin(const DevParams& P, uint32_t w, WalkerRec& r, double e
 // energy_binning.rs / histogram.rs counterpart of first_bin (book_binning.cuh)
 __device__ inline void first_bin_binning(const DevParams& P, uint32_t w, WalkerRec& r, double e0, long long kb_base, int method_param,
                                          bool writer);
+__device__ inline void first_bin_linear(const DevParams& P, uint32_t w, WalkerRec& r, double e0, long long kb_base, int method_param, bool writer);
 
 // `from_params` for every walker: optional randomize, the downhill relaxation
 // (energy.rs:840-851), then the first bin.
@@ -189,7 +190,9 @@ __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) init_kernel(const
       }
     }
   }
-  if (P.flags & SADMC_FLAG_BINNING)
+  if (P.flags & SADMC_FLAG_BINNING_LINEAR)
+    first_bin_linear(P, w, wr, sys.energy(), k_base, method_param, lane == 0);
+  else if (P.flags & SADMC_FLAG_BINNING)
     first_bin_binning(P, w, wr, sys.energy(), k_base, method_param, lane == 0);
   else
     first_bin<G>(P, w, wr, sys.energy(), k_base, method_param, lane == 0);

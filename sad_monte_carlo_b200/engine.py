@@ -194,6 +194,14 @@ class WalkerEngine:
         types = [u64p, u64p, f64p, f64p, f64p, u64p, u8p, u64p, f64p, u64p]
         self._check(self.L.sadmc_set_walker_bins(self.h, w, C.byref(state), *[_p(a, t) for a, t in zip(keep, types)]))
 
+    def binning_bins_f64(self, w=0):
+        """As binning_bins with every count as f64 (FLAG_BINNING_LINEAR engines keep fractional counts)."""
+        n = self.binning_walker(w).bins_len
+        keys = ["lnw_total", "lnw_count", "energy_total", "energy_count", "t_found_total", "t_found_count", "hist_count", "extra_total", "extra_count"]
+        out = {k: np.zeros(n) for k in keys}
+        self._check(self.L.sadmc_get_binning_bins_f64(self.h, w, n, *[_p(out[k], f64p) for k in keys]))
+        return out
+
     def high_resolution(self, w=0):
         """FLAG_BINNING engines created with high_resolution_de: (Bins::min, counts) of the finer histogram of walker w."""
         mn, n = C.c_double(), C.c_uint32()

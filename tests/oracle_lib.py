@@ -81,6 +81,7 @@ def load_oracle():
     L.oracle_binning_run.argtypes = [C.c_void_p, C.c_uint64]
     L.oracle_binning_get_walker.argtypes = [C.c_void_p, C.POINTER(BinningState)]
     L.oracle_binning_get_bins.argtypes = [C.c_void_p, C.c_uint32, f64p, u64p, f64p, u64p, f64p, u64p, u64p, f64p, u64p]
+    L.oracle_binning_get_bins_f64.argtypes = [C.c_void_p, C.c_uint32, f64p, f64p, f64p, f64p, f64p, f64p, f64p, f64p, f64p]
     L.oracle_binning_get_aggregates.argtypes = [C.c_void_p, C.c_char_p, f64p]
     L.oracle_binning_get_high_resolution.argtypes = [C.c_void_p, C.c_uint32, f64p, C.POINTER(C.c_uint32), u64p]
     L.oracle_binning_system_len.restype = C.c_size_t
@@ -231,6 +232,13 @@ class OracleBinningMC:
             _ptr(out["energy_count"], u64p), _ptr(out["t_found_total"], f64p), _ptr(out["t_found_count"], u64p),
             _ptr(out["hist_count"], u64p), _ptr(out["extra_total"], f64p), _ptr(out["extra_count"], u64p))
         assert rc == 0
+        return out
+
+    def bins_f64(self):
+        n = self.walker().bins_len
+        keys = ["lnw_total", "lnw_count", "energy_total", "energy_count", "t_found_total", "t_found_count", "hist_count", "extra_total", "extra_count"]
+        out = {k: np.zeros(n) for k in keys}
+        assert self.L.oracle_binning_get_bins_f64(self.h, n, *[_ptr(out[k], f64p) for k in keys]) == 0
         return out
 
     def high_resolution(self):

@@ -192,6 +192,83 @@ def test_high_resolution_histogram_rides_along(system, kw):
         assert gm == om and np.array_equal(gc, oc) and int(gc.sum()) == 30001
 
 
+# ---- binning::linear (SADMC_FLAG_BINNING_LINEAR, csrc/book_linear.cuh) ------------------------------------------------
+LSCALARS = [f for f in SCALARS if f not in ("lnw_max_count", "hist_min_count")] + ["lnw_max_count_f64", "hist_min_count_f64"]
+
+
+def assert_linear_equal(eng, w, o, context=""):
+    g, s = eng.binning_walker(w), o.walker()
+    assert g.status == 0, "%s walker %d status %d" % (context, w, g.status)
+    sad_only = ("too_lo", "too_hi", "latest_parameter", "tF", "tL", "num_states", "t_found_max_total")
+    wl_only = ("wl_gamma", "hist_min_count_f64", "hist_total_count")
+    for f in LSCALARS:
+        if (f == "samc_t0" and s.method != _abi.METHOD_SAMC) or (f in sad_only and s.method != _abi.METHOD_SAD) or (
+                f in wl_only and s.method not in (_abi.METHOD_WL, _abi.METHOD_INV_T_WL)):
+            continue
+        assert getattr(g, f) == getattr(s, f), "%s walker %d: %s gpu=%r oracle=%r" % (context, w, f, getattr(g, f), getattr(s, f))
+    gb, ob = eng.binning_bins_f64(w), o.bins_f64()
+    for k in BINS:
+        assert np.array_equal(gb[k], ob[k]), "%s walker %d: bins.%s differ at %s" % (context, w, k, np.nonzero(gb[k] != ob[k])[0][:5])
+    assert np.array_equal(eng.system(w), o.system())
+
+
+def _check_linear(cfg, moves, walkers):
+    cfg.flags |= _abi.FLAG_BINNING | _abi.FLAG_BINNING_LINEAR
+    eng = WalkerEngine(cfg)
+    oracles = {w: OracleBinningMC(cfg, walker=cfg.walker_offset + w) for w in walkers}
+    for w, o in oracles.items():
+        assert_linear_equal(eng, w, o, "init")
+    for n in moves:
+        eng.run(n)
+        for w, o in oracles.items():
+            o.run(n)
+            assert_linear_equal(eng, w, o, "after %d" % eng.num_moves())
+    return eng
+
+
+@pytest.mark.parametrize("fn,kw,bounds", [
+    (_abi.FAKE_LINEAR, {}, (0.0, 0.99)),
+    (_abi.FAKE_QUADRATIC, dict(N=3), (0.0, 0.99)),
+    (_abi.FAKE_GAUSSIAN, dict(fake_sigma=0.3), (-0.95, -0.05)),
+])
+@pytest.mark.parametrize("method,mkw", METHODS)
+def test_linear_bins_fake_systems_bit_exact(fn, kw, bounds, method, mkw):
+    b = dict(min_allowed_energy=bounds[0], max_allowed_energy=bounds[1]) if "wl" in method else {}
+    cfg = make_config("fake", method, fake_function=fn, energy_bin=0.01, move_value=0.05, n_walkers=40, seed=3,
+                      bin_window_lo=-2.5, bin_window_hi=4.0, **kw, **mkw, **b)
+    _check_linear(cfg, [1, 2999, 40000], walkers=(0, 39))
+
+
+def test_linear_bins_two_wells_with_which_and_high_resolution():
+    cfg = make_config("two-wells", "sad", N=12, tw_h2_to_h1=1.1, tw_barrier_over_h1=0.1, tw_r2=0.5, energy_bin=1e-3, sad_min_T=0.001,
+                      move_value=1e-2, n_walkers=20, seed=1, high_resolution_de=2.5e-4)
+    eng = _check_linear(cfg, [2000, 30000], walkers=(0, 19))
+    o = OracleBinningMC(cfg, walker=7)
+    o.run(32000)
+    (gm, gc), (om, oc) = eng.high_resolution(7), o.high_resolution()
+    assert gm == om and np.array_equal(gc, oc)
+    assert abs(eng.binning_bins_f64(7)["extra_count"].sum() - 32000) < 1e-6
+
+
+@pytest.mark.parametrize("method,mkw", [("sad", dict(sad_min_T=1.0)), ("inv-t-wl", dict(min_allowed_energy=-300.0, max_allowed_energy=0.0))])
+def test_linear_bins_ising(method, mkw):
+    cfg = make_config("ising", method, N=16, energy_bin=4.0, n_walkers=33, seed=2, **mkw)
+    _check_linear(cfg, [500, 20000], walkers=(0, 32))
+
+
+def test_linear_bins_lj13_reference_order():
+    cfg = make_config("lj", "sad", N=13, lj_radius=2.0, max_allowed_energy=0.0, sad_min_T=0.05, energy_bin=0.05, move_value=0.05,
+                      n_walkers=20, seed=7, lanes_per_walker=1, init_mode=_abi.INIT_RANDOMIZE, bin_window_lo=-46.0, bin_window_hi=0.5)
+    _check_linear(cfg, [300, 10000], walkers=(0, 19))
+
+
+def test_linear_needs_the_binning_flag_and_a_thread_per_walker_system():
+    with pytest.raises(Exception):
+        WalkerEngine(make_config("fake", "sad", fake_function=_abi.FAKE_LINEAR, energy_bin=0.01, flags=_abi.FLAG_BINNING_LINEAR))
+    with pytest.raises(Exception):
+        WalkerEngine(make_config("sw", "sad", N=50, filling_fraction=0.3, sw_well_width=1.3, flags=_abi.FLAG_BINNING | _abi.FLAG_BINNING_LINEAR))
+
+
 def test_energy_layout_calls_refuse_a_binning_engine_and_canonical_is_rejected():
     cfg = make_config("fake", "sad", fake_function=_abi.FAKE_LINEAR, sad_min_T=0.001, energy_bin=0.01, n_walkers=4,
                       flags=_abi.FLAG_BINNING)

@@ -62,6 +62,20 @@ def test_binning_resume_continues_bit_for_bit(tmp_path, sysargs, method):
         assert len(a) == len(b) and all(x.startswith("save_as") for x, _ in diff), diff[:3]
 
 
+def test_binning_linear_run_writes_the_linear_variant(tmp_path):
+    args = "--fake-quadratic-dimensions 3 --linear-bin 0.02 --translation-scale 0.05 --sad-min-T 0.001 --seed 4 --max-iter 20000 --quiet --save-as lin.json".split()
+    _run(binning, args, tmp_path)
+    doc = checkpoint.load(str(tmp_path / "lin.json"))
+    h = doc["bins"]["Linear"]
+    assert h["width"] == 0.02 and abs(sum(h["extra"]["energy"]["count"]) - 20000) < 1e-6 and isinstance(h["lnw"]["count"][0], float)
+    o = OracleBinningMC(make_config("fake", "sad", fake_function=_abi.FAKE_QUADRATIC, N=3, sad_min_T=0.001, energy_bin=0.02, move_value=0.05, seed=4,
+                                    flags=_abi.FLAG_BINNING | _abi.FLAG_BINNING_LINEAR))
+    o.run(20000)
+    b = o.bins_f64()
+    assert np.array_equal(np.array(h["lnw"]["total"]), b["lnw_total"]) and np.array_equal(np.array(h["lnw"]["count"]), b["lnw_count"])
+    assert h["lnw"]["max_count"] == o.walker().lnw_max_count_f64
+
+
 def test_tempering_run_writes_one_document_per_simulation(tmp_path):
     T = tempering.geometric_spacing(0.01, 1.0, 6)
     args = ("--two-wells-N 12 --two-wells-h2-to-h1 1.1 --two-wells-barrier-over-h1 0.1 --two-wells-r2 0.5 --canonical-steps 10 --seed 2 "

@@ -79,8 +79,9 @@ def test_erfinv_per_move_energy_within_tolerance():
 
 
 def test_erfinv_short_trajectory_tracks_oracle():
+    # |erfinv(x)| < 5.9 for every double |x| < 1: eight coordinates stay inside [-48, 48]
     cfg = make_config("fake-erfinv", "sad", N=8, erfinv_mean_energy=0.0, sad_min_T=0.05, energy_bin=0.05,
-                      move_value=0.05, n_walkers=33, seed=2, bin_window_lo=-20.0, bin_window_hi=20.0)
+                      move_value=0.05, n_walkers=33, seed=2, bin_window_lo=-50.0, bin_window_hi=50.0)
     eng = WalkerEngine(cfg)
     o = OracleMC(cfg, walker=32)
     eng.run(20000)

@@ -35,7 +35,7 @@ def test_binning_wca_line():
 
 
 @pytest.mark.parametrize("argv,msg", [
-    ("--fake-linear --linear-bin 0.01 --sad-min-T 0.001", "binning::linear"),
+    ("--fake-linear --linear-bin 0.01 --histogram-bin 0.01 --sad-min-T 0.001", "more than one binning"),
     ("--fake-linear --energy-bin 0.01 --sad-min-T 0.001", "--histogram-bin"),
     ("--fake-linear --histogram-bin 0.01 --T 0.5", "no canonical method"),
 ])
@@ -50,6 +50,11 @@ def test_binning_high_resolution_flag():
     assert cfg.high_resolution_de == 0.001
     cfg = binning.config_from_flags({"fake-linear": True, "histogram-bin": 0.01, "sad-min-T": 0.1})
     assert cfg.high_resolution_de != cfg.high_resolution_de  # None
+
+
+def test_binning_linear_flag():
+    cfg = binning.config_from_flags({"fake-linear": True, "linear-bin": 0.02, "sad-min-T": 0.1})
+    assert cfg.flags & _abi.FLAG_BINNING_LINEAR and cfg.flags & _abi.FLAG_BINNING and cfg.energy_bin == 0.02
 
 
 def test_binning_config_carries_the_flag():

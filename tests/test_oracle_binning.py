@@ -12,6 +12,25 @@ def test_reference_trait_test_passes():
     assert load_oracle().oracle_binning_reference_test() == 0
 
 
+def test_reference_linear_tests_pass():
+    # `test_linear` (linear.rs:167-186) including test_binning::<linear::Bins>
+    assert load_oracle().oracle_binning_reference_test_linear() == 0
+
+
+def test_linear_bins_interpolate_and_converge_to_the_flat_density():
+    cfg = make_config("fake", "sad", fake_function=_abi.FAKE_LINEAR, sad_min_T=0.001, energy_bin=0.01, move_value=0.05,
+                      flags=_abi.FLAG_BINNING | _abi.FLAG_BINNING_LINEAR)
+    o = OracleBinningMC(cfg, walker=3)
+    o2 = OracleBinningMC(cfg, walker=3)
+    assert o2.walker().bins_len == 0
+    o.run(3_000_001)
+    s, b = o.walker(), o.bins_f64()
+    assert abs(b["energy_count"].sum() - 3_000_001) < 1e-3  # each visit adds (1 - offset) + offset
+    assert b["lnw_count"].min() >= 0.0 and s.lnw_max_count_f64 >= b["lnw_count"].max()
+    lnw = b["lnw_total"][2:-2] * 0.01  # the totals are per unit energy (rescaled_gamma = gamma / width, linear.rs:250)
+    assert len(lnw) >= 95 and lnw.std() < 0.05  # the flat density of states of fake-linear
+
+
 def _linear(method, **kw):
     return make_config("fake", method, fake_function=_abi.FAKE_LINEAR, energy_bin=0.01, move_value=0.05, **kw)
 
