@@ -435,6 +435,41 @@ int sadmc_tempering_cell_box(sadmc_tempering* t, double box_diagonal[3], double*
 /* Device time of the last sadmc_tempering_run (move and swap kernels), CUDA events. */
 int sadmc_tempering_last_run_ms(sadmc_tempering* t, float* ms);
 
+/* ---- energy-ceiling replicas: the `replicas` binary (src/mc/energy_replicas.rs) ----------------------------------
+ * `n_sim` independent simulations on one GPU (simulation k = the reference process `--seed cfg->seed + cfg->walker_offset + k`),
+ * each with up to `max_replicas` replica slots: a replica accepts every proposal below its max_energy, neighbours swap
+ * systems when the upper one has come below the lower one's ceiling, and a new, lower replica is split off at the median of
+ * the energies seen below the lowest cutoff once `independent_systems_before_new_bin` independent systems have visited it
+ * (MC::run_once, energy_replicas.rs:504-600).  cfg: system parameters, seed, walker_offset, device, n_walkers = n_sim; the
+ * systems need `System::randomize` (Ising, LJ, WCA, fake, erfinv; the reference leaves the square well's as todo!(), the
+ * two-wells sampler is not restated).  max_init: MAX_INIT of from_params (346-368), 0 = the reference's 1 << 15. */
+typedef struct sadmc_replicas sadmc_replicas;
+/* `Replica` (energy_replicas.rs:103-145) without its system; above_extra holds the system's one data_to_collect key */
+typedef struct sadmc_zeno_replica_state {
+  double max_energy, cutoff_energy, lowest_max_energy, translation_scale;
+  uint64_t rejected_count, accepted_count, above_count, below_count, upwelling_count, unique_visitors;
+  double above_total, below_total, above_total_squared, below_total_squared;
+  double above_extra_total;
+  uint64_t above_extra_count;
+  int32_t collecting_data, _pad;
+  uint64_t rng_s0, rng_s1;
+  double energy;
+} sadmc_zeno_replica_state;
+int sadmc_replicas_create(const sadmc_config* cfg, double min_T, uint64_t independent_systems_before_new_bin, uint32_t max_replicas,
+                          uint32_t max_init, sadmc_replicas** out);
+void sadmc_replicas_destroy(sadmc_replicas* z);
+/* n_rounds x MC::run_once: two launches per round (moves; swaps + median + split).  Blocking.  SADMC_ERR_WINDOW when a
+ * simulation wanted to split off a replica with all max_replicas slots in use (it carries on without). */
+int sadmc_replicas_run(sadmc_replicas* z, uint64_t n_rounds);
+int sadmc_replicas_num_moves(sadmc_replicas* z, uint32_t sim, uint64_t* moves);            /* MC::moves */
+int sadmc_replicas_num_replicas(sadmc_replicas* z, uint32_t sim, uint32_t* n);            /* replicas.len() */
+int sadmc_replicas_get_replicas(sadmc_replicas* z, uint32_t sim, uint32_t cap, sadmc_zeno_replica_state* out);
+int sadmc_replicas_get_rng(sadmc_replicas* z, uint32_t sim, uint64_t s[2]);                /* MC::rng */
+int sadmc_replicas_get_median(sadmc_replicas* z, uint32_t sim, uint32_t cap, double* energies, uint32_t* len); /* MedianEstimator */
+int sadmc_replicas_system_len(sadmc_replicas* z, size_t* n_doubles);
+int sadmc_replicas_get_system(sadmc_replicas* z, uint32_t sim, uint32_t replica, double* buf, size_t n);
+int sadmc_replicas_last_run_ms(sadmc_replicas* z, float* ms);
+
 /* ---- measurement utility (bench.py) --------------------------------------- */
 /* Achievable FP64 FMA throughput of `device` in TFLOP/s (independent DFMA chains,
  * best of `reps`): the denominator of the FP64 roofline fraction. */

@@ -12,6 +12,7 @@
 #include "../include/sadmc_gpu.h" // config / state structs only (shared vocabulary with the engine)
 #include "oracle_binning.hpp"
 #include "oracle_mc.hpp"
+#include "oracle_replicas.hpp"
 #include "oracle_tempering.hpp"
 
 namespace oracle {
@@ -604,6 +605,106 @@ void oracle_rng_jump(uint64_t* s) {
   tempering::jump(g);
   s[0] = g.s0;
   s[1] = g.s1;
+}
+
+// ---- the `replicas` binary (oracle_replicas.hpp) ----
+struct oracle_zmc {
+  sadmc_config cfg;
+  std::unique_ptr<replicas::MC> mc;
+};
+static std::unique_ptr<System> clone_system(const System& s, const void* ctx) {
+  sadmc_config c = *static_cast<const sadmc_config*>(ctx);
+  c.init_mode = SADMC_INIT_EXTERNAL;
+  std::unique_ptr<System> n = make_system(c, 0);
+  n->set_state(s.get_state());
+  return n;
+}
+oracle_zmc* oracle_replicas_create(const sadmc_config* cfg, uint32_t sim, double min_T, uint64_t indep, uint32_t max_init, uint64_t attempts_override) {
+  try {
+    oracle_zmc* o = new oracle_zmc;
+    o->cfg = *cfg;
+    sadmc_config c0 = *cfg;
+    c0.init_mode = SADMC_INIT_REFERENCE;
+    replicas::SystemTraits tr;
+    tr.min_moves_to_randomize = min_moves_to_randomize(*cfg);
+    switch (cfg->system) { // MovableSystem::max_size, System::dimensionality
+      case SADMC_SYS_LJ: tr.max_size = cfg->lj_radius; tr.dimensionality = 3ull * cfg->N; break;
+      case SADMC_SYS_WCA: {
+        const Vec3 b = box_from_config(*cfg, false);
+        tr.max_size = std::sqrt(b.x * b.x + b.y * b.y + b.z * b.z);
+        tr.dimensionality = 3ull * cfg->N;
+        break;
+      }
+      case SADMC_SYS_ISING: tr.max_size = 0.5; tr.dimensionality = (uint64_t)cfg->N * cfg->N; break;
+      case SADMC_SYS_FAKE: tr.max_size = 0.5; tr.dimensionality = tr.min_moves_to_randomize; break;
+      case SADMC_SYS_FAKE_ERFINV: tr.max_size = 0.5; tr.dimensionality = 3ull * cfg->N; break;
+      default: throw std::invalid_argument("replicas: this system has no System::randomize restated");
+    }
+    o->mc.reset(new replicas::MC(cfg->seed + sim, min_T, indep, tr, make_system(c0, attempts_override), clone_system, &o->cfg,
+                                 max_init ? (size_t)max_init : ((size_t)1 << 15)));
+    return o;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return nullptr;
+  }
+}
+void oracle_replicas_destroy(oracle_zmc* o) { delete o; }
+int oracle_replicas_run(oracle_zmc* o, uint64_t n_rounds) {
+  try {
+    for (uint64_t k = 0; k < n_rounds; k++) o->mc->run_once();
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+uint64_t oracle_replicas_num_moves(oracle_zmc* o) { return o->mc->moves; }
+uint32_t oracle_replicas_num_replicas(oracle_zmc* o) { return (uint32_t)o->mc->replicas.size(); }
+void oracle_replicas_get_rng(oracle_zmc* o, uint64_t* s) {
+  s[0] = o->mc->rng.s0;
+  s[1] = o->mc->rng.s1;
+}
+uint32_t oracle_replicas_get_median(oracle_zmc* o, uint32_t cap, double* energies) {
+  const std::vector<double>& e = o->mc->median.energies;
+  for (size_t i = 0; i < e.size() && i < cap; i++) energies[i] = e[i];
+  return (uint32_t)e.size();
+}
+int oracle_replicas_get_replicas(oracle_zmc* o, sadmc_zeno_replica_state* out) {
+  for (size_t r = 0; r < o->mc->replicas.size(); r++) {
+    const replicas::Replica& q = o->mc->replicas[r];
+    sadmc_zeno_replica_state& s = out[r];
+    std::memset(&s, 0, sizeof s);
+    s.max_energy = q.max_energy;
+    s.cutoff_energy = q.cutoff_energy;
+    s.lowest_max_energy = q.lowest_max_energy;
+    s.translation_scale = q.translation_scale;
+    s.rejected_count = q.rejected_count;
+    s.accepted_count = q.accepted_count;
+    s.above_count = q.above_count;
+    s.below_count = q.below_count;
+    s.upwelling_count = q.upwelling_count;
+    s.unique_visitors = q.unique_visitors;
+    s.above_total = q.above_total;
+    s.below_total = q.below_total;
+    s.above_total_squared = q.above_total_squared;
+    s.below_total_squared = q.below_total_squared;
+    if (!q.above_extra.empty()) {
+      s.above_extra_total = q.above_extra.begin()->second.first;
+      s.above_extra_count = q.above_extra.begin()->second.second;
+    }
+    s.collecting_data = q.collecting_data ? 1 : 0;
+    s.rng_s0 = q.rng.s0;
+    s.rng_s1 = q.rng.s1;
+    s.energy = q.energy();
+  }
+  return 0;
+}
+size_t oracle_replicas_system_len(oracle_zmc* o) { return o->mc->replicas[0].system->get_state().size(); }
+int oracle_replicas_get_system(oracle_zmc* o, uint32_t replica, double* buf, size_t n) {
+  const std::vector<double> s = o->mc->replicas[replica].system->get_state();
+  if (n < s.size()) return -1;
+  std::memcpy(buf, s.data(), s.size() * sizeof(double));
+  return 0;
 }
 
 // ---- RNG / math probes for tests ----

@@ -117,6 +117,22 @@ class ReplicaState(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class ZenoReplicaState(C.Structure):
+    """struct sadmc_zeno_replica_state (`Replica` of src/mc/energy_replicas.rs:103-145 without its system)"""
+    _fields_ = [
+        ("max_energy", C.c_double), ("cutoff_energy", C.c_double), ("lowest_max_energy", C.c_double), ("translation_scale", C.c_double),
+        ("rejected_count", C.c_uint64), ("accepted_count", C.c_uint64), ("above_count", C.c_uint64), ("below_count", C.c_uint64),
+        ("upwelling_count", C.c_uint64), ("unique_visitors", C.c_uint64),
+        ("above_total", C.c_double), ("below_total", C.c_double), ("above_total_squared", C.c_double), ("below_total_squared", C.c_double),
+        ("above_extra_total", C.c_double), ("above_extra_count", C.c_uint64),
+        ("collecting_data", C.c_int32), ("_pad", C.c_int32),
+        ("rng_s0", C.c_uint64), ("rng_s1", C.c_uint64), ("energy", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}
+
+
 def make_config(system, method="sad", **kw):
     """Build a Config with the reference's defaults (EnergyMCParams::default, energy.rs:99-115)."""
     c = Config()

@@ -1,7 +1,7 @@
 """ctypes prototypes for every symbol include/sadmc_gpu.h declares."""
 import ctypes as C
 
-from ._abi import BinningState, Config, ReplicaState, WalkerState
+from ._abi import BinningState, Config, ReplicaState, WalkerState, ZenoReplicaState
 
 u64p = C.POINTER(C.c_uint64)
 f64p = C.POINTER(C.c_double)
@@ -76,6 +76,17 @@ PROTOTYPES = {
     "sadmc_tempering_set_system": (C.c_int, [vp, C.c_uint32, C.c_uint32, f64p, C.c_size_t]),
     "sadmc_tempering_cell_box": (C.c_int, [vp, f64p, f64p]),
     "sadmc_tempering_last_run_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+    "sadmc_replicas_create": (C.c_int, [C.POINTER(Config), C.c_double, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
+    "sadmc_replicas_destroy": (None, [vp]),
+    "sadmc_replicas_run": (C.c_int, [vp, C.c_uint64]),
+    "sadmc_replicas_num_moves": (C.c_int, [vp, C.c_uint32, u64p]),
+    "sadmc_replicas_num_replicas": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "sadmc_replicas_get_replicas": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.POINTER(ZenoReplicaState)]),
+    "sadmc_replicas_get_rng": (C.c_int, [vp, C.c_uint32, u64p]),
+    "sadmc_replicas_get_median": (C.c_int, [vp, C.c_uint32, C.c_uint32, f64p, C.POINTER(C.c_uint32)]),
+    "sadmc_replicas_system_len": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
+    "sadmc_replicas_get_system": (C.c_int, [vp, C.c_uint32, C.c_uint32, f64p, C.c_size_t]),
+    "sadmc_replicas_last_run_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "sadmc_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, f64p]),
     "sadmc_selftest_exp_cmp": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, u64p, u64p]),
 }
@@ -90,4 +101,5 @@ def bind(lib):
     lib.sadmc_sizeof_walker_state.restype = C.c_size_t
     lib.sadmc_sizeof_binning_state.restype = C.c_size_t
     lib.sadmc_sizeof_replica_state.restype = C.c_size_t
+    lib.sadmc_sizeof_zeno_replica_state.restype = C.c_size_t
     return lib

@@ -6,6 +6,7 @@
 // computes launches a kernel of this library.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -20,6 +21,7 @@
 #include "kernel_set.cuh"
 #include "rng.cuh"
 #include "sys_limits.hpp"
+#include "replicas_round.cuh"
 #include "tempering_swap.cuh"
 
 using namespace sadmc;
@@ -456,6 +458,7 @@ size_t sadmc_sizeof_config(void) { return sizeof(sadmc_config); }
 size_t sadmc_sizeof_walker_state(void) { return sizeof(sadmc_walker_state); }
 size_t sadmc_sizeof_binning_state(void) { return sizeof(sadmc_binning_state); }
 size_t sadmc_sizeof_replica_state(void) { return sizeof(sadmc_replica_state); }
+size_t sadmc_sizeof_zeno_replica_state(void) { return sizeof(sadmc_zeno_replica_state); }
 
 int sadmc_reference_system(const sadmc_config* cfg, double* buf, size_t n, size_t* needed) {
   if (!cfg) return fail(SADMC_ERR_INVALID, "null argument");
@@ -1774,6 +1777,287 @@ int sadmc_tempering_set_system(sadmc_tempering* t, uint32_t sim, uint32_t replic
   if (sim >= t->n_sim || replica >= t->n_T) return fail(SADMC_ERR_INVALID, "replica (%u, %u) out of range", sim, replica);
   t->settled = false;
   return sadmc_set_system(t->e, sim * t->n_T + replica, buf, n);
+}
+
+// ---- energy-ceiling replicas: the `replicas` binary (src/mc/energy_replicas.rs; kernels in replicas.cuh / replicas_round.cuh) ----
+struct sadmc_replicas {
+  sadmc_engine* e = nullptr; // systems, generators, kernels (dummy bins; never started)
+  uint32_t n_sim = 0, r_max = 0;
+  unsigned long long steps = 0;
+  double dimensionality = 1.0;
+  ReplicaRec* d_reps = nullptr;
+  ReplicaSim* d_sims = nullptr;
+  double* d_energy = nullptr;
+  double* d_median = nullptr;
+  float last_ms = 0.f;
+};
+static double system_max_size(const sadmc_engine* e) { // MovableSystem::max_size
+  const sadmc_config& c = e->cfg;
+  switch (c.system) {
+    case SADMC_SYS_LJ: return c.lj_radius;                                                                // lj.rs:375-377
+    case SADMC_SYS_WCA:
+    case SADMC_SYS_SW: return std::sqrt(e->P.box[0] * e->P.box[0] + e->P.box[1] * e->P.box[1] + e->P.box[2] * e->P.box[2]); // wca.rs:354-356
+    case SADMC_SYS_TWO_WELLS: return 2.0;                                                                 // two_wells.rs:465-467
+    default: return 0.5;                                                                                  // fake.rs:145, erfinv.rs:111, ising.rs:120
+  }
+}
+static double system_dimensionality(const sadmc_config& c) { // System::dimensionality
+  switch (c.system) {
+    case SADMC_SYS_ISING: return (double)c.N * c.N;                                   // ising.rs:89-91
+    case SADMC_SYS_FAKE: return (double)min_moves_to_randomize(c);                    // fake.rs:116-118
+    case SADMC_SYS_TWO_WELLS: return (double)c.N;                                     // two_wells.rs:405-407
+    default: return 3.0 * (double)c.N;                                                // lj.rs:283-285, wca.rs:271-273, erfinv.rs:89-91
+  }
+}
+int sadmc_replicas_create(const sadmc_config* cfg, double min_T, uint64_t indep, uint32_t max_replicas, uint32_t max_init, sadmc_replicas** out) {
+  if (!cfg || !out) return fail(SADMC_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->n_walkers < 1) return fail(SADMC_ERR_INVALID, "replicas needs at least one simulation");
+  if (max_replicas < 2 || max_replicas > 256) return fail(SADMC_ERR_INVALID, "max_replicas must be 2..256");
+  if (cfg->system == SADMC_SYS_SW || cfg->system == SADMC_SYS_TWO_WELLS)
+    return fail(SADMC_ERR_UNSUPPORTED, "replicas needs System::randomize: todo!() for the square well in the reference (optsquare.rs:202-204), not restated for two-wells");
+  if ((unsigned long long)max_replicas * cfg->n_walkers > 0x7fffffffull) return fail(SADMC_ERR_INVALID, "too many replica slots");
+  if (max_init == 0) max_init = 1u << 15; // MAX_INIT, energy_replicas.rs:350
+  sadmc_config c = *cfg;
+  const uint32_t n_sim = cfg->n_walkers;
+  c.n_walkers = n_sim * max_replicas;
+  c.method = SADMC_METHOD_CANONICAL; // unused: dummy bins
+  c.canonical_T = 1.0;
+  c.energy_bin = 1.0;
+  c.min_allowed_energy = c.max_allowed_energy = NAN;
+  c.bin_window_lo = 0.0;
+  c.bin_window_hi = 1.0;
+  c.flags &= ~(uint32_t)(SADMC_FLAG_BINNING | SADMC_FLAG_BINNING_LINEAR);
+  c.high_resolution_de = NAN;
+  if (c.system == SADMC_SYS_LJ && c.lanes_per_walker == 0) c.lanes_per_walker = 1;
+  if (c.system == SADMC_SYS_WCA && c.lanes_per_walker == 0) c.lanes_per_walker = 32;
+  c.init_mode = SADMC_INIT_EXTERNAL;
+  sadmc_engine* e = nullptr;
+  int rc = sadmc_create(&c, &e);
+  if (rc) return rc;
+  if (!e->ks.replica_move || !e->ks.replica_init) {
+    sadmc_destroy(e);
+    return fail(SADMC_ERR_UNSUPPORTED, "no replicas kernel for this system / lanes_per_walker");
+  }
+  sadmc_replicas* z = new sadmc_replicas;
+  z->e = e;
+  z->n_sim = n_sim;
+  z->r_max = max_replicas;
+  z->steps = min_moves_to_randomize(*cfg); // energy_replicas.rs:507
+  z->dimensionality = system_dimensionality(*cfg);
+#define ZBAIL(expr)              \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc) {                   \
+      sadmc_replicas_destroy(z); \
+      return _rc;                \
+    }                            \
+  } while (0)
+#define ZCK(call)                                                                      \
+  do {                                                                                 \
+    cudaError_t _e = (call);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      sadmc_replicas_destroy(z);                                                       \
+      return fail(SADMC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e));     \
+    }                                                                                  \
+  } while (0)
+  { // every slot starts as the constructor's system (only slots 0 and 1 of each simulation are in use at first)
+    std::vector<double> img;
+    e->cfg.init_mode = SADMC_INIT_REFERENCE;
+    rc = reference_image(e, img);
+    e->cfg.init_mode = SADMC_INIT_EXTERNAL;
+    ZBAIL(rc);
+    std::vector<double> all((size_t)c.n_walkers * e->sys_len);
+    for (uint32_t w = 0; w < c.n_walkers; w++) memcpy(&all[(size_t)w * e->sys_len], img.data(), e->sys_len * sizeof(double));
+    ZBAIL(sadmc_set_systems(e, all.data(), all.size()));
+  }
+  const size_t n_slots = c.n_walkers;
+  double* d_init = nullptr;
+  unsigned long long* d_rng = nullptr;
+  ZBAIL(dev_alloc(e, (void**)&z->d_reps, n_slots * sizeof(ReplicaRec), true));
+  ZBAIL(dev_alloc(e, (void**)&z->d_sims, (size_t)n_sim * sizeof(ReplicaSim), true));
+  ZBAIL(dev_alloc(e, (void**)&z->d_energy, n_slots * 8, true));
+  ZBAIL(dev_alloc(e, (void**)&z->d_median, (size_t)n_sim * REPLICA_ESTIMATOR_SIZE * 8, true));
+  ZBAIL(dev_alloc(e, (void**)&d_init, (size_t)n_sim * max_init * 8, false));
+  ZBAIL(dev_alloc(e, (void**)&d_rng, (size_t)n_sim * 16, false));
+  if (e->ks.smem > 48 * 1024) {
+    ZCK(cudaFuncSetAttribute((const void*)e->ks.replica_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ks.smem));
+    ZCK(cudaFuncSetAttribute((const void*)e->ks.replica_move, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ks.smem));
+  }
+  {
+    const long long threads = (long long)n_sim * e->ks.G;
+    const int grid = (int)((threads + e->ks.block - 1) / e->ks.block);
+    e->ks.replica_init<<<grid, e->ks.block, e->ks.smem, e->stream>>>(e->P, cfg->seed + cfg->walker_offset, n_sim, max_replicas, d_init, max_init, d_rng);
+    ZCK(cudaGetLastError());
+    e->launches++;
+  }
+  std::vector<double> en((size_t)n_sim * max_init);
+  std::vector<unsigned long long> mc((size_t)n_sim * 2);
+  ZCK(cudaMemcpyAsync(en.data(), d_init, en.size() * 8, cudaMemcpyDeviceToHost, e->stream));
+  ZCK(cudaMemcpyAsync(mc.data(), d_rng, mc.size() * 8, cudaMemcpyDeviceToHost, e->stream));
+  ZCK(cudaStreamSynchronize(e->stream));
+  std::vector<ReplicaRec> reps(n_slots);
+  std::vector<ReplicaSim> sims(n_sim);
+  std::vector<double> med((size_t)n_sim * REPLICA_ESTIMATOR_SIZE, 0.0);
+  const double max_size = system_max_size(e);
+  for (uint32_t k = 0; k < n_sim; k++) { // energy_replicas.rs:369-398
+    double* a = &en[(size_t)k * max_init];
+    std::sort(a, a + max_init);
+    const double half = a[max_init / 2], quarter = a[max_init / 4];
+    memset(&reps[(size_t)k * max_replicas], 0, sizeof(ReplicaRec) * max_replicas);
+    ReplicaRec& r0 = reps[(size_t)k * max_replicas];
+    ReplicaRec& r1 = reps[(size_t)k * max_replicas + 1];
+    r0.max_energy = INFINITY;
+    r0.cutoff = half;
+    r1.max_energy = half;
+    r1.cutoff = quarter;
+    for (ReplicaRec* r : {&r0, &r1}) { // Replica::new, 147-170
+      r->lowest_max = r->max_energy;
+      r->tscale = max_size;
+      r->unique_visitors = 1;
+      r->collecting = 1;
+    }
+    ReplicaSim& S = sims[k];
+    memset(&S, 0, sizeof S);
+    S.s0 = mc[2 * k];
+    S.s1 = mc[2 * k + 1];
+    S.indep = indep;
+    S.min_T = min_T;
+    S.n_rep = 2;
+    S.median_len = 1;
+    med[(size_t)k * REPLICA_ESTIMATOR_SIZE] = quarter; // MedianEstimator::new(energies[len / 4])
+  }
+  ZCK(cudaMemcpyAsync(z->d_reps, reps.data(), reps.size() * sizeof(ReplicaRec), cudaMemcpyHostToDevice, e->stream));
+  ZCK(cudaMemcpyAsync(z->d_sims, sims.data(), sims.size() * sizeof(ReplicaSim), cudaMemcpyHostToDevice, e->stream));
+  ZCK(cudaMemcpyAsync(z->d_median, med.data(), med.size() * 8, cudaMemcpyHostToDevice, e->stream));
+  ZCK(cudaStreamSynchronize(e->stream));
+#undef ZBAIL
+#undef ZCK
+  *out = z;
+  return 0;
+}
+void sadmc_replicas_destroy(sadmc_replicas* z) {
+  if (!z) return;
+  if (z->e) sadmc_destroy(z->e);
+  delete z;
+}
+int sadmc_replicas_run(sadmc_replicas* z, uint64_t n_rounds) {
+  if (!z) return fail(SADMC_ERR_INVALID, "null argument");
+  sadmc_engine* e = z->e;
+  CK(cudaSetDevice(e->cfg.device));
+  int grid;
+  launch_cfg(e, &grid);
+  CK(cudaEventRecord(e->ev0, e->stream));
+  for (uint64_t r = 0; r < n_rounds; r++) {
+    e->ks.replica_move<<<grid, e->ks.block, e->ks.smem, e->stream>>>(e->P, z->d_reps, z->d_sims, z->r_max, z->steps, z->d_energy);
+    CK(cudaGetLastError());
+    replica_round_kernel<<<z->n_sim, 128, 0, e->stream>>>(e->P, z->d_reps, z->d_sims, z->d_energy, z->d_median, z->r_max, z->steps, z->dimensionality);
+    CK(cudaGetLastError());
+    e->launches += 2;
+  }
+  CK(cudaEventRecord(e->ev1, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaEventElapsedTime(&z->last_ms, e->ev0, e->ev1));
+  std::vector<ReplicaSim> sims(z->n_sim);
+  CK(cudaMemcpy(sims.data(), z->d_sims, sims.size() * sizeof(ReplicaSim), cudaMemcpyDeviceToHost));
+  uint32_t over = 0;
+  for (const ReplicaSim& S : sims) over += S.overflow ? 1u : 0u;
+  if (over) return fail(SADMC_ERR_WINDOW, "%u simulation(s) wanted to split off a replica with all %u slots in use: raise max_replicas", over, z->r_max);
+  return 0;
+}
+int sadmc_replicas_last_run_ms(sadmc_replicas* z, float* ms) {
+  if (!z || !ms) return fail(SADMC_ERR_INVALID, "null argument");
+  *ms = z->last_ms;
+  return 0;
+}
+static int fetch_sim(sadmc_replicas* z, uint32_t sim, ReplicaSim* S) {
+  if (!z) return fail(SADMC_ERR_INVALID, "null argument");
+  if (sim >= z->n_sim) return fail(SADMC_ERR_INVALID, "simulation %u out of range", sim);
+  CK(cudaMemcpyAsync(S, z->d_sims + sim, sizeof(ReplicaSim), cudaMemcpyDeviceToHost, z->e->stream));
+  CK(cudaStreamSynchronize(z->e->stream));
+  return 0;
+}
+int sadmc_replicas_num_moves(sadmc_replicas* z, uint32_t sim, uint64_t* moves) {
+  ReplicaSim S;
+  int rc = fetch_sim(z, sim, &S);
+  if (!rc && moves) *moves = S.moves;
+  return rc;
+}
+int sadmc_replicas_num_replicas(sadmc_replicas* z, uint32_t sim, uint32_t* n) {
+  ReplicaSim S;
+  int rc = fetch_sim(z, sim, &S);
+  if (!rc && n) *n = (uint32_t)S.n_rep;
+  return rc;
+}
+int sadmc_replicas_get_rng(sadmc_replicas* z, uint32_t sim, uint64_t s[2]) {
+  ReplicaSim S;
+  int rc = fetch_sim(z, sim, &S);
+  if (!rc && s) {
+    s[0] = S.s0;
+    s[1] = S.s1;
+  }
+  return rc;
+}
+int sadmc_replicas_get_median(sadmc_replicas* z, uint32_t sim, uint32_t cap, double* energies, uint32_t* len) {
+  ReplicaSim S;
+  int rc = fetch_sim(z, sim, &S);
+  if (rc) return rc;
+  if (len) *len = (uint32_t)S.median_len;
+  if (energies) {
+    if (cap < (uint32_t)S.median_len) return fail(SADMC_ERR_INVALID, "capacity %u < %d energies", cap, S.median_len);
+    CK(cudaMemcpyAsync(energies, z->d_median + (size_t)sim * REPLICA_ESTIMATOR_SIZE, (size_t)S.median_len * 8, cudaMemcpyDeviceToHost, z->e->stream));
+    CK(cudaStreamSynchronize(z->e->stream));
+  }
+  return 0;
+}
+int sadmc_replicas_get_replicas(sadmc_replicas* z, uint32_t sim, uint32_t cap, sadmc_zeno_replica_state* out) {
+  ReplicaSim S;
+  int rc = fetch_sim(z, sim, &S);
+  if (rc) return rc;
+  if (!out) return fail(SADMC_ERR_INVALID, "null argument");
+  if (cap < (uint32_t)S.n_rep) return fail(SADMC_ERR_INVALID, "capacity %u < %d replicas", cap, S.n_rep);
+  sadmc_engine* e = z->e;
+  const size_t base = (size_t)sim * z->r_max;
+  std::vector<ReplicaRec> reps(S.n_rep);
+  std::vector<WalkerRec> recs(S.n_rep);
+  CK(cudaMemcpyAsync(reps.data(), z->d_reps + base, reps.size() * sizeof(ReplicaRec), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(recs.data(), e->P.walkers + base, recs.size() * sizeof(WalkerRec), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  for (int r = 0; r < S.n_rep; r++) {
+    sadmc_zeno_replica_state& o = out[r];
+    memset(&o, 0, sizeof o);
+    const ReplicaRec& q = reps[r];
+    o.max_energy = q.max_energy;
+    o.cutoff_energy = q.cutoff;
+    o.lowest_max_energy = q.lowest_max;
+    o.translation_scale = q.tscale;
+    o.rejected_count = q.rejected;
+    o.accepted_count = q.accepted;
+    o.above_count = q.above_count;
+    o.below_count = q.below_count;
+    o.upwelling_count = q.upwelling;
+    o.unique_visitors = q.unique_visitors;
+    o.above_total = q.above_total;
+    o.below_total = q.below_total;
+    o.above_total_squared = q.above_sq;
+    o.below_total_squared = q.below_sq;
+    o.above_extra_total = q.xtot;
+    o.above_extra_count = q.xcnt;
+    o.collecting_data = q.collecting;
+    o.rng_s0 = recs[r].s0;
+    o.rng_s1 = recs[r].s1;
+    o.energy = recs[r].E;
+  }
+  return 0;
+}
+int sadmc_replicas_system_len(sadmc_replicas* z, size_t* n) {
+  if (!z) return fail(SADMC_ERR_INVALID, "null argument");
+  return sadmc_system_len(z->e, n);
+}
+int sadmc_replicas_get_system(sadmc_replicas* z, uint32_t sim, uint32_t replica, double* buf, size_t n) {
+  if (!z) return fail(SADMC_ERR_INVALID, "null argument");
+  if (sim >= z->n_sim || replica >= z->r_max) return fail(SADMC_ERR_INVALID, "replica (%u, %u) out of range", sim, replica);
+  return sadmc_get_system(z->e, sim * z->r_max + replica, buf, n);
 }
 
 // ---- trait shims -------------------------------------------------------------

@@ -26,7 +26,26 @@ struct TemperRec {
   double tscale; // Replica::translation_scale: 1.0 from the constructor (tempering.rs:88), a serialised field otherwise
 };
 
+// one replica slot of a `replicas` simulation (replicas.cuh; `Replica`, src/mc/energy_replicas.rs:103-145, minus system and generator)
+struct ReplicaRec {
+  double max_energy, cutoff, lowest_max, tscale;
+  unsigned long long rejected, accepted, above_count, below_count, upwelling, unique_visitors;
+  double above_total, below_total, above_sq, below_sq;
+  double xtot; // above_extra of the system's one data_to_collect key: total, count
+  unsigned long long xcnt;
+  int collecting, pad;
+};
+// one simulation (`MC`, energy_replicas.rs:307-333, minus the replicas)
+struct ReplicaSim {
+  unsigned long long s0, s1; // MC::rng
+  unsigned long long moves, indep;
+  double min_T;
+  int n_rep, median_len, overflow, pad;
+};
+
 typedef void (*temper_fn)(const DevParams, TemperRec*, unsigned long long);
+typedef void (*replica_init_fn)(const DevParams, unsigned long long, uint32_t, uint32_t, double*, uint32_t, unsigned long long*);
+typedef void (*replica_move_fn)(const DevParams, ReplicaRec*, const ReplicaSim*, uint32_t, unsigned long long, double*);
 typedef void (*move_fn)(const DevParams, unsigned long long, unsigned long long);
 typedef void (*init_fn)(const DevParams, unsigned long long, int, long long, int, double, unsigned long long);
 typedef void (*shim_fn)(const DevParams, uint32_t, int, double, ShimOut*, double*);
@@ -36,6 +55,8 @@ struct KernelSet {
   move_fn move_binning[6]; // SADMC_FLAG_BINNING: energy_binning.rs bookkeeping (book_binning.cuh); null where not built
   move_fn move_linear[6];  // ... | SADMC_FLAG_BINNING_LINEAR: the same over binning::linear (book_linear.cuh)
   temper_fn temper; // Replica::run_once x steps (tempering.cuh); null where not built
+  replica_init_fn replica_init; // energy_replicas.rs (replicas.cuh); null where not built
+  replica_move_fn replica_move;
   init_fn init;
   shim_fn shim;
   int G, block;

@@ -4,6 +4,7 @@
 #include "book_binning.cuh"
 #include "book_linear.cuh"
 #include "move_kernel.cuh"
+#include "replicas.cuh"
 #include "tempering.cuh"
 
 namespace sadmc {
@@ -25,6 +26,8 @@ static KernelSet make_set(const DevParams& P) {
     k.move_binning[SADMC_METHOD_WL] = move_kernel_binning<Sys, SADMC_METHOD_WL>;
     k.move_binning[SADMC_METHOD_INV_T_WL] = move_kernel_binning<Sys, SADMC_METHOD_WL>;
     k.temper = temper_move_kernel<Sys>;
+    k.replica_init = replica_init_kernel<Sys>;
+    k.replica_move = replica_move_kernel<Sys>;
     if constexpr (Sys::G == 1) {
       k.move_linear[SADMC_METHOD_SAD] = move_kernel_linear<Sys, SADMC_METHOD_SAD>;
       k.move_linear[SADMC_METHOD_SAMC] = move_kernel_linear<Sys, SADMC_METHOD_SAMC>;

@@ -5,7 +5,7 @@ import subprocess
 
 import numpy as np
 
-from sad_monte_carlo_b200._abi import BinningState, Config, ReplicaState, WalkerState
+from sad_monte_carlo_b200._abi import BinningState, Config, ReplicaState, WalkerState, ZenoReplicaState
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _LIB = None
@@ -62,6 +62,21 @@ def load_oracle():
     L.oracle_bench.restype = C.c_double
     L.oracle_bench.argtypes = [C.POINTER(Config), C.c_uint32, C.c_uint64, C.c_uint64]
     L.oracle_set_math_mode.argtypes = [C.c_int]
+    L.oracle_replicas_create.restype = C.c_void_p
+    L.oracle_replicas_create.argtypes = [C.POINTER(Config), C.c_uint32, C.c_double, C.c_uint64, C.c_uint32, C.c_uint64]
+    L.oracle_replicas_destroy.argtypes = [C.c_void_p]
+    L.oracle_replicas_run.argtypes = [C.c_void_p, C.c_uint64]
+    L.oracle_replicas_num_moves.restype = C.c_uint64
+    L.oracle_replicas_num_moves.argtypes = [C.c_void_p]
+    L.oracle_replicas_num_replicas.restype = C.c_uint32
+    L.oracle_replicas_num_replicas.argtypes = [C.c_void_p]
+    L.oracle_replicas_get_rng.argtypes = [C.c_void_p, u64p]
+    L.oracle_replicas_get_median.restype = C.c_uint32
+    L.oracle_replicas_get_median.argtypes = [C.c_void_p, C.c_uint32, f64p]
+    L.oracle_replicas_get_replicas.argtypes = [C.c_void_p, C.POINTER(ZenoReplicaState)]
+    L.oracle_replicas_system_len.restype = C.c_size_t
+    L.oracle_replicas_system_len.argtypes = [C.c_void_p]
+    L.oracle_replicas_get_system.argtypes = [C.c_void_p, C.c_uint32, f64p, C.c_size_t]
     L.oracle_tempering_create.restype = C.c_void_p
     L.oracle_tempering_create.argtypes = [C.POINTER(Config), C.c_uint32, f64p, C.c_uint32, C.c_uint64, f64p, C.c_size_t, C.c_uint64]
     L.oracle_tempering_destroy.argtypes = [C.c_void_p]
@@ -314,4 +329,56 @@ class OracleTempering:
         n = self.L.oracle_tempering_system_len(self.h)
         buf = np.zeros(n)
         assert self.L.oracle_tempering_get_system(self.h, replica, _ptr(buf, f64p), n) == 0
+        return buf
+
+
+class OracleReplicas:
+    """One reference `replicas` process: `MC<Any>` of src/mc/energy_replicas.rs, restated on the CPU."""
+
+    def __init__(self, cfg, min_T=0.2, independent_systems_before_new_bin=64, sim=0, max_init=0, attempts_override=0):
+        self.L = load_oracle()
+        self.h = self.L.oracle_replicas_create(C.byref(cfg), sim, float(min_T), int(independent_systems_before_new_bin), int(max_init), attempts_override)
+        if not self.h:
+            raise RuntimeError("oracle_replicas_create: " + self.L.oracle_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.oracle_replicas_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_once(self, n_rounds=1):
+        if self.L.oracle_replicas_run(self.h, int(n_rounds)) != 0:
+            raise RuntimeError("oracle_replicas_run: " + self.L.oracle_last_error().decode())
+
+    def moves(self):
+        return self.L.oracle_replicas_num_moves(self.h)
+
+    def num_replicas(self):
+        return self.L.oracle_replicas_num_replicas(self.h)
+
+    def rng(self):
+        s = np.zeros(2, np.uint64)
+        self.L.oracle_replicas_get_rng(self.h, _ptr(s, u64p))
+        return int(s[0]), int(s[1])
+
+    def median(self):
+        e = np.zeros(4096)
+        n = self.L.oracle_replicas_get_median(self.h, 4096, _ptr(e, f64p))
+        return e[:n].copy()
+
+    def replicas(self):
+        out = (ZenoReplicaState * self.num_replicas())()
+        self.L.oracle_replicas_get_replicas(self.h, out)
+        return list(out)
+
+    def system(self, replica):
+        n = self.L.oracle_replicas_system_len(self.h)
+        buf = np.zeros(n)
+        assert self.L.oracle_replicas_get_system(self.h, replica, _ptr(buf, f64p), n) == 0
         return buf

@@ -32,6 +32,7 @@ def test_struct_sizes_match_the_compiled_library(gpu_lib):
     assert gpu_lib.sadmc_sizeof_walker_state() == C.sizeof(_abi.WalkerState)
     assert gpu_lib.sadmc_sizeof_binning_state() == C.sizeof(_abi.BinningState)
     assert gpu_lib.sadmc_sizeof_replica_state() == C.sizeof(_abi.ReplicaState)
+    assert gpu_lib.sadmc_sizeof_zeno_replica_state() == C.sizeof(_abi.ZenoReplicaState)
     assert gpu_lib.sadmc_abi_version() == _abi.ABI_VERSION
 
 
