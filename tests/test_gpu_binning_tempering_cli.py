@@ -5,8 +5,8 @@ import os
 import numpy as np
 import pytest
 
-from sad_monte_carlo_b200 import _abi, binning, checkpoint, make_config, tempering
-from tests.oracle_lib import OracleBinningMC, OracleTempering
+from sad_monte_carlo_b200 import _abi, binning, checkpoint, make_config, replicas, tempering
+from tests.oracle_lib import OracleBinningMC, OracleReplicas, OracleTempering
 
 pytestmark = pytest.mark.gpu
 
@@ -117,3 +117,19 @@ def test_tempering_resume_continues_bit_for_bit(tmp_path):
         b = checkpoint.load(str(tmp_path / ("b-w%06d.json" % k)))
         a.pop("save_as"), b.pop("save_as")
         assert a == b
+
+
+def test_replicas_run_writes_one_document_per_simulation(tmp_path):
+    args = "--fake-quadratic-dimensions 3 --min-T 0.001 --independent-systems-before-new-bin 16 --seed 2 --num-walkers 2 --max-iter 300000 --quiet --save-as r.yaml".split()
+    _run(replicas, args, tmp_path)
+    doc = checkpoint.load(str(tmp_path / "r-w000001.yaml"))
+    assert set(doc) == {"min_T", "rng", "save_as", "moves", "independent_systems_before_new_bin", "median", "replicas", "save", "movie", "report"}
+    o = OracleReplicas(make_config("fake", fake_function=_abi.FAKE_QUADRATIC, N=3, seed=2), 0.001, 16, sim=1)
+    while o.moves() < doc["moves"]:
+        o.run_once(1)
+    assert o.moves() == doc["moves"] and (doc["rng"]["s0"], doc["rng"]["s1"]) == o.rng() and len(doc["replicas"]) == o.num_replicas() > 3
+    assert doc["median"]["energies"] == list(o.median())
+    for r, q in zip(doc["replicas"], o.replicas()):
+        assert (r["cutoff_energy"], r["above_count"], r["below_total"], r["unique_visitors"], r["translation_scale"]) == (
+            q.cutoff_energy, q.above_count, q.below_total, q.unique_visitors, q.translation_scale)
+    assert doc["replicas"][0]["max_energy"] == float("inf")

@@ -4,7 +4,7 @@ import json
 
 import pytest
 
-from sad_monte_carlo_b200 import _abi, binning, tempering
+from sad_monte_carlo_b200 import _abi, binning, replicas, tempering
 
 
 def _dry(mod, argv):
@@ -79,3 +79,13 @@ def test_tempering_default_ladder_and_refused_flags():
     assert d["T"][0] == 0.001 and d["T"][-1] == 1.024 and len(d["T"]) == 11 and d["canonical_steps"] == 1  # tempering.rs:31-35
     with pytest.raises(SystemExit):
         tempering.main("--fake-linear --sad-min-T 0.1 --dry-run".split(), out=lambda s: None)
+
+
+def test_replicas_job_script_line_of_run_fake():
+    # fake/run-fake.py:16-23: replicas <system> --movie-time 10^(1/4) --save-time 0.5 --save-as r-linear.yaml --max-iter 1e11 --min-T 0.001
+    d = _dry(replicas, "--fake-linear --movie-time 10^(1/4) --save-time 0.5 --save-as r-linear.yaml --max-iter 1e11 --min-T 0.001".split())
+    assert d["min_T"] == 0.001 and d["independent_systems_before_new_bin"] == 64 and d["save_as"] == "r-linear.yaml"
+    d = _dry(replicas, "--fake-erfinv-mean-energy 0 --fake-erfinv-N 3 --min-T 0.1 --independent-systems-before-new-bin 16".split())
+    assert d["min_T"] == 0.1 and d["independent_systems_before_new_bin"] == 16
+    with pytest.raises(SystemExit):
+        replicas.main("--fake-linear --sad-min-T 0.1 --dry-run".split(), out=lambda s: None)

@@ -70,6 +70,29 @@ def main():
         except Exception as ex:
             out = {"config": name, "error": str(ex)}
         print(json.dumps(out), flush=True)
+    # energy-ceiling replicas
+    from sad_monte_carlo_b200.replicas import ReplicasMC
+    for name, cfg, args, rounds in (
+        ("replicas fake quadratic d=3, 16384 simulations x up to 48 replicas, min_T 0.001", make_config("fake", fake_function=_abi.FAKE_QUADRATIC, N=3, n_walkers=16384, seed=0),
+         (0.001, 64, 48, 4096), 2000),
+        ("replicas LJ31 R=2.5 fast-math, 1184 simulations x up to 32 replicas, min_T 0.1", make_config("lj", N=31, lj_radius=2.5, n_walkers=1184, seed=0, lanes_per_walker=1, flags=FM),
+         (0.1, 16, 32, 1024), 500),
+    ):
+        try:
+            z = ReplicasMC(cfg, *args)
+            z.run_once(rounds)
+            m0 = sum(z.moves(k) for k in range(0, z.n_sim, max(1, z.n_sim // 64)))
+            z.run_once(rounds)
+            ms = z.last_run_ms()
+            sample = list(range(0, z.n_sim, max(1, z.n_sim // 64)))
+            m1 = sum(z.moves(k) for k in sample)
+            moves = (m1 - m0) / len(sample) * z.n_sim
+            out = {"config": name, "rounds_per_call": rounds, "ms_per_call": ms, "moves_per_s": moves / (ms * 1e-3), "launches_per_call": 2 * rounds,
+                   "replicas_per_simulation_now": float(np.mean([z.num_replicas(k) for k in sample]))}
+            z.close()
+        except Exception as ex:
+            out = {"config": name, "error": str(ex)}
+        print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":

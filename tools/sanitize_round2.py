@@ -57,3 +57,13 @@ for name, cfg, T in (
     print("%-36s simulations %d x %d replicas, moves %d, swaps tried by replica 0: %d" % (name, mc.n_sim, mc.n_T, mc.moves,
                                                                                        reps[0].accepted_swap_count + reps[0].rejected_swap_count), flush=True)
     mc.close()
+from sad_monte_carlo_b200.replicas import ReplicasMC  # noqa: E402
+for name, cfg, args in (
+    ("replicas fake quadratic", make_config("fake", fake_function=_abi.FAKE_QUADRATIC, N=3, n_walkers=5, seed=3), (0.001, 4, 24, 256)),
+    ("replicas ising", make_config("ising", N=8, n_walkers=3, seed=2), (2.0, 4, 64, 128)),
+    ("replicas wca (warp per walker)", make_config("wca", N=20, reduced_density=0.3, n_walkers=2, seed=4, lanes_per_walker=32), (0.5, 4, 16, 64)),
+):
+    z = ReplicasMC(cfg, *args)
+    z.run_once(300 if "wca" not in name else 60)
+    print("%-36s simulations %d, replicas of the last %d, moves %d" % (name, z.n_sim, z.num_replicas(z.n_sim - 1), z.moves(z.n_sim - 1)), flush=True)
+    z.close()
