@@ -1548,7 +1548,8 @@ int sadmc_tempering_create(const sadmc_config* cfg, const double* T, uint32_t n_
   c.min_allowed_energy = c.max_allowed_energy = NAN;
   c.bin_window_lo = 0.0;
   c.bin_window_hi = 1.0;
-  c.flags &= ~(uint32_t)SADMC_FLAG_BINNING;
+  c.flags &= ~(uint32_t)(SADMC_FLAG_BINNING | SADMC_FLAG_BINNING_LINEAR);
+  c.high_resolution_de = NAN;
   if (c.system == SADMC_SYS_LJ && c.lanes_per_walker == 0) c.lanes_per_walker = 1;
   if (c.system == SADMC_SYS_WCA && c.lanes_per_walker == 0) c.lanes_per_walker = 32;
   c.init_mode = SADMC_INIT_EXTERNAL;
