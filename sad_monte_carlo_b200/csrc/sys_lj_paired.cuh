@@ -22,9 +22,9 @@ namespace sadmc {
 __device__ __forceinline__ void named_barrier_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 template <int NT>
-struct LjPairedSys : LjThreadSys<true, NT, 1> {
+struct LjPairedSys : LjThreadSys<true, NT, 1, 128> {
   static_assert(NT > 1, "compile-time atom counts only");
-  typedef LjThreadSys<true, NT, 1> Base;
+  typedef LjThreadSys<true, NT, 1, 128> Base;
   static constexpr bool HELPERS = true;
   static constexpr int BLOCK = 256;     // threads per CTA at launch: 128 bookkeeping + 128 helpers
   static constexpr int MIN_BLOCKS = 2;

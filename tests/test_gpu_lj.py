@@ -239,3 +239,26 @@ def test_lj31_heat_capacity_short_run_approaches_the_reference_curve(lanes):
     assert len(T) >= 3
     assert np.abs(err).max() < 0.12
     assert (sem / cv).max() < 0.02
+
+
+@pytest.mark.parametrize("flags", [0, _abi.FLAG_FAST_MATH])
+def test_lj38_one_224_thread_cta_per_sm_tracks_the_oracle_across_cta_boundaries(flags):
+    """LJ38 runs one 224-thread CTA per SM (7 warps; two 128-thread CTAs do not fit shared memory): walkers at CTA and warp
+    boundaries, a partial last CTA, exact tier bit for bit and tolerance tier within 1e-12."""
+    walkers = 2 * 224 + 37
+    cfg = lj_cfg(N=38, R=3.0, lanes=1, n_walkers=walkers, flags=flags)
+    eng = WalkerEngine(cfg)
+    ocfg = lj_cfg(N=38, R=3.0, lanes=1, n_walkers=walkers)
+    ws = (0, 223, 224, 447, 448, walkers - 1)
+    eng.run(4000)
+    for w in ws:
+        o = OracleMC(ocfg, walker=w)
+        o.run(4000)
+        if flags == 0:
+            assert_walker_equal(eng, w, o, exact=True, context="LJ38 walker %d" % w)
+        else:
+            g, s = eng.walker(w), o.walker()
+            assert g.status == 0 and (g.rng_s0, g.rng_s1, g.accepted_moves) == (s.rng_s0, s.rng_s1, s.accepted_moves), w
+            assert abs(g.energy - s.energy) <= 1e-12 * abs(s.energy)
+            assert np.array_equal(eng.bins(w)["histogram"], o.bins()["histogram"])
+            assert abs(eng.compute_energy(w) - g.energy) <= 1e-11 * abs(g.energy)
