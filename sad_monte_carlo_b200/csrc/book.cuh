@@ -126,6 +126,7 @@ struct DevParams {
   double* sys;         // [n_walkers][sys_stride] f64 system image (LJ/WCA/SW/fake/two-wells)
   uint32_t* sys_words; // Ising: [n_walkers][ising_words] packed spins
   const double* zig;   // X[257] then F[257]
+  double* zstream;     // LJ move kernels with the z coordinates streamed from L2 (sys_lj_thread.cuh, ZG): 32 doubles per thread, else null
   unsigned int* halted; // [0] walkers that left the bin window, [1] walkers whose verify_energy failed (since creation)
   unsigned long long* hr_count; // [n_walkers][hr_cap] counts of the high-resolution histogram, null when there is none
   double hr_width;

@@ -559,6 +559,12 @@ int sadmc_create(const sadmc_config* cfg, sadmc_engine** out) {
   if (P.hr_cap) BAIL(dev_alloc(e, (void**)&P.hr_count, (size_t)P.n_walkers * P.hr_cap * 8, true));
   BAIL(dev_alloc(e, (void**)&P.walkers, (size_t)P.n_walkers * sizeof(WalkerRec), true));
   BAIL(dev_alloc(e, (void**)&P.sys, (size_t)P.n_walkers * (P.sys_stride ? P.sys_stride : 1) * 8, true));
+  if (e->ks.zstream_per_thread) { // scratch of the move kernels that stream part of the configuration from L2: laid out by thread
+    const size_t blk = e->ks.move_block ? e->ks.move_block : e->ks.block;
+    const size_t tpw = e->ks.move_block ? e->ks.move_threads_per_walker : e->ks.G;
+    const size_t threads = ((size_t)P.n_walkers * tpw + blk - 1) / blk * blk;
+    BAIL(dev_alloc(e, (void**)&P.zstream, threads * e->ks.zstream_per_thread * 8, true));
+  }
   BAIL(dev_alloc(e, (void**)&P.sys_words, (size_t)P.n_walkers * (P.ising_words ? P.ising_words : 1) * 4, true));
   BAIL(dev_alloc(e, (void**)&e->d_zig, 2 * SADMC_ZIG_TABLE_LEN * 8, false));
   BAIL(dev_alloc(e, (void**)&e->d_shim, sizeof(ShimOut), true));

@@ -64,6 +64,7 @@ struct KernelSet {
   // when the move kernels are launched differently from init / shim (helper warps): 0 = as above
   int move_block, move_threads_per_walker;
   size_t move_smem;
+  int zstream_per_thread; // doubles of DevParams::zstream per move-kernel thread (0: none)
 };
 
 // factories, one per translation unit; the bool ones return false when no instance was built

@@ -4,8 +4,29 @@
 namespace sadmc {
 bool kernels_lj_thread_fast(int N, int G, const DevParams& P, KernelSet* out) {
   if (N > 64 || G != 1) return false;
-  if (N == 31)
+#ifdef SADMC_EXP_NT /* occupancy probe (tools/exp_build.sh): a compile-time atom count other than 31 / 38 */
+  if (N == SADMC_EXP_NT) {
+    *out = make_set<LjThreadSys<true, SADMC_EXP_NT, 1>, true>(P);
+    return true;
+  }
+#endif
+  if (N == 31) {
     *out = make_set<LjThreadSys<true, 31, 1>, true>(P);
+#ifndef SADMC_LJ31_SMEM_Z /* (defined: the all-shared-memory move kernels, 2 CTAs per SM -- the A/B partner) */
+    // histogram-method move kernels: z streamed from L2, three CTAs per SM (sys_lj_thread.cuh, ZG); init, shims, binning,
+    // tempering and replicas keep the shared-memory layout
+    typedef LjThreadSys<true, 31, 1, 0, true> S;
+    out->move[SADMC_METHOD_SAD] = move_kernel<S, SADMC_METHOD_SAD>;
+    out->move[SADMC_METHOD_SAMC] = move_kernel<S, SADMC_METHOD_SAMC>;
+    out->move[SADMC_METHOD_WL] = move_kernel<S, SADMC_METHOD_WL>;
+    out->move[SADMC_METHOD_INV_T_WL] = move_kernel<S, SADMC_METHOD_WL>;
+    out->move[SADMC_METHOD_CANONICAL] = move_kernel<S, SADMC_METHOD_CANONICAL>;
+    out->move_block = S::BLOCK;
+    out->move_threads_per_walker = 1;
+    out->move_smem = zig_smem_bytes<S>() + S::smem_bytes(P, S::BLOCK);
+    out->zstream_per_thread = S::ZSTREAM_PER_WALKER;
+#endif
+  }
   else if (N == 38)
     *out = make_set<LjThreadSys<true, 38, 1>, true>(P);
   else
