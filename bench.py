@@ -291,7 +291,7 @@ def run_ours(args):
                          "per_unit": "900 FP64 flop per move (30 per pair x 30 pairs), divide = 1 flop; "
                                      "`achieved` = 900 x moves per launch / average launch duration",
                          "peak_source": "DFMA microkernel in this library, measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                         "kernel": "move_kernel<LjThreadSys<%s, 31, %d>, SAD>" % ("exact" if args.exact else "fast", args.lanes), "ms_per_launch": ms_max / args.steps},
+                         "kernel": "move_kernel<LjThreadSys<%s, 31, %d%s>, SAD>" % ("exact" if args.exact else "fast", args.lanes, ", z streamed from L2" if eng.streams_z() else ""), "ms_per_launch": ms_max / args.steps},
             "roofline_hbm": {"bound": "hbm", "achieved": per_gpu_moves_s * BYTES_PER_MOVE / 1e9, "peak": peaks.get("hbm_gbs"),
                              "unit": "GB/s", "frac": per_gpu_moves_s * BYTES_PER_MOVE / 1e9 / peaks.get("hbm_gbs"),
                              "traffic": traffic["dram_bytes_per_move"] * W * args.moves_per_step if traffic else None,
@@ -323,7 +323,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--walkers", type=int, default=int(os.environ.get("SADMC_BENCH_WALKERS", 0)),
-                    help="walkers per GPU (default: whole waves of resident CTAs: 75 776 = two waves at one lane per walker, 85 248 = three at two)")
+                    help="walkers per GPU (default: whole waves of resident CTAs: 56 832 = 148 SMs x 3 CTAs x 128 walkers, one lane per walker with z streamed from L2; 75 776 = two waves of 2 CTAs for --exact; 85 248 at two lanes)")
     ap.add_argument("--moves-per-step", type=int, default=int(os.environ.get("SADMC_BENCH_MOVES", 0)),
                     help="moves per walker and launch (default: so that the K timed steps cover 1e7 moves of every walker)")
     ap.add_argument("--burn-in", type=int, default=int(os.environ.get("SADMC_BENCH_BURN_IN", 1000000)),
@@ -344,8 +344,9 @@ def main():
     if args.exact and args.lanes != 1:
         args.lanes = 1  # the reference's sequential pair sum cannot be split across lanes
     if args.walkers == 0:
-        # whole waves of resident CTAs: 148 SMs x 2 CTAs x 128 walkers x 2 waves (one lane per walker) / 148 x 3 x 64 x 3 (two lanes)
-        args.walkers = 85248 if args.lanes == 2 else 75776
+        # whole waves of resident CTAs: 148 SMs x 3 CTAs x 128 walkers (one lane per walker, z streamed from L2: the engine picks that
+        # layout for this count), 148 x 2 x 128 x 2 waves (--exact: all coordinates in shared memory), 148 x 3 x 64 x 3 (two lanes)
+        args.walkers = 85248 if args.lanes == 2 else (75776 if args.exact else 56832)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -115,6 +115,13 @@ typedef enum {
  * (lnw_max_count_f64 / hist_min_count_f64) and sadmc_get_binning_bins_f64.  A correctness path: every access goes to HBM
  * uncached (no job script of the reference uses --linear-bin). */
 #define SADMC_FLAG_BINNING_LINEAR 32u
+/* LJ31, SADMC_FLAG_FAST_MATH, one lane per walker: the histogram move kernels exist in two layouts with the same results
+ * bit for bit (tests/test_gpu_lj.py) -- all three coordinates in shared memory (two 128-thread CTAs per SM, 249 registers),
+ * or x and y in shared memory and z streamed from an L2-resident array through a cp.async ring (three CTAs per SM, 168
+ * registers; ~3 % faster when the walkers fill whole waves of 384 per SM).  By default the engine takes whichever needs
+ * less time for the walker count (waves of 384 against waves of 256 per SM); these flags force one. */
+#define SADMC_FLAG_LJ_SMEM_Z 64u
+#define SADMC_FLAG_LJ_STREAM_Z 128u
 
 typedef struct sadmc_config {
   uint32_t abi_version; /* = SADMC_ABI_VERSION */
@@ -268,6 +275,10 @@ int sadmc_num_halted(sadmc_engine* e, uint64_t* left_window, uint64_t* failed_ve
 int sadmc_last_run_ms(sadmc_engine* e, float* ms);
 /* How many kernels of this library have been launched by this engine. */
 int sadmc_launch_count(sadmc_engine* e, uint64_t* n);
+/* How the move kernel of this engine is launched: threads per CTA, threads per walker, dynamic shared memory per CTA, and
+ * the bytes of walker state streamed from L2 per walker (0 unless the LJ z stream is in use, see SADMC_FLAG_LJ_STREAM_Z).
+ * Any pointer may be null.  (GPU-side diagnostic: the reference has no counterpart.) */
+int sadmc_move_launch_shape(sadmc_engine* e, uint32_t* block, uint32_t* threads_per_walker, uint64_t* shared_bytes, uint32_t* stream_bytes_per_walker);
 
 /* ---- state out (what Report/Save/Movie and the parity tests read) ------ */
 int sadmc_num_moves(sadmc_engine* e, uint64_t* moves);                  /* MonteCarlo::num_moves, energy.rs:981 */

@@ -25,6 +25,8 @@ FLAG_SUM_TREE = 2
 FLAG_FAST_MATH = 4
 FLAG_BINNING = 16  # energy_binning.rs bookkeeping over binning::histogram (the `binning` binary)
 FLAG_BINNING_LINEAR = 32  # with FLAG_BINNING: binning::linear (interpolated ln w, f64 counts)
+FLAG_LJ_SMEM_Z = 64  # LJ31 fast tier: force all coordinates in shared memory (2 CTAs per SM) ...
+FLAG_LJ_STREAM_Z = 128  # ... or force z streamed from L2 (3 CTAs per SM); default: by walker count.  Same results bit for bit.
 FLAG_HELPER_WARPS = 8  # experiment: helper warps for the LJ pair loop (with FLAG_FAST_MATH, lanes_per_walker = 1)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WINDOW, ERR_UNSUPPORTED, ERR_VERIFY = 0, -1, -2, -3, -4, -5

@@ -23,6 +23,7 @@ PROTOTYPES = {
     "sadmc_sync": (C.c_int, [vp]),
     "sadmc_last_run_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "sadmc_launch_count": (C.c_int, [vp, u64p]),
+    "sadmc_move_launch_shape": (C.c_int, [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), u64p, C.POINTER(C.c_uint32)]),
     "sadmc_num_moves": (C.c_int, [vp, u64p]),
     "sadmc_num_accepted_moves": (C.c_int, [vp, u64p]),
     "sadmc_num_halted": (C.c_int, [vp, u64p, u64p]),

@@ -693,6 +693,15 @@ int sadmc_last_run_ms(sadmc_engine* e, float* ms) {
   CK(cudaEventElapsedTime(ms, e->ev0, e->ev1));
   return 0;
 }
+int sadmc_move_launch_shape(sadmc_engine* e, uint32_t* block, uint32_t* threads_per_walker, uint64_t* shared_bytes, uint32_t* stream_bytes_per_walker) {
+  if (!e) return fail(SADMC_ERR_INVALID, "null engine");
+  const bool own = e->ks.move_block != 0; // move kernels with their own launch shape
+  if (block) *block = (uint32_t)(own ? e->ks.move_block : e->ks.block);
+  if (threads_per_walker) *threads_per_walker = (uint32_t)(own ? e->ks.move_threads_per_walker : e->ks.G);
+  if (shared_bytes) *shared_bytes = own ? e->ks.move_smem : e->ks.smem;
+  if (stream_bytes_per_walker) *stream_bytes_per_walker = (uint32_t)e->ks.zstream_per_thread * 8u * (uint32_t)(own ? e->ks.move_threads_per_walker : e->ks.G);
+  return 0;
+}
 int sadmc_launch_count(sadmc_engine* e, uint64_t* n) {
   if (!e || !n) return fail(SADMC_ERR_INVALID, "null argument");
   *n = e->launches;

@@ -12,7 +12,17 @@ bool kernels_lj_thread_fast(int N, int G, const DevParams& P, KernelSet* out) {
 #endif
   if (N == 31) {
     *out = make_set<LjThreadSys<true, 31, 1>, true>(P);
-#ifndef SADMC_LJ31_SMEM_Z /* (defined: the all-shared-memory move kernels, 2 CTAs per SM -- the A/B partner) */
+#ifndef SADMC_LJ31_SMEM_Z /* (defined: only the all-shared-memory move kernels are built) */
+    // Which layout needs less time for this many walkers: a wave of 384 walkers per SM (stream) takes 1.457 x as long as
+    // a wave of 256 (shared memory) -- 9.05e9 against 8.79e9 moves/s with whole waves of either, profiles/r02_zg_ab.log.
+    bool stream = (P.flags & SADMC_FLAG_LJ_STREAM_Z) != 0;
+    if (!(P.flags & (SADMC_FLAG_LJ_STREAM_Z | SADMC_FLAG_LJ_SMEM_Z))) {
+      int dev = 0, sms = 148;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const long long w = P.n_walkers, zg_wave = 384ll * sms, sm_wave = 256ll * sms;
+      stream = (double)((w + zg_wave - 1) / zg_wave) * 1.457 < (double)((w + sm_wave - 1) / sm_wave);
+    }
+    if (stream) {
     // histogram-method move kernels: z streamed from L2, three CTAs per SM (sys_lj_thread.cuh, ZG); init, shims, binning,
     // tempering and replicas keep the shared-memory layout
     typedef LjThreadSys<true, 31, 1, 0, true> S;
@@ -25,6 +35,7 @@ bool kernels_lj_thread_fast(int N, int G, const DevParams& P, KernelSet* out) {
     out->move_threads_per_walker = 1;
     out->move_smem = zig_smem_bytes<S>() + S::smem_bytes(P, S::BLOCK);
     out->zstream_per_thread = S::ZSTREAM_PER_WALKER;
+    }
 #endif
   }
   else if (N == 38)

@@ -82,6 +82,16 @@ class WalkerEngine:
         self._check(self.L.sadmc_last_run_ms(self.h, C.byref(ms)))
         return ms.value
 
+    def move_launch_shape(self):
+        """(threads per CTA, threads per walker, shared bytes per CTA, bytes per walker streamed from L2) of the move kernel"""
+        b, t, z = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        sm = C.c_uint64()
+        self._check(self.L.sadmc_move_launch_shape(self.h, C.byref(b), C.byref(t), C.byref(sm), C.byref(z)))
+        return b.value, t.value, sm.value, z.value
+
+    def streams_z(self):
+        return self.move_launch_shape()[3] != 0
+
     def launch_count(self):
         n = C.c_uint64()
         self._check(self.L.sadmc_launch_count(self.h, C.byref(n)))
