@@ -138,6 +138,7 @@ struct DevParams {
   double min_allowed, max_allowed;
   double min_T;
   int inv_t, has_min_gamma;
+  int method_kind; // sadmc_method_kind of the run (host-side kernel choice; the kernels are compiled per method)
   double min_gamma, canonical_T;
   int move_plan;
   double move_value;

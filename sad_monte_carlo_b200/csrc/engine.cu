@@ -150,6 +150,7 @@ static int setup_params(sadmc_engine* e) {
   P.max_allowed = c.max_allowed_energy;
   P.min_T = c.sad_min_T;
   P.inv_t = c.method == SADMC_METHOD_INV_T_WL;
+  P.method_kind = c.method;
   P.has_min_gamma = c.method == SADMC_METHOD_WL && !is_none(c.wl_min_gamma);
   P.min_gamma = c.wl_min_gamma;
   P.canonical_T = c.canonical_T;

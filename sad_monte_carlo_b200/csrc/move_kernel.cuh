@@ -248,8 +248,18 @@ __device__ __forceinline__ void bookkeep(Sys& sys, BookT& bk, unsigned long long
 #endif
 }
 
+// Systems whose register budget is that of a larger CTA than the one they launch declare LAUNCH_BOUND_THREADS.
+template <class S, class = void>
+struct LaunchBound {
+  static constexpr int threads = S::BLOCK;
+};
+template <class S>
+struct LaunchBound<S, decltype((void)S::LAUNCH_BOUND_THREADS)> {
+  static constexpr int threads = S::LAUNCH_BOUND_THREADS;
+};
+
 template <class Sys, int METHOD>
-__global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS) move_kernel(const DevParams P, unsigned long long moves0, unsigned long long n_moves) {
+__global__ void __launch_bounds__(LaunchBound<Sys>::threads, Sys::MIN_BLOCKS) move_kernel(const DevParams P, unsigned long long moves0, unsigned long long n_moves) {
   extern __shared__ __align__(16) unsigned char smem[];
   const double* zx = stage_zig<Sys>(P, smem);
   const double* zf = zx + SADMC_ZIG_TABLE_LEN;

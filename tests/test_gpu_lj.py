@@ -264,19 +264,24 @@ def test_lj38_one_224_thread_cta_per_sm_tracks_the_oracle_across_cta_boundaries(
             assert abs(eng.compute_energy(w) - g.energy) <= 1e-11 * abs(g.energy)
 
 
-@pytest.mark.parametrize("method,kw", [("sad", {}), ("wl", dict(min_allowed_energy=-110.0)), ("samc", dict(samc_t0=1e4)),
-                                       ("canonical", dict(canonical_T=0.3))])
-def test_lj31_z_streamed_from_l2_is_bit_identical_to_the_shared_memory_layout(method, kw):
-    """The LJ31 tolerance-tier move kernels keep x and y in shared memory and stream z from an L2-resident array through a
-    cp.async ring (three CTAs per SM, SADMC_FLAG_LJ_STREAM_Z) or keep all three in shared memory (SADMC_FLAG_LJ_SMEM_Z).  Same operations in the
-    same order: every configuration, energy, generator state and bin vector must agree bit for bit -- across CTA and warp
-    boundaries, a partial last CTA, several launches (the stream is rebuilt from the stored configurations at every launch),
-    and through the warp-cooperative energy re-summation (every ~300 accepted moves of a walker)."""
-    walkers = 3 * 128 + 45
-    a = WalkerEngine(lj_cfg(lanes=1, n_walkers=walkers, method=method, flags=_abi.FLAG_FAST_MATH | _abi.FLAG_LJ_STREAM_Z, **kw))
-    b = WalkerEngine(lj_cfg(lanes=1, n_walkers=walkers, method=method, flags=_abi.FLAG_FAST_MATH | _abi.FLAG_LJ_SMEM_Z, **kw))
-    assert a.move_launch_shape() == (128, 1, 4128 + 128 * 31 * 16 + 4 * 2048, 256)  # x, y + a two-stage ring per warp; 32 doubles streamed
-    assert b.move_launch_shape() == (128, 1, 4128 + 128 * 31 * 24, 0)
+@pytest.mark.parametrize("N,R,method,kw", [(31, 2.5, "sad", {}), (31, 2.5, "wl", dict(min_allowed_energy=-110.0)), (31, 2.5, "samc", dict(samc_t0=1e4)),
+                                           (31, 2.5, "canonical", dict(canonical_T=0.3)), (38, 3.0, "sad", {}),
+                                           (38, 3.0, "inv-t-wl", dict(min_allowed_energy=-150.0))])
+def test_lj_z_streamed_from_l2_is_bit_identical_to_the_shared_memory_layout(N, R, method, kw):
+    """The LJ31 / LJ38 tolerance-tier move kernels keep x and y in shared memory and stream z from an L2-resident array through a
+    cp.async ring (LJ31: three 128-thread CTAs per SM, LJ38: one of 320 threads; SADMC_FLAG_LJ_STREAM_Z) or keep all three in shared
+    memory (SADMC_FLAG_LJ_SMEM_Z).  Same operations in the same order: every configuration, energy, generator state and bin vector
+    must agree bit for bit -- across CTA and warp boundaries, a partial last CTA, several launches (the stream is rebuilt from the
+    stored configurations at every launch), and through the warp-cooperative energy re-summation (every ~10 N accepted moves of a
+    walker)."""
+    block = 128 if N == 31 else 320
+    walkers = 3 * block + 45
+    a = WalkerEngine(lj_cfg(N=N, R=R, lanes=1, n_walkers=walkers, method=method, flags=_abi.FLAG_FAST_MATH | _abi.FLAG_LJ_STREAM_Z, **kw))
+    b = WalkerEngine(lj_cfg(N=N, R=R, lanes=1, n_walkers=walkers, method=method, flags=_abi.FLAG_FAST_MATH | _abi.FLAG_LJ_SMEM_Z, **kw))
+    groups = (N + 3) // 4
+    # x, y + a two-stage ring per warp + the ziggurat tables; whole groups of four z values streamed
+    assert a.move_launch_shape() == (block, 1, 4128 + block * N * 16 + (block // 32) * 2048, groups * 32)
+    assert b.move_launch_shape() == (128 if N == 31 else 224, 1, 4128 + (128 if N == 31 else 224) * N * 24, 0)
     for n in (1, 999, 20000, 30000):
         a.run(n)
         b.run(n)
@@ -284,15 +289,15 @@ def test_lj31_z_streamed_from_l2_is_bit_identical_to_the_shared_memory_layout(me
         assert np.array_equal(a.systems(), b.systems()), "configurations differ after %d moves" % a.num_moves()
         assert np.array_equal(a.rngs(), b.rngs())
         assert np.array_equal(a.energies(), b.energies())
-        for w in (0, 31, 32, 127, 128, 383, 384, walkers - 1):
+        for w in (0, 31, 32, block - 1, block, 3 * block - 1, 3 * block, walkers - 1):
             ga, gb = a.walker(w), b.walker(w)
             assert (ga.energy, ga.accepted_moves, ga.rng_s0, ga.rng_s1) == (gb.energy, gb.accepted_moves, gb.rng_s0, gb.rng_s1), w
             ba, bb = a.bins(w), b.bins(w)
             for k in ba:
                 assert np.array_equal(ba[k], bb[k]), (w, k)
     # and the streamed layout against the reference-order oracle, in the tolerance tier
-    o = OracleMC(lj_cfg(lanes=1, n_walkers=walkers, method=method, **kw), walker=128)
+    o = OracleMC(lj_cfg(N=N, R=R, lanes=1, n_walkers=walkers, method=method, **kw), walker=block)
     o.run(a.num_moves())
-    g, s = a.walker(128), o.walker()
+    g, s = a.walker(block), o.walker()
     if (g.rng_s0, g.rng_s1, g.accepted_moves) == (s.rng_s0, s.rng_s1, s.accepted_moves):  # same accept decisions over 5e4 moves
         assert abs(g.energy - s.energy) <= 1e-11 * abs(s.energy)
