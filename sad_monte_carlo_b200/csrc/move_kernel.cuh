@@ -255,7 +255,7 @@ struct LaunchBound {
 };
 template <class S>
 struct LaunchBound<S, decltype((void)S::LAUNCH_BOUND_THREADS)> {
-  static constexpr int threads = S::LAUNCH_BOUND_THREADS;
+  static constexpr int threads = S::LAUNCH_BOUND_THREADS > S::BLOCK ? S::LAUNCH_BOUND_THREADS : S::BLOCK; // (a derived system may widen BLOCK)
 };
 
 template <class Sys, int METHOD>
