@@ -174,6 +174,7 @@ static const FlagSpec FLAGS[] = {
     {"save-as", PATH, "mc"}, {"num-threads", INT, "mc"}, {"resume-from", PATH, "mc"},                                       // mc/mod.rs:22-32
     {"num-walkers", INT, "gpu"}, {"gpu-device", INT, "gpu"}, {"bin-window-lo", F64, "gpu"}, {"bin-window-hi", F64, "gpu"},
     {"lanes-per-walker", INT, "gpu"}, {"fast-math", FLAG, "gpu"}, {"checkpoint-walkers", INT, "gpu"}, {"dry-run", FLAG, "gpu"},
+    {"lj-stream-z", FLAG, "gpu"}, {"lj-smem-z", FLAG, "gpu"}, // SADMC_FLAG_LJ_STREAM_Z / _SMEM_Z: force one LJ31 / LJ38 layout
     {"max-launch", INT, "gpu"}, {"help", FLAG, "gpu"}, {"convert", PATH, "gpu"}, {"convert-to", PATH, "gpu"},
 };
 
@@ -424,6 +425,8 @@ inline sadmc_config config_from_flags(const Flags& f) {
   c.seed = f.count("seed") ? f.at("seed").u : 0; // energy.rs:835: params.seed.unwrap_or(0)
   c.n_walkers = f.count("num-walkers") ? (uint32_t)f.at("num-walkers").u : 1;
   if (f.count("fast-math")) c.flags |= SADMC_FLAG_FAST_MATH;
+  if (f.count("lj-stream-z")) c.flags |= SADMC_FLAG_LJ_STREAM_Z;
+  if (f.count("lj-smem-z")) c.flags |= SADMC_FLAG_LJ_SMEM_Z;
   return c;
 }
 

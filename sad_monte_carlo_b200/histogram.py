@@ -15,7 +15,7 @@ energy.rs:899-902), `--resume-from FILE` continues a checkpoint as it is, the ru
 
 What is added for the GPU: `--num-walkers W` independent walkers (walker w is the reference run with `--seed
 seed+w`; with W > 1 every walker gets its own file `name-w000017.yaml`), `--gpu-device`, `--bin-window-lo/-hi`
-(the device keeps a fixed bin window per walker), `--lanes-per-walker`, `--fast-math` (LJ: tolerance tier, <= 1e-12
+(the device keeps a fixed bin window per walker), `--lanes-per-walker`, `--lj-stream-z` / `--lj-smem-z` (force one LJ31 / LJ38 kernel layout; same results), `--fast-math` (LJ: tolerance tier, <= 1e-12
 relative per move), `--checkpoint-walkers K` (write only the first K walkers: such a set is marked `name.partial` and
 cannot be resumed), `--dry-run` (print the parsed configuration as JSON and stop: needs no GPU).  `--num-threads` is
 accepted and ignored, as `EnergyMC` ignores rayon.  With W > 1 the per-run quantities of the reference are per-walker
@@ -185,7 +185,8 @@ MC_FLAGS = {"seed": INT, "energy-bin": F64, "min-allowed-energy": F64, "max-allo
             "movie-time": F64, "save-time": F64,                                                  # plugin.rs:411-415, 322-326
             "save-as": PATH, "num-threads": INT, "resume-from": PATH}                             # mc/mod.rs:22-32
 GPU_FLAGS = {"num-walkers": INT, "gpu-device": INT, "bin-window-lo": F64, "bin-window-hi": F64, "lanes-per-walker": INT,
-             "fast-math": FLAG, "checkpoint-walkers": INT, "dry-run": FLAG, "max-launch": INT, "help": FLAG}
+             "fast-math": FLAG, "lj-stream-z": FLAG, "lj-smem-z": FLAG,  # SADMC_FLAG_LJ_STREAM_Z / _SMEM_Z: force one LJ31 / LJ38 layout
+             "checkpoint-walkers": INT, "dry-run": FLAG, "max-launch": INT, "help": FLAG}
 
 ALL_FLAGS = {}
 for _t in list(SYSTEM_FLAGS.values()) + [METHOD_FLAGS, MC_FLAGS, GPU_FLAGS]:
@@ -343,6 +344,10 @@ def config_from_flags(flags):
     kw["n_walkers"] = flags.get("num-walkers", 1)
     if flags.get("fast-math"):
         kw["flags"] = _abi.FLAG_FAST_MATH
+    if flags.get("lj-stream-z"):
+        kw["flags"] = kw.get("flags", 0) | _abi.FLAG_LJ_STREAM_Z
+    if flags.get("lj-smem-z"):
+        kw["flags"] = kw.get("flags", 0) | _abi.FLAG_LJ_SMEM_Z
     return _abi.make_config(system, method, **kw)
 
 

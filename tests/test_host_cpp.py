@@ -33,6 +33,8 @@ COMMAND_LINES = [
     "--two-wells-N 12 --two-wells-h2-to-h1 1.1 --two-wells-barrier-over-h1 0.1 --two-wells-r2 1/2 --sad-min-T 0.001 --seed 7",
     "--ising-N 16 --T 2.5",
     "--ising-N 16 --sad-min-T sqrt(2)*pi --num-walkers 4096 --gpu-device 3 --bin-window-lo -600 --bin-window-hi 600 --fast-math --lanes-per-walker 1",
+    "--lj-N 31 --lj-radius 2.5 --max-allowed-energy=0 --sad-min-T 0.01 --energy-bin 0.01 --translation-scale 0.05 --num-walkers 56832 --fast-math --lj-stream-z",
+    "--lj-N 38 --lj-radius 3 --max-allowed-energy=0 --sad-min-T 0.01 --energy-bin 0.01 --num-walkers 300 --fast-math --lj-smem-z --lanes-per-walker 1",
 ]
 
 
