@@ -115,11 +115,11 @@ typedef enum {
  * (lnw_max_count_f64 / hist_min_count_f64) and sadmc_get_binning_bins_f64.  A correctness path: every access goes to HBM
  * uncached (no job script of the reference uses --linear-bin). */
 #define SADMC_FLAG_BINNING_LINEAR 32u
-/* LJ31, SADMC_FLAG_FAST_MATH, one lane per walker: the histogram move kernels exist in two layouts with the same results
+/* LJ31 and LJ38, SADMC_FLAG_FAST_MATH, one lane per walker: the histogram move kernels exist in two layouts with the same results
  * bit for bit (tests/test_gpu_lj.py) -- all three coordinates in shared memory (two 128-thread CTAs per SM, 249 registers),
  * or x and y in shared memory and z streamed from an L2-resident array through a cp.async ring (three CTAs per SM, 168
- * registers; ~3 % faster when the walkers fill whole waves of 384 per SM).  By default the engine takes whichever needs
- * less time for the walker count (waves of 384 against waves of 256 per SM); these flags force one. */
+ * registers; LJ31 ~4 % faster when the walkers fill whole waves of 384 per SM; LJ38: one 320-thread CTA instead of one of 224,
+ * 1/t-WL + 23 %).  By default the engine takes whichever needs less time for the walker count and method; these flags force one. */
 #define SADMC_FLAG_LJ_SMEM_Z 64u
 #define SADMC_FLAG_LJ_STREAM_Z 128u
 
