@@ -301,3 +301,28 @@ def test_lj_z_streamed_from_l2_is_bit_identical_to_the_shared_memory_layout(N, R
     g, s = a.walker(block), o.walker()
     if (g.rng_s0, g.rng_s1, g.accepted_moves) == (s.rng_s0, s.rng_s1, s.accepted_moves):  # same accept decisions over 5e4 moves
         assert abs(g.energy - s.energy) <= 1e-11 * abs(s.energy)
+
+
+def test_lj_layout_follows_the_walker_count_and_method():
+    """Without a forcing flag the engine takes the layout that needs less time for the walker count: waves of 384 (LJ31) / 320
+    (LJ38) walkers per SM with z streamed from L2 against waves of 256 / 224 with everything in shared memory, weighted by the
+    measured time of a wave (kernels_lj_thread_fast.cu).  Narrow bin windows: the engines are created, not run."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+
+    def picks_stream(N, R, method, walkers, **kw):
+        kw.setdefault("bin_window_lo", -2.0)
+        eng = WalkerEngine(lj_cfg(N=N, R=R, lanes=1, method=method, n_walkers=walkers, flags=_abi.FLAG_FAST_MATH,
+                                  init_mode=_abi.INIT_EXTERNAL, bin_window_hi=0.6, **kw))
+        z = eng.streams_z()
+        eng.close()
+        return z
+
+    assert picks_stream(31, 2.5, "sad", 384 * sms)            # bench.py's count: one wave of three CTAs
+    assert picks_stream(31, 2.5, "sad", 2 * 384 * sms)        # 2 x 1.44 < 3
+    assert not picks_stream(31, 2.5, "sad", 2 * 256 * sms)    # two waves either way: shared memory
+    assert not picks_stream(31, 2.5, "sad", 4096)             # a partial wave either way
+    assert picks_stream(38, 3.0, "inv-t-wl", 320 * sms, min_allowed_energy=-150.0, energy_bin=0.5, bin_window_lo=-151.0)  # 1.16 < 2
+    assert not picks_stream(38, 3.0, "sad", 224 * sms)        # 1.40 > 1
+    assert picks_stream(38, 3.0, "sad", 2 * 320 * sms)        # 2.8 < 3
+    assert not picks_stream(13, 2.0, "sad", 384 * sms)        # other sizes have one layout
