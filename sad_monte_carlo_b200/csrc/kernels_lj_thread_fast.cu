@@ -31,12 +31,13 @@ bool kernels_lj_thread_fast(int N, int G, const DevParams& P, KernelSet* out) {
     // Histogram-method move kernels with z streamed from L2 (sys_lj_thread.cuh, ZG): LJ31 three 128-thread CTAs per SM instead of
     // two, LJ38 one 320-thread CTA instead of one of 224.  Init, shims, binning, tempering and replicas keep the shared-memory
     // layout.  Which layout needs less time for this many walkers, from the rates measured with whole waves of either:
-    //   LJ31        a wave of 384 walkers per SM takes 1.44 x as long as a wave of 256 (9.16e9 / 8.79e9 moves/s, profiles/r02_zg_ab.log);
+    //   LJ31 SAD    a wave of 384 walkers per SM takes 1.44 x as long as a wave of 256 (9.16e9 / 8.79e9 moves/s, profiles/r02_zg_ab.log);
+    //   LJ31 WL     1.19 x (1/t-WL 5.52e9 / 4.39e9, profiles/r02_lj31_wl_zg.log);
     //   LJ38 WL     a wave of 320 takes 1.16 x as long as a wave of 224 (1/t-WL 4.05e9 / 3.30e9, profiles/r02_lj38_zg.log);
     //   LJ38 other  1.40 x (SAD 6.06e9 / 5.92e9).
     const long long zg_per_sm = N == 31 ? 384 : 320, sm_per_sm = N == 31 ? 256 : 224;
     const bool wl = P.method_kind == SADMC_METHOD_WL || P.method_kind == SADMC_METHOD_INV_T_WL;
-    const double wave_ratio = N == 31 ? 1.44 : (wl ? 1.16 : 1.40);
+    const double wave_ratio = N == 31 ? (wl ? 1.19 : 1.44) : (wl ? 1.16 : 1.40);
     bool stream = (P.flags & SADMC_FLAG_LJ_STREAM_Z) != 0;
     if (!(P.flags & (SADMC_FLAG_LJ_STREAM_Z | SADMC_FLAG_LJ_SMEM_Z))) {
       int dev = 0, sms = 148;
